@@ -1,0 +1,131 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference in the build container.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Needs /root/reference (absent on the GPU box — the fixtures are what travels).  The reference module
+is imported as-is with one harness-side shim (`collections.Iterable`, removed in Python 3.10, is used
+by /root/reference/CSNet/model/conv2d.py:15).  Nothing is copied from the reference: the fixtures hold
+(a) the shipped checkpoints' tensors re-serialised as .npz (the function to match is defined by them),
+(b) outputs of the reference forward on seeded synthetic inputs (sod100k_b200/synth.py).
+"""
+from __future__ import annotations
+
+import collections
+import collections.abc
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+collections.Iterable = collections.abc.Iterable          # harness-side shim, reference untouched
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/CSNet")
+
+import torch  # noqa: E402
+
+import model.csnet as ref  # noqa: E402  (the reference)
+from sod100k_b200 import synth  # noqa: E402
+
+CK = "/root/reference/CSNet/checkpoints"
+N_SAMPLE = 64
+
+
+def cfg_to_json(layer_config):
+    out = []
+    for entry in layer_config[:-1]:
+        out.append([np.asarray(e, np.float64).tolist() if not np.isscalar(e) else [float(e)] for e in entry])
+    return json.dumps(dict(blocks=out, stages=[int(s) for s in layer_config[-1]]))
+
+
+def build(layer_config=None, predefine=None, **kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        if predefine:
+            return ref.build_model(predefine=predefine)
+        return ref.build_model(**kw)
+
+
+def sample_idx(numel, seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, numel, N_SAMPLE)
+
+
+def run_case(model, x, taps_out=None):
+    """Reference forward in eval mode; optionally record per-ILBlock / head taps via forward hooks."""
+    hooks = []
+    if taps_out is not None:
+        for name, m in model.named_modules():
+            if isinstance(m, ref.ILBlock) or name in ("oct_fuse.fuse", "oct_fuse.ms", "oct_fuse.fuse1x1"):
+                def fn(mod, inp, out, name=name):
+                    for b, t in enumerate(out if isinstance(out, (list, tuple)) else [out]):
+                        if t is None:
+                            continue
+                        flat = t.detach().reshape(-1).numpy()
+                        idx = sample_idx(flat.size, 99)
+                        taps_out[f"{name}/{b}"] = np.concatenate(
+                            [[flat.mean(), flat.std(), np.abs(flat).max()], flat[idx]]).astype(np.float32)
+                hooks.append(m.register_forward_hook(fn))
+    with torch.no_grad():
+        y = model(torch.from_numpy(x))
+    for h in hooks:
+        h.remove()
+    return y.numpy()
+
+
+def main():
+    torch.manual_seed(0)
+    fwd = {}
+    meta = {}
+    for tag in ("csnet-L-x2", "csnet-L-x1"):
+        model = build(predefine=f"{CK}/{tag}/{tag}.bin")
+        ck = torch.load(f"{CK}/{tag}/{tag}.pth.tar", map_location="cpu", weights_only=False)
+        model.load_state_dict(ck["state_dict"])
+        model.eval()
+        arrays = {k: v.numpy() for k, v in ck["state_dict"].items()}
+        np.savez(os.path.join(HERE, f"{tag}.npz"), __layer_config__=np.array(cfg_to_json(model.layer_config)), **arrays)
+        # 224x224, N=2, noise + blobs (full logits)
+        x = synth.randn_images(2, 224, 224, 1234)
+        taps = {}
+        fwd[f"{tag}/randn224"] = run_case(model, x, taps if tag.endswith("x2") else None)
+        for k, v in taps.items():
+            fwd[f"{tag}/randn224/tap/{k}"] = v
+        xb, _ = synth.blob_images(2, 224, 224, 1235)
+        fwd[f"{tag}/blobs224"] = run_case(model, xb)
+        # non-square, N=1
+        fwd[f"{tag}/randn96x160"] = run_case(model, synth.randn_images(1, 96, 160, 1237))
+        # 512x512, N=1 (sampled)
+        y = run_case(model, synth.randn_images(1, 512, 512, 1238)).reshape(-1)
+        idx = np.random.default_rng(5).integers(0, y.size, 8192)
+        fwd[f"{tag}/randn512/sample"] = y[idx]
+        fwd[f"{tag}/randn512/stats"] = np.array([y.mean(), y.std(), y.min(), y.max()], np.float32)
+        meta[tag] = dict(params=int(sum(p.numel() for p in model.parameters())), n_state=len(arrays))
+
+    # un-pruned architectures with seeded synthetic weights (weights are regenerated from the seed by the tests)
+    for tag, kw, seed, hw in (("init-x2", dict(basic_split=[0.5, 0.5], expand=2.0), 7, (224, 224)),
+                              ("init-std", dict(basic_split=[1]), 8, (64, 64)),
+                              ("init-3br", dict(basic_split=[0.5, 0.25, 0.25]), 9, (128, 128))):
+        model = build(**kw)
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        sd = synth.synth_state(shapes, seed)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        model.eval()
+        taps = {}
+        fwd[f"{tag}/randn"] = run_case(model, synth.randn_images(1, hw[0], hw[1], 1240 + seed), taps)
+        for k, v in taps.items():
+            fwd[f"{tag}/randn/tap/{k}"] = v
+        meta[tag] = dict(layer_config=cfg_to_json(model.layer_config), seed=seed, hw=hw,
+                         shapes={k: list(v) for k, v in shapes.items()}, kw={k: (list(v) if isinstance(v, list) else v) for k, v in kw.items()})
+    meta["torch"] = torch.__version__
+    meta["numpy"] = np.__version__
+    meta["threads"] = torch.get_num_threads()
+    np.savez_compressed(os.path.join(HERE, "forward.npz"), __meta__=np.array(json.dumps(meta)), **fwd)
+    print("wrote", sorted(os.listdir(HERE)))
+
+
+if __name__ == "__main__":
+    main()

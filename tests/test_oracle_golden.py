@@ -1,0 +1,93 @@
+"""Pin the oracle (oracle/csnet_oracle.py) against outputs of the unmodified reference (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import csnet_oracle as O
+from sod100k_b200 import synth
+from tests import fixtures
+
+TOL = 2e-5   # same ATen calls in a different call order/graph; observed 0 .. 1e-6
+
+
+@pytest.mark.parametrize("tag", ["csnet-L-x2", "csnet-L-x1"])
+def test_checkpoint_forward_matches_reference(tag):
+    cfg, sd = fixtures.checkpoint(tag)
+    z, _ = fixtures.forward_golden()
+    with torch.no_grad():
+        y = O.csnet_forward(cfg, sd, torch.from_numpy(synth.randn_images(2, 224, 224, 1234))).numpy()
+        assert np.abs(y - z[f"{tag}/randn224"]).max() <= TOL
+        xb, _ = synth.blob_images(2, 224, 224, 1235)
+        y = O.csnet_forward(cfg, sd, torch.from_numpy(xb)).numpy()
+        assert np.abs(y - z[f"{tag}/blobs224"]).max() <= TOL
+        y = O.csnet_forward(cfg, sd, torch.from_numpy(synth.randn_images(1, 96, 160, 1237))).numpy()
+        assert np.abs(y - z[f"{tag}/randn96x160"]).max() <= TOL
+
+
+@pytest.mark.parametrize("tag", ["csnet-L-x2", "csnet-L-x1"])
+def test_checkpoint_forward_512_sampled(tag):
+    cfg, sd = fixtures.checkpoint(tag)
+    z, _ = fixtures.forward_golden()
+    with torch.no_grad():
+        y = O.csnet_forward(cfg, sd, torch.from_numpy(synth.randn_images(1, 512, 512, 1238))).numpy().reshape(-1)
+    idx = np.random.default_rng(5).integers(0, y.size, 8192)
+    assert np.abs(y[idx] - z[f"{tag}/randn512/sample"]).max() <= TOL
+    assert np.allclose([y.mean(), y.std(), y.min(), y.max()], z[f"{tag}/randn512/stats"], atol=1e-4)
+
+
+def _check_taps(z, prefix, taps):
+    n = 0
+    for key in z.files:
+        if not key.startswith(prefix + "/tap/"):
+            continue
+        name, b = key[len(prefix) + 5:].rsplit("/", 1)
+        t = taps[name]
+        t = t[int(b)] if isinstance(t, (list, tuple)) else t
+        flat = t.reshape(-1).numpy()
+        idx = np.random.default_rng(99).integers(0, flat.size, 64)
+        got = np.concatenate([[flat.mean(), flat.std(), np.abs(flat).max()], flat[idx]])
+        assert np.allclose(got, z[key], atol=1e-4, rtol=1e-5), key
+        n += 1
+    return n
+
+
+def test_per_block_taps_x2():
+    cfg, sd = fixtures.checkpoint("csnet-L-x2")
+    z, _ = fixtures.forward_golden()
+    taps = {}
+    with torch.no_grad():
+        O.csnet_forward(cfg, sd, torch.from_numpy(synth.randn_images(2, 224, 224, 1234)), taps=taps)
+    assert _check_taps(z, "csnet-L-x2/randn224", taps) >= 18 * 2 - 3
+
+
+@pytest.mark.parametrize("tag", ["init-x2", "init-std", "init-3br"])
+def test_unpruned_architectures(tag):
+    cfg, sd, m = fixtures.synthetic_model(tag)
+    z, _ = fixtures.forward_golden()
+    taps = {}
+    with torch.no_grad():
+        x = torch.from_numpy(synth.randn_images(1, m["hw"][0], m["hw"][1], 1240 + m["seed"]))
+        y = O.csnet_forward(cfg, sd, x, taps=taps).numpy()
+    assert np.abs(y - z[f"{tag}/randn"]).max() <= TOL * max(1.0, np.abs(y).max())
+    assert _check_taps(z, f"{tag}/randn", taps) > 0
+
+
+def test_state_shapes_and_init_config_match_reference_fixture():
+    _, meta = fixtures.forward_golden()
+    for tag in ("init-x2", "init-std", "init-3br"):
+        m = meta[tag]
+        cfg = fixtures.cfg_from_json(m["layer_config"])
+        shapes = O.state_shapes(cfg)
+        assert {k: list(v) for k, v in shapes.items()} == m["shapes"], tag
+        kw = m["kw"]
+        width = int(round(20 * kw.get("expand", 1.0))) if kw.get("expand", 1.0) > 1 else 20
+        mine = O.init_layer_config(width, kw["basic_split"])
+        assert mine[-1] == cfg[-1]
+        for a, b in zip(mine[:-1], cfg[:-1]):
+            assert len(a) == len(b)
+            for u, v in zip(a, b):
+                assert np.array_equal(np.asarray(u, np.float64), np.asarray(v, np.float64))
+    for tag in ("csnet-L-x2", "csnet-L-x1"):
+        cfg, sd = fixtures.checkpoint(tag)
+        assert {k: tuple(v.shape) for k, v in sd.items()} == O.state_shapes(cfg)
+        assert len(sd) == meta[tag]["n_state"]
