@@ -1,0 +1,167 @@
+/*
+ * csnet_b200.h — C ABI of libcsnet_b200.so, the B200 (sm_100a) CSNet forward/backward engine.
+ *
+ * The reference (ShangHua-Gao/SOD100K) has no FFI of its own: its hot path is Python calling
+ * torch.nn.functional (ATen/cuDNN).  This header is the boundary a maintainer would bind instead of
+ * those library calls; every entry point names the reference call site it replaces.  All arguments
+ * are plain pointers and sizes; device pointers are raw CUdeviceptr-compatible addresses; `stream`
+ * is a cudaStream_t passed as void*.  No torch types cross this boundary.
+ *
+ * Execution model: the host side (sod100k_b200/compiler.py, mirroring the reference's module tree
+ * CSNet/model/csnet.py) lowers a CSNet `layer_config` + `state_dict` into a flat PROGRAM: a tensor
+ * table, a list of fused ops and one fp32 parameter blob.  A plan owns the blob copy and the
+ * activation arena on one device and replays the program for a batch.
+ *
+ * Data layout in HBM: activations are planar NCHW (batch stride C*H*W, plane stride H*W, row
+ * stride W, all dense), element type per tensor (fp32 / fp16 / bf16).  Channel counts are never
+ * padded (CSNet widths are 8..79 and differ per layer), so algorithmic bytes == allocated bytes.
+ *
+ * Errors: every function returns 0 on success or a negative CSNET_E_* code; csnet_last_error()
+ * returns a thread-local message.  The reference's own convention is Python exceptions
+ * (CSNet/test.py:24 `assert`); the Python wrapper turns non-zero codes into RuntimeError.
+ * Threading: a plan is used by one host thread / one stream at a time; no global mutable state.
+ * Ownership: the caller owns inputs, outputs and parameters; the plan owns its blob copy + arena.
+ */
+#ifndef CSNET_B200_H
+#define CSNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSNET_ABI_VERSION 1
+
+enum { CSNET_F32 = 0, CSNET_F16 = 1, CSNET_BF16 = 2 };
+
+enum {
+  CSNET_OK = 0,
+  CSNET_E_INVALID = -1,   /* malformed program / argument */
+  CSNET_E_CUDA = -2,      /* CUDA runtime error (message holds cudaGetErrorString) */
+  CSNET_E_NOMEM = -3,
+  CSNET_E_UNSUPPORTED = -4
+};
+
+#define CSNET_MAX_PATHS 8
+
+/* One activation tensor of the program (per image: [C,H,W]; a run adds the batch dimension). */
+typedef struct {
+  int32_t C, H, W;
+  int32_t dtype;          /* CSNET_F32 / F16 / BF16 */
+  int32_t external;       /* >= 0: bound at run time to ext_ptrs[external]; -1: lives in the arena */
+  int32_t _pad;
+  int64_t arena_offset;   /* bytes PER IMAGE from the arena base (multiple of 256); the run address is
+                             base + N * arena_offset, so tensors of a smaller batch stay disjoint */
+} csnet_tensor_desc;
+
+/*
+ * One accumulation path of a MIX op.  out[cout0 : cout0+cout] += path(src[c0 : c0+cin]).
+ *
+ * ksize > 0 — convolution path, replaces the F.conv2d calls of gOctaveConv.forward
+ *   (CSNet/model/csnet.py:702-717), Conv2dX100.forward (CSNet/model/conv2d.py:104) and
+ *   MSBlock.forward (csnet.py:141-146), with the resampling the reference does around them folded
+ *   into the read: pre_avg=1 applies avg_pool2d(2,2) first (csnet.py:679-680), pool=k applies
+ *   max_pool2d(k,k) next (csnet.py:709-712); the convolution (cross-correlation, zero padding `pad`,
+ *   dilation `dil`, stride `stride`) then runs on that pooled grid.
+ * ksize == 0 — resample-add path: channel c of src is bilinearly up-sampled by the integer factor
+ *   `up` (align_corners=False, source index (dst+0.5)/up-0.5 clamped at 0 — F.interpolate at
+ *   csnet.py:705-707 and :382-385) and added to out[cout0+c]; cin == cout.
+ */
+typedef struct {
+  int32_t src;            /* tensor id */
+  int32_t c0, cin;
+  int32_t pre_avg, pool;
+  int32_t ksize, dil, stride, pad;
+  int32_t up;
+  int32_t cout0, cout;
+  int64_t w_off;          /* blob offset (floats) of weights laid out [cin][ksize*ksize][cout] (cout innermost,
+                             the compiler transposes the reference's [cout][cin][k][k]); -1 if ksize==0 */
+} csnet_path_desc;
+
+enum {
+  CSNET_OP_MIX = 1,       /* dst = prelu(sum_paths + bias)   — gOctaveCBR / MSBlock / cls_layer */
+  CSNET_OP_DW = 2         /* dst = prelu(dw3x3(src) + bias)  — SimplifiedGOctConvBR branch */
+};
+
+/*
+ * One fused op.  Epilogue (both kinds): y = acc + bias[c] (bias_off >= 0), then PReLU with
+ * per-channel slope (slope_off >= 0): y > 0 ? y : slope[c]*y  (F.batch_norm + F.prelu,
+ * csnet.py:786,791,846-847,148; eval-mode BN scale is folded into the weights by the compiler).
+ * CSNET_OP_DW uses paths[0] with ksize=3, dil=1, pad=1, cin==cout, weights [C][9]
+ * (Conv2dX100 groups=C, csnet.py:817-824).
+ */
+typedef struct {
+  int32_t kind;
+  int32_t dst;            /* tensor id */
+  int32_t n_paths;
+  int32_t _pad;
+  int64_t bias_off;       /* blob offset of bias[dst.C] or -1 */
+  int64_t slope_off;      /* blob offset of PReLU slope[dst.C] or -1 */
+  csnet_path_desc paths[CSNET_MAX_PATHS];
+} csnet_op_desc;
+
+typedef struct csnet_plan csnet_plan;
+
+/* ABI version of the loaded library (== CSNET_ABI_VERSION of the header it was built from). */
+int csnet_abi_version(void);
+
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* csnet_last_error(void);
+
+/* Number of CUDA devices visible; < 0 on error.  Used by the wrapper to fail loudly without a GPU. */
+int csnet_device_count(void);
+
+/*
+ * Build a plan on `device` for batches up to `max_batch`.  Validates the program (shapes of every
+ * path against its destination, blob bounds) and allocates blob + arena.
+ * Replaces: model construction + `.cuda()` (CSNet/test.py:39-40, CSNet_training/train.py:77-92).
+ */
+int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_t n_tensors,
+                      const csnet_op_desc* ops, int32_t n_ops, int64_t blob_floats,
+                      int32_t max_batch, int32_t device);
+
+/* Upload the fp32 parameter blob (host pointer, `n` floats == blob_floats) on `stream`.
+ * Replaces: load_state_dict + per-call `100.0 * weight` / BN arithmetic (conv2d.py:104, csnet.py:786). */
+int csnet_plan_set_blob(csnet_plan* plan, const float* host_blob, int64_t n, void* stream);
+
+/*
+ * Run the program for a batch of N images.  ext_ptrs[i] is the DEVICE address bound to tensors with
+ * external == i (network input fp32 NCHW, logits fp32 NCHW, ...).  Asynchronous on `stream`.
+ * Replaces: CSNet.forward (CSNet/model/csnet.py:365-387) == `model(input_var)` at CSNet/test.py:90.
+ */
+int csnet_plan_run(csnet_plan* plan, int32_t N, const void* const* ext_ptrs, int32_t n_ext, void* stream);
+
+/*
+ * Same as csnet_plan_run, but records a CUDA event on `stream` around every op and writes each op's device
+ * time in milliseconds to ms_per_op[n_ops] (synchronises the stream).  Measurement aid for bench.py's roofline.
+ */
+int csnet_plan_profile(csnet_plan* plan, int32_t N, const void* const* ext_ptrs, int32_t n_ext, void* stream,
+                       float* ms_per_op, int32_t n_ops);
+
+/* Device address of an arena tensor for a batch of N (for tests / taps); NULL if external/invalid. */
+void* csnet_plan_tensor_ptr(csnet_plan* plan, int32_t tensor, int32_t N);
+
+/* Copy an arena tensor of the last run of batch N into caller-owned DEVICE memory (same dtype, dense). */
+int csnet_plan_read_tensor(csnet_plan* plan, int32_t tensor, int32_t N, void* dst_device, void* stream);
+
+/* Number of kernel launches one csnet_plan_run issues (bench.py reports it as gpu_launches). */
+int32_t csnet_plan_launches(const csnet_plan* plan);
+
+/* Bytes of arena the plan holds. */
+int64_t csnet_plan_arena_bytes(const csnet_plan* plan);
+
+void csnet_plan_destroy(csnet_plan* plan);
+
+/*
+ * Convenience for hosts that keep their data in pageable/pinned HOST memory (the e2e path of
+ * bench.py and of CSNet/test.py:86-93): copies x (fp32 NCHW, N*3*H*W floats) to the device, runs,
+ * copies the logits (N*H*W floats) back, all on `stream`, and synchronises the stream.
+ * The plan must bind external 0 = input, external 1 = logits.
+ */
+int csnet_plan_run_host(csnet_plan* plan, int32_t N, const float* x_host, float* y_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSNET_B200_H */

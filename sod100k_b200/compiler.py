@@ -1,0 +1,214 @@
+"""Lower a CSNet (layer_config + parameters) to the engine's program IR.
+
+Host-side mirror of the reference's module tree: the walk below visits exactly the modules that
+`CSNet.__init__` builds (CSNet/model/csnet.py:209-311) and emits, for each reference module call, the
+fused op(s) that replace it:
+
+    gOctaveCBR   (csnet.py:729-792)  -> one MIX op per output branch (+ one raw low-res MIX per up path)
+    SimplifiedGOctConvBR (:795-851)  -> one DW op per branch
+    MSBlock      (:116-149)          -> one MIX op with a conv path per live dilation (concat = cout0 offsets)
+    cls_layer + F.interpolate (:381-385) -> MIX (1x1 + bias, at H/2) then MIX (resample x2, fp32 logits)
+
+Eval-mode folding done here, once per weight update, instead of per call in the reference:
+  * BatchNorm (running stats, eps 1e-5): y = s*x + t with s = gamma/sqrt(var+eps), t = beta - mean*s;
+    s is multiplied into the conv weights (bilinear resampling is linear with weights summing to 1 and
+    max/avg pooling happen before the conv, so s commutes with every path); t becomes the op bias.
+  * the `100.0 * weight` of Conv2dX100 (CSNet/model/conv2d.py:104) is multiplied into dw / dilated /
+    single-branch conv weights.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Mapping, Optional
+
+import numpy as np
+
+from . import ir, splits
+
+BN_EPS = 1e-5
+
+
+def _np(v) -> np.ndarray:
+    if hasattr(v, "detach"):
+        v = v.detach().cpu().numpy()
+    return np.asarray(v)
+
+
+class _Lowering:
+    def __init__(self, layer_config, params: Mapping[str, object], H: int, W: int, act_dtype: int):
+        if H % 16 or W % 16:
+            # the reference's own callers enforce this (CSNet/test.py:80-85); its branch sums fail otherwise
+            raise ValueError(f"input size {H}x{W} must be a multiple of 16")
+        self.cfg = layer_config
+        self.P = params
+        self.H, self.W = H, W
+        self.dt = act_dtype
+        self.b = ir.Builder()
+
+    # ---- parameters -----------------------------------------------------------------------------
+    def p(self, key: str) -> np.ndarray:
+        if key not in self.P:
+            raise KeyError(f"missing parameter '{key}' (state_dict does not match layer_config)")
+        return _np(self.P[key]).astype(np.float64)
+
+    def bn_fold(self, prefix: str):
+        s = self.p(prefix + ".weight") / np.sqrt(self.p(prefix + ".running_var") + BN_EPS)
+        t = self.p(prefix + ".bias") - self.p(prefix + ".running_mean") * s
+        return s, t
+
+    def conv_w(self, w: np.ndarray) -> int:
+        """[cout][cin][k][k] -> blob layout [cin][k*k][cout]."""
+        co, ci, kh, kw = w.shape
+        return self.b.param(np.transpose(w.reshape(co, ci, kh * kw), (1, 2, 0)))
+
+    def dims(self, t: int):
+        d = self.b.prog.tensors[t]
+        return d.C, d.H, d.W
+
+    # ---- modules --------------------------------------------------------------------------------
+    def goct_cbr(self, prefix: str, xs: List[Optional[int]], a_in, a_out, ksize: int, stride: int):
+        """gOctaveCBR.forward (csnet.py:778-792) incl. gOctaveConv.forward (:664-726)."""
+        W4 = self.p(prefix + ".conv.weight")
+        cout_t, cin_t = W4.shape[0], W4.shape[1]
+        pad = 1 if ksize == 3 else 0
+        if len(a_in) == 1 and len(a_out) == 1:                      # plain Conv2dX100 (csnet.py:751-754)
+            s, t = self.bn_fold(prefix + ".bns.0")
+            C_, H_, W_ = self.dims(xs[0])
+            Ho, Wo = (H_ + 2 * pad - ksize) // stride + 1, (W_ + 2 * pad - ksize) // stride + 1
+            dst = self.b.tensor(cout_t, Ho, Wo, self.dt, name=prefix + "/0")
+            path = ir.Path(xs[0], cin_t, cout_t, ksize=ksize, pad=pad, stride=stride,
+                           w_off=self.conv_w(100.0 * W4 * s[:, None, None, None]))
+            self.b.op(ir.OP_MIX, dst, [path], bias=t, slope=self.p(prefix + ".prelus.0.weight"), name=prefix)
+            return [dst]
+        ci, co = splits.cuts(cin_t, a_in), splits.cuts(cout_t, a_out)
+        base = None                                                   # resolution of branch 0 after the stride-2 pool
+        for i, x in enumerate(xs):
+            if x is not None:
+                _, H_, W_ = self.dims(x)
+                base = (H_ * 2 ** i // stride, W_ * 2 ** i // stride)
+                break
+        outs: List[Optional[int]] = []
+        for j in range(len(a_out)):
+            cj = co[j + 1] - co[j]
+            if cj == 0:
+                outs.append(None)
+                continue
+            Hj, Wj = base[0] // 2 ** j, base[1] // 2 ** j
+            s, t = self.bn_fold(f"{prefix}.bns.{j}")
+            paths = []
+            for i, x in enumerate(xs):
+                if x is None or ci[i] == ci[i + 1]:
+                    continue
+                cin = ci[i + 1] - ci[i]
+                w = W4[co[j]:co[j + 1], ci[i]:ci[i + 1]] * s[:, None, None, None]
+                common = dict(pre_avg=int(stride == 2), ksize=ksize, pad=pad, w_off=self.conv_w(w))
+                if i > j:                                            # conv at low res, then bilinear (:702-707)
+                    _, Hi, Wi = self.dims(x)
+                    low = self.b.tensor(cj, Hi // stride, Wi // stride, ir.F32, name=f"{prefix}/low{i}to{j}")
+                    self.b.op(ir.OP_MIX, low, [ir.Path(x, cin, cj, **common)], name=f"{prefix}.low{i}to{j}")
+                    paths.append(ir.Path(low, cj, cj, ksize=0, up=2 ** (i - j)))
+                else:                                                # same res, or max-pool first (:708-717)
+                    paths.append(ir.Path(x, cin, cj, pool=2 ** (j - i), **common))
+            if not paths:
+                outs.append(None)
+                continue
+            dst = self.b.tensor(cj, Hj, Wj, self.dt, name=f"{prefix}/{j}")
+            self.b.op(ir.OP_MIX, dst, paths, bias=t, slope=self.p(f"{prefix}.prelus.{j}.weight"), name=f"{prefix}.{j}")
+            outs.append(dst)
+        return outs
+
+    def dw_cbr(self, prefix: str, xs: List[Optional[int]]):
+        """SimplifiedGOctConvBR.forward (csnet.py:838-851)."""
+        outs = []
+        for b_, x in enumerate(xs):
+            if x is None:
+                outs.append(None)
+                continue
+            C_, H_, W_ = self.dims(x)
+            s, t = self.bn_fold(f"{prefix}.bns.{b_}")
+            w = 100.0 * self.p(f"{prefix}.convs.{b_}.weight").reshape(C_, 9) * s[:, None]
+            dst = self.b.tensor(C_, H_, W_, self.dt, name=f"{prefix}/{b_}")
+            path = ir.Path(x, C_, C_, ksize=3, pad=1, w_off=self.b.param(w))
+            self.b.op(ir.OP_DW, dst, [path], bias=t, slope=self.p(f"{prefix}.prelus.{b_}.weight"), name=f"{prefix}.{b_}")
+            outs.append(dst)
+        return outs
+
+    def il_block(self, prefix, xs, in_split, out_split, stride, first):
+        """ILBlock.forward (csnet.py:72-76)."""
+        a_in, a_out = splits.alphas(in_split), splits.alphas(out_split)
+        k = 3 if (first or stride == 2) else 1
+        y = self.goct_cbr(prefix + ".conv1x1", xs, a_in, a_out, k, stride)
+        y = self.dw_cbr(prefix + ".conv3x3_1", y)
+        y = self.dw_cbr(prefix + ".conv3x3_2", y)
+        for b_, t in enumerate(y):
+            if t is not None:
+                self.b.prog.taps[f"{prefix}/{b_}"] = t
+        return y
+
+    def ms_block(self, prefix: str, x: int, dil_channels):
+        """MSBlock.forward (csnet.py:141-149)."""
+        C_, H_, W_ = self.dims(x)
+        s, t = self.bn_fold(prefix + ".bn")
+        cout_t = int(s.shape[0])
+        dst = self.b.tensor(cout_t, H_, W_, self.dt, name=prefix)
+        paths, c = [], 0
+        for d, dil in enumerate(splits.DILATIONS):
+            n = int(dil_channels[d])
+            if n == 0:
+                continue
+            w = 100.0 * self.p(f"{prefix}.msconv.{d}.weight") * s[c:c + n, None, None, None]
+            paths.append(ir.Path(x, C_, n, cout0=c, ksize=3, dil=dil, pad=dil, w_off=self.conv_w(w)))
+            c += n
+        if c != cout_t:
+            raise ValueError(f"{prefix}: dilation split sums to {c}, BN has {cout_t} channels")
+        self.b.op(ir.OP_MIX, dst, paths, bias=t, slope=self.p(prefix + ".prelu.weight"), name=prefix)
+        return dst
+
+    def csf_head(self, prefix: str, xs, cfg3):
+        """CSFHead.forward (csnet.py:202-206), PallMSBlock.forward (:102-113)."""
+        a_in, a_mid_in, a_mid_out = splits.alphas(cfg3[0][0]), splits.alphas(cfg3[1][0]), splits.alphas(cfg3[1][1])
+        dils = np.asarray(cfg3[1][2])
+        y = self.goct_cbr(prefix + ".fuse", xs, a_in, a_mid_in, 1, 1)
+        z = []
+        for b_ in range(len(a_mid_in)):
+            z.append(self.ms_block(f"{prefix}.ms.convs.{b_}", y[b_], dils[b_]) if max(dils[b_]) != 0 else None)
+        out = self.goct_cbr(prefix + ".fuse1x1", z, a_mid_out, [1], 1, 1)
+        for name, ts in ((".fuse", y), (".ms", z), (".fuse1x1", out)):
+            for b_, t in enumerate(ts):
+                if t is not None:
+                    self.b.prog.taps[f"{prefix}{name}/{b_}"] = t
+        return out
+
+    def run(self, reuse: bool) -> ir.Program:
+        """CSNet.forward (csnet.py:365-387)."""
+        b = self.b
+        x = b.tensor(3, self.H, self.W, ir.F32, external=0, name="input")
+        walk, idx = splits.block_walk(self.cfg)
+        feats: Dict[str, List[Optional[int]]] = {}
+        cur: List[Optional[int]] = [x]
+        for prefix, ci, stride, first in walk:
+            in_split = np.array([3]) if first else self.cfg[ci][0]
+            cur = self.il_block(prefix, cur, in_split, self.cfg[ci][1], stride, first)
+            feats[prefix] = cur
+        stages = [int(s) for s in self.cfg[-1]]
+        ends = [f"stage{s + 1}.{stages[s] - 1}" for s in (1, 2, 3)]
+        fuse = self.csf_head("oct_fuse", [feats[e][0] for e in ends], self.cfg[idx:idx + 3])
+        C_, Hf, Wf = self.dims(fuse[0])
+        cls_w = self.p("cls_layer.weight")
+        low = b.tensor(cls_w.shape[0], Hf, Wf, ir.F32, name="cls/low")
+        b.op(ir.OP_MIX, low, [ir.Path(fuse[0], C_, cls_w.shape[0], ksize=1, w_off=self.conv_w(cls_w))],
+             bias=self.p("cls_layer.bias"), name="cls_layer")
+        if self.H % Hf or self.W % Wf or self.H // Hf != self.W // Wf:
+            raise ValueError("final resample factor is not an integer")
+        out = b.tensor(cls_w.shape[0], self.H, self.W, ir.F32, external=1, name="logits")
+        b.op(ir.OP_MIX, out, [ir.Path(low, cls_w.shape[0], cls_w.shape[0], ksize=0, up=self.H // Hf)], name="upsample")
+        prog = b.finish(reuse=reuse)
+        prog.input, prog.output = x, out
+        return prog
+
+
+def compile_csnet(layer_config, params: Mapping[str, object], H: int, W: int, dtype="fp32",
+                  reuse_arena: bool = True) -> ir.Program:
+    """layer_config: the reference's pickle structure (list of [in_split, out_split(, dil_split)] + stages);
+    params: state_dict-like mapping (torch tensors or numpy arrays); returns the eval-mode program."""
+    dt = ir.DTYPE_NAMES[dtype] if isinstance(dtype, str) else int(dtype)
+    return _Lowering(layer_config, params, H, W, dt).run(reuse_arena)

@@ -1,0 +1,383 @@
+// plan.cu — C ABI (include/csnet_b200.h) and the program executor of libcsnet_b200.so.
+//
+// A plan holds: the validated program, the device copy of the parameter blob, and one activation arena.
+// csnet_plan_run() walks the op list and launches one fused kernel per op on the caller's stream.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/csnet_b200.h"
+#include "generic_ops.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_CHECK(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(CSNET_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+size_t dtype_size(int dt) { return dt == CSNET_F32 ? 4 : 2; }
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) mix_generic_kernel(const __grid_constant__ csnet::MixArgs A) {
+  extern __shared__ float ws[];
+  const int co_base = blockIdx.y * csnet::kMixCT;
+  csnet::mix_stage_weights(A, co_base, ws, threadIdx.x, kThreads);
+  __syncthreads();
+  const int pix = blockIdx.x * kThreads + threadIdx.x;
+  if (pix >= A.H * A.W) return;
+  csnet::mix_thread(A, ws, blockIdx.z, pix / A.W, pix % A.W, co_base);
+}
+
+__global__ void __launch_bounds__(kThreads) dw_generic_kernel(const __grid_constant__ csnet::DwArgs A) {
+  const int item = blockIdx.x * kThreads + threadIdx.x;
+  const int strips = (A.H + csnet::kDwRows - 1) / csnet::kDwRows;
+  if (item >= strips * A.W) return;
+  csnet::dw_thread(A, blockIdx.z, blockIdx.y, (item / A.W) * csnet::kDwRows, item % A.W);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct csnet_plan {
+  int device = 0;
+  int max_batch = 0;
+  std::vector<csnet_tensor_desc> tensors;
+  std::vector<csnet_op_desc> ops;
+  int64_t blob_floats = 0;
+  float* blob = nullptr;
+  char* arena = nullptr;
+  int64_t arena_per_image = 0;   // bytes
+  int n_ext = 0;
+  size_t mix_smem_max = 0;
+  std::vector<size_t> op_smem;
+
+  void* tensor_ptr(int t, int N, const void* const* ext) const {
+    const csnet_tensor_desc& d = tensors[t];
+    if (d.external >= 0) return ext ? const_cast<void*>(ext[d.external]) : nullptr;
+    return arena + (int64_t)N * d.arena_offset;
+  }
+};
+
+namespace {
+
+int validate(const csnet_plan& P) {
+  const int nt = (int)P.tensors.size();
+  char buf[256];
+  for (int t = 0; t < nt; ++t) {
+    const csnet_tensor_desc& d = P.tensors[t];
+    if (d.C <= 0 || d.H <= 0 || d.W <= 0 || d.dtype < 0 || d.dtype > 2) {
+      snprintf(buf, sizeof buf, "tensor %d: bad dims/dtype", t);
+      return fail(CSNET_E_INVALID, buf);
+    }
+    if (d.external < 0 && (d.arena_offset < 0 || d.arena_offset % 256 != 0)) {
+      snprintf(buf, sizeof buf, "tensor %d: arena offset must be a non-negative multiple of 256", t);
+      return fail(CSNET_E_INVALID, buf);
+    }
+  }
+  for (size_t i = 0; i < P.ops.size(); ++i) {
+    const csnet_op_desc& op = P.ops[i];
+    auto bad = [&](const char* why) {
+      snprintf(buf, sizeof buf, "op %zu: %s", i, why);
+      return fail(CSNET_E_INVALID, buf);
+    };
+    if (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_DW) return bad("unknown kind");
+    if (op.dst < 0 || op.dst >= nt) return bad("dst out of range");
+    if (op.n_paths < 1 || op.n_paths > CSNET_MAX_PATHS) return bad("n_paths out of range");
+    const csnet_tensor_desc& D = P.tensors[op.dst];
+    if (op.bias_off >= 0 && op.bias_off + D.C > P.blob_floats) return bad("bias outside blob");
+    if (op.slope_off >= 0 && op.slope_off + D.C > P.blob_floats) return bad("slope outside blob");
+    if (op.kind == CSNET_OP_DW && op.n_paths != 1) return bad("DW takes one path");
+    for (int p = 0; p < op.n_paths; ++p) {
+      const csnet_path_desc& q = op.paths[p];
+      if (q.src < 0 || q.src >= nt) return bad("path src out of range");
+      if (q.src == op.dst) return bad("in-place op");
+      const csnet_tensor_desc& S = P.tensors[q.src];
+      if (q.c0 < 0 || q.cin <= 0 || q.c0 + q.cin > S.C) return bad("path input channel slice");
+      if (q.cout0 < 0 || q.cout <= 0 || q.cout0 + q.cout > D.C) return bad("path output channel slice");
+      if (op.kind == CSNET_OP_DW) {
+        if (q.ksize != 3 || q.dil != 1 || q.pad != 1 || q.stride != 1 || q.pre_avg || q.pool != 1 || q.up != 1)
+          return bad("DW must be 3x3 pad 1");
+        if (q.cin != D.C || q.cout != D.C || q.c0 != 0 || q.cout0 != 0 || S.C != D.C || S.H != D.H || S.W != D.W)
+          return bad("DW shape");
+        if (q.w_off < 0 || q.w_off + (int64_t)D.C * 9 > P.blob_floats) return bad("DW weights outside blob");
+        continue;
+      }
+      if (q.ksize == 0) {
+        if (q.up < 1 || q.cin != q.cout) return bad("resample path");
+        if (S.H * q.up != D.H || S.W * q.up != D.W) return bad("resample path size");
+      } else {
+        if (q.ksize != 1 && q.ksize != 3) return bad("ksize must be 1 or 3");
+        if (q.up != 1) return bad("conv path with up != 1 (lower it to conv + resample)");
+        if (q.pool < 1 || q.stride < 1 || q.dil < 1 || q.pad < 0) return bad("conv path params");
+        const int div = (q.pre_avg ? 2 : 1) * q.pool;
+        if (S.H % div || S.W % div) return bad("pooling does not divide the source");
+        const int Hc = S.H / div, Wc = S.W / div;
+        const int Ho = (Hc + 2 * q.pad - q.dil * (q.ksize - 1) - 1) / q.stride + 1;
+        const int Wo = (Wc + 2 * q.pad - q.dil * (q.ksize - 1) - 1) / q.stride + 1;
+        if (Ho != D.H || Wo != D.W) return bad("conv path output size != dst");
+        const int64_t nw = (int64_t)q.cout * q.cin * q.ksize * q.ksize;
+        if (q.w_off < 0 || q.w_off + nw > P.blob_floats) return bad("weights outside blob");
+      }
+    }
+  }
+  return CSNET_OK;
+}
+
+csnet::MixArgs make_mix(const csnet_plan& P, const csnet_op_desc& op, int N, const void* const* ext) {
+  csnet::MixArgs A{};
+  const csnet_tensor_desc& D = P.tensors[op.dst];
+  A.dst = P.tensor_ptr(op.dst, N, ext);
+  A.bias = op.bias_off >= 0 ? P.blob + op.bias_off : nullptr;
+  A.slope = op.slope_off >= 0 ? P.blob + op.slope_off : nullptr;
+  A.dtype = D.dtype; A.C = D.C; A.H = D.H; A.W = D.W;
+  A.n_paths = op.n_paths;
+  for (int p = 0; p < op.n_paths; ++p) {
+    const csnet_path_desc& q = op.paths[p];
+    const csnet_tensor_desc& S = P.tensors[q.src];
+    csnet::MixPath& m = A.p[p];
+    m.src = P.tensor_ptr(q.src, N, ext);
+    m.w = q.ksize > 0 ? P.blob + q.w_off : nullptr;
+    m.dtype = S.dtype; m.C = S.C; m.H = S.H; m.W = S.W;
+    m.c0 = q.c0; m.cin = q.cin; m.pre_avg = q.pre_avg; m.pool = q.pool;
+    m.ksize = q.ksize; m.dil = q.dil; m.stride = q.stride; m.pad = q.pad; m.up = q.up;
+    m.cout0 = q.cout0; m.cout = q.cout;
+  }
+  return A;
+}
+
+size_t mix_smem_bytes(const csnet::MixArgs& A) {
+  size_t mx = 0;
+  for (int co = 0; co < A.C; co += csnet::kMixCT) {
+    size_t f = 0;
+    for (int p = 0; p < A.n_paths; ++p) {
+      const csnet::MixPath& q = A.p[p];
+      if (q.ksize == 0) continue;
+      const int lo = co > q.cout0 ? co : q.cout0;
+      const int hi = (co + csnet::kMixCT) < (q.cout0 + q.cout) ? (co + csnet::kMixCT) : (q.cout0 + q.cout);
+      if (lo >= hi) continue;
+      f += (size_t)q.cin * q.ksize * q.ksize * csnet::kMixCT;
+    }
+    mx = f > mx ? f : mx;
+  }
+  return mx * sizeof(float);
+}
+
+}  // namespace
+
+extern "C" {
+
+int csnet_abi_version(void) { return CSNET_ABI_VERSION; }
+
+const char* csnet_last_error(void) { return g_err.c_str(); }
+
+int csnet_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(CSNET_E_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  return n;
+}
+
+int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_t n_tensors,
+                      const csnet_op_desc* ops, int32_t n_ops, int64_t blob_floats, int32_t max_batch,
+                      int32_t device) {
+  if (!out || !tensors || !ops || n_tensors <= 0 || n_ops <= 0 || blob_floats <= 0 || max_batch <= 0)
+    return fail(CSNET_E_INVALID, "csnet_plan_create: null/empty argument");
+  csnet_plan* P = new (std::nothrow) csnet_plan();
+  if (!P) return fail(CSNET_E_NOMEM, "host allocation failed");
+  P->device = device;
+  P->max_batch = max_batch;
+  P->tensors.assign(tensors, tensors + n_tensors);
+  P->ops.assign(ops, ops + n_ops);
+  P->blob_floats = blob_floats;
+  int rc = validate(*P);
+  if (rc != CSNET_OK) { delete P; return rc; }
+  for (const auto& d : P->tensors) {
+    if (d.external >= 0) { P->n_ext = d.external + 1 > P->n_ext ? d.external + 1 : P->n_ext; continue; }
+    const int64_t end = d.arena_offset + (int64_t)d.C * d.H * d.W * (int64_t)dtype_size(d.dtype);
+    P->arena_per_image = end > P->arena_per_image ? end : P->arena_per_image;
+  }
+  P->arena_per_image = (P->arena_per_image + 255) / 256 * 256;
+  auto cleanup = [&](int code, const std::string& m) { csnet_plan_destroy(P); return fail(code, m); };
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  e = cudaMalloc(&P->blob, (size_t)blob_floats * sizeof(float));
+  if (e != cudaSuccess) return cleanup(CSNET_E_NOMEM, std::string("cudaMalloc(blob): ") + cudaGetErrorString(e));
+  const size_t arena_bytes = (size_t)P->arena_per_image * (size_t)max_batch + 256;
+  e = cudaMalloc(&P->arena, arena_bytes);
+  if (e != cudaSuccess) return cleanup(CSNET_E_NOMEM, std::string("cudaMalloc(arena): ") + cudaGetErrorString(e));
+  // dynamic shared memory each MIX op needs (weights of one cout tile)
+  P->op_smem.assign(P->ops.size(), 0);
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    if (P->ops[i].kind != CSNET_OP_MIX) continue;
+    csnet::MixArgs A = make_mix(*P, P->ops[i], 1, nullptr);
+    P->op_smem[i] = mix_smem_bytes(A);
+    P->mix_smem_max = P->op_smem[i] > P->mix_smem_max ? P->op_smem[i] : P->mix_smem_max;
+  }
+  if (P->mix_smem_max > 227 * 1024) return cleanup(CSNET_E_UNSUPPORTED, "MIX op weights exceed shared memory");
+  if (P->mix_smem_max > 48 * 1024) {
+    e = cudaFuncSetAttribute(mix_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->mix_smem_max);
+    if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  }
+  *out = P;
+  return CSNET_OK;
+}
+
+int csnet_plan_set_blob(csnet_plan* P, const float* host_blob, int64_t n, void* stream) {
+  if (!P || !host_blob || n != P->blob_floats) return fail(CSNET_E_INVALID, "csnet_plan_set_blob: size mismatch");
+  CU_CHECK(cudaSetDevice(P->device));
+  CU_CHECK(cudaMemcpyAsync(P->blob, host_blob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return CSNET_OK;
+}
+
+static int check_run_args(csnet_plan* P, int32_t N, const void* const* ext_ptrs, int32_t n_ext) {
+  if (!P) return fail(CSNET_E_INVALID, "null plan");
+  if (N <= 0 || N > P->max_batch) return fail(CSNET_E_INVALID, "batch size outside [1, max_batch]");
+  if (n_ext < P->n_ext || (P->n_ext > 0 && !ext_ptrs)) return fail(CSNET_E_INVALID, "missing external tensor pointers");
+  for (int i = 0; i < P->n_ext; ++i)
+    if (!ext_ptrs[i]) return fail(CSNET_E_INVALID, "null external tensor pointer");
+  return CSNET_OK;
+}
+
+static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_ptrs, cudaStream_t stream) {
+  const csnet_op_desc& op = P->ops[i];
+  const csnet_tensor_desc& D = P->tensors[op.dst];
+  if (op.kind == CSNET_OP_MIX) {
+    csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
+    dim3 grid((D.H * D.W + kThreads - 1) / kThreads, (D.C + csnet::kMixCT - 1) / csnet::kMixCT, N);
+    mix_generic_kernel<<<grid, kThreads, P->op_smem[i], stream>>>(A);
+  } else {
+    const csnet_path_desc& q = op.paths[0];
+    const csnet_tensor_desc& S = P->tensors[q.src];
+    csnet::DwArgs A{};
+    A.src = P->tensor_ptr(q.src, N, ext_ptrs);
+    A.dst = P->tensor_ptr(op.dst, N, ext_ptrs);
+    A.w = P->blob + q.w_off;
+    A.bias = op.bias_off >= 0 ? P->blob + op.bias_off : nullptr;
+    A.slope = op.slope_off >= 0 ? P->blob + op.slope_off : nullptr;
+    A.src_dtype = S.dtype; A.dst_dtype = D.dtype; A.C = D.C; A.H = D.H; A.W = D.W;
+    const int strips = (D.H + csnet::kDwRows - 1) / csnet::kDwRows;
+    dim3 grid((strips * D.W + kThreads - 1) / kThreads, D.C, N);
+    dw_generic_kernel<<<grid, kThreads, 0, stream>>>(A);
+  }
+  CU_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_plan_run(csnet_plan* P, int32_t N, const void* const* ext_ptrs, int32_t n_ext, void* stream_) {
+  int rc = check_run_args(P, N, ext_ptrs, n_ext);
+  if (rc != CSNET_OK) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CU_CHECK(cudaSetDevice(P->device));
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    rc = launch_op(P, i, N, ext_ptrs, stream);
+    if (rc != CSNET_OK) return rc;
+  }
+  return CSNET_OK;
+}
+
+int csnet_plan_profile(csnet_plan* P, int32_t N, const void* const* ext_ptrs, int32_t n_ext, void* stream_,
+                       float* ms_per_op, int32_t n_ops) {
+  int rc = check_run_args(P, N, ext_ptrs, n_ext);
+  if (rc != CSNET_OK) return rc;
+  if (!ms_per_op || n_ops != (int32_t)P->ops.size()) return fail(CSNET_E_INVALID, "csnet_plan_profile: n_ops mismatch");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CU_CHECK(cudaSetDevice(P->device));
+  std::vector<cudaEvent_t> ev(P->ops.size() + 1);
+  for (auto& e : ev) CU_CHECK(cudaEventCreate(&e));
+  CU_CHECK(cudaEventRecord(ev[0], stream));
+  for (size_t i = 0; i < P->ops.size() && rc == CSNET_OK; ++i) {
+    rc = launch_op(P, i, N, ext_ptrs, stream);
+    if (rc == CSNET_OK && cudaEventRecord(ev[i + 1], stream) != cudaSuccess) rc = fail(CSNET_E_CUDA, "cudaEventRecord");
+  }
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (rc == CSNET_OK && e != cudaSuccess) rc = fail(CSNET_E_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+  if (rc == CSNET_OK)
+    for (size_t i = 0; i < P->ops.size(); ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+  for (auto& e2 : ev) cudaEventDestroy(e2);
+  return rc;
+}
+
+void* csnet_plan_tensor_ptr(csnet_plan* P, int32_t tensor, int32_t N) {
+  if (!P || tensor < 0 || tensor >= (int)P->tensors.size() || N <= 0 || N > P->max_batch) return nullptr;
+  if (P->tensors[tensor].external >= 0) return nullptr;
+  return P->tensor_ptr(tensor, N, nullptr);
+}
+
+int csnet_plan_read_tensor(csnet_plan* P, int32_t tensor, int32_t N, void* dst, void* stream) {
+  void* src = csnet_plan_tensor_ptr(P, tensor, N);
+  if (!src || !dst) return fail(CSNET_E_INVALID, "csnet_plan_read_tensor: bad tensor / batch / destination");
+  const csnet_tensor_desc& d = P->tensors[tensor];
+  CU_CHECK(cudaSetDevice(P->device));
+  CU_CHECK(cudaMemcpyAsync(dst, src, (size_t)N * d.C * d.H * d.W * dtype_size(d.dtype), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return CSNET_OK;
+}
+
+int32_t csnet_plan_launches(const csnet_plan* P) { return P ? (int32_t)P->ops.size() : 0; }
+
+int64_t csnet_plan_arena_bytes(const csnet_plan* P) { return P ? P->arena_per_image * (int64_t)P->max_batch : 0; }
+
+void csnet_plan_destroy(csnet_plan* P) {
+  if (!P) return;
+  if (P->blob || P->arena) cudaSetDevice(P->device);
+  if (P->blob) cudaFree(P->blob);
+  if (P->arena) cudaFree(P->arena);
+  delete P;
+}
+
+int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_host, void* stream_) {
+  if (!P || !x_host || !y_host) return fail(CSNET_E_INVALID, "null argument");
+  if (P->n_ext != 2) return fail(CSNET_E_INVALID, "run_host needs a plan with externals {0: input, 1: logits}");
+  const csnet_tensor_desc *in = nullptr, *lo = nullptr;
+  for (const auto& d : P->tensors) {
+    if (d.external == 0) in = &d;
+    if (d.external == 1) lo = &d;
+  }
+  if (!in || !lo || in->dtype != CSNET_F32 || lo->dtype != CSNET_F32)
+    return fail(CSNET_E_INVALID, "run_host: externals must be fp32");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CU_CHECK(cudaSetDevice(P->device));
+  const size_t xb = (size_t)N * in->C * in->H * in->W * sizeof(float);
+  const size_t yb = (size_t)N * lo->C * lo->H * lo->W * sizeof(float);
+  void *dx = nullptr, *dy = nullptr;
+  CU_CHECK(cudaMallocAsync(&dx, xb, stream));
+  CU_CHECK(cudaMallocAsync(&dy, yb, stream));
+  CU_CHECK(cudaMemcpyAsync(dx, x_host, xb, cudaMemcpyHostToDevice, stream));
+  const void* ext[2] = {dx, dy};
+  int rc = csnet_plan_run(P, N, ext, 2, stream_);
+  if (rc == CSNET_OK) {
+    cudaError_t e = cudaMemcpyAsync(y_host, dy, yb, cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) rc = fail(CSNET_E_CUDA, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(dx, stream);
+  cudaFreeAsync(dy, stream);
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (rc == CSNET_OK && e != cudaSuccess) rc = fail(CSNET_E_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+}  // extern "C"

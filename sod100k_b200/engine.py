@@ -1,0 +1,92 @@
+"""Per-model engine state: compiled programs and device plans, keyed by input size / precision, refreshed
+when parameters change.  This is the host logic between the `nn.Module` surface and the C ABI."""
+from __future__ import annotations
+
+import os
+from typing import Dict, Tuple
+
+import torch
+
+from . import compiler, ir, runtime
+
+
+def _has_hooks(model) -> bool:
+    """True if any descendant carries a forward (pre-)hook: those callers expect sub-module __call__s."""
+    for m in model.modules():
+        if m is model:
+            continue
+        if m._forward_hooks or m._forward_pre_hooks:
+            return True
+    return False
+
+
+class ModelEngine:
+    def __init__(self, model):
+        self.model = model
+        self.dtype = os.environ.get("CSNET_B200_DTYPE", "fp32")
+        self._plans: Dict[Tuple, runtime.Plan] = {}
+        self._plan_version: Dict[Tuple, int] = {}
+        self.frozen = False
+
+    def set_precision(self, dtype: str):
+        if dtype not in ir.DTYPE_NAMES:
+            raise ValueError(f"unknown precision {dtype!r}")
+        self.dtype = dtype
+
+    def freeze(self, flag: bool = True):
+        """Skip the per-call parameter-version scan (weights will not change; latency-critical serving)."""
+        self.frozen = flag
+
+    def _version(self) -> int:
+        h = 0
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            h = (h * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFF
+        return h
+
+    def _state(self):
+        return {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+
+    def plan_for(self, N: int, H: int, W: int, device: torch.device) -> runtime.Plan:
+        key = (H, W, self.dtype, device.index or 0)
+        plan = self._plans.get(key)
+        if plan is not None and self.frozen and plan.max_batch >= N:
+            return plan
+        ver = self._version()
+        if plan is None or plan.max_batch < N:
+            prog = compiler.compile_csnet(self.model.layer_config, self._state(), H, W, self.dtype)
+            if plan is not None:
+                plan.close()
+            plan = runtime.Plan(prog, max_batch=N, device=key[3])
+            self._plans[key] = plan
+        elif self._plan_version.get(key) != ver:
+            prog = compiler.compile_csnet(self.model.layer_config, self._state(), H, W, self.dtype)
+            plan.set_blob(prog.blob, torch.cuda.current_stream(device).cuda_stream)
+        self._plan_version[key] = ver
+        return plan
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected input [N,3,H,W], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise runtime.EngineError("CSNet (B200 engine) needs a CUDA input; call model.cuda() / input.cuda() "
+                                      "as the reference's test.py does — there is no CPU path")
+        if self.model.training or _has_hooks(self.model) or torch.is_grad_enabled() and x.requires_grad:
+            from . import modular
+
+            return modular.csnet_forward(self.model, x)
+        N, _, H, W = x.shape
+        return self.plan_for(N, H, W, x.device).forward(x)
+
+    def forward_host(self, x_host: torch.Tensor, out: torch.Tensor = None, device: int = 0) -> torch.Tensor:
+        """End-to-end call on HOST tensors (float32 [N,3,H,W], ideally pinned): H2D, program, D2H, synchronised.
+        Mirrors CSNet/test.py:86-93 (`.cuda()` ... `.cpu()`) in one C-ABI call."""
+        if x_host.is_cuda or x_host.dtype != torch.float32:
+            raise ValueError("forward_host takes a float32 host tensor")
+        x_host = x_host.contiguous()
+        N, _, H, W = x_host.shape
+        dev = torch.device("cuda", device)
+        plan = self.plan_for(N, H, W, dev)
+        if out is None:
+            out = torch.empty((N, 1, H, W), dtype=torch.float32, pin_memory=True)
+        plan.run_host(N, x_host.data_ptr(), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        return out

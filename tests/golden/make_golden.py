@@ -120,6 +120,13 @@ def main():
             fwd[f"{tag}/randn/tap/{k}"] = v
         meta[tag] = dict(layer_config=cfg_to_json(model.layer_config), seed=seed, hw=hw,
                          shapes={k: list(v) for k, v in shapes.items()}, kw={k: (list(v) if isinstance(v, list) else v) for k, v in kw.items()})
+    # same seed -> same initial parameters (construction order + initialisers are part of the surface)
+    torch.manual_seed(0)
+    model = build(basic_split=[0.5, 0.5], expand=2.0)
+    for k, v in model.state_dict().items():
+        if k in ("stage0.0.conv1x1.conv.weight", "stage2.1.conv3x3_2.convs.1.weight", "oct_fuse.fuse.conv.weight",
+                 "oct_fuse.ms.convs.1.msconv.3.weight", "cls_layer.weight", "cls_layer.bias"):
+            fwd[f"seed0-init/{k}"] = v.numpy().reshape(-1)[:256].copy()
     meta["torch"] = torch.__version__
     meta["numpy"] = np.__version__
     meta["threads"] = torch.get_num_threads()

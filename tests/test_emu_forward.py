@@ -1,0 +1,52 @@
+"""Host-side check of compiler + generic kernel bodies (emulated on the CPU) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import csnet_oracle as O
+from sod100k_b200 import compiler, synth
+from tests import emu, fixtures
+
+
+def _oracle(cfg, sd, x, taps=None):
+    with torch.no_grad():
+        return O.csnet_forward(cfg, sd, torch.from_numpy(x), taps=taps).numpy()
+
+
+@pytest.mark.parametrize("tag,hw", [("csnet-L-x2", (64, 96)), ("csnet-L-x1", (64, 64))])
+def test_emulated_program_matches_oracle_checkpoints(tag, hw):
+    cfg, sd = fixtures.checkpoint(tag)
+    x = synth.randn_images(2, hw[0], hw[1], 11)
+    prog = compiler.compile_csnet(cfg, sd, hw[0], hw[1], "fp32", reuse_arena=False)
+    names = ["stage1.0/0", "stage1.0/1", "stage2.0/1", "stage2.3/0", "stage4.3/0", "oct_fuse.ms/2", "oct_fuse.fuse1x1/0"]
+    y, got = emu.run(prog, x, names)
+    taps = {}
+    ref = _oracle(cfg, sd, x, taps)
+    for n in names:
+        blk, b = n.rsplit("/", 1)
+        r = taps[blk][int(b)].numpy()
+        assert np.abs(got[n] - r).max() <= 1e-4 * max(1.0, np.abs(r).max()), n
+    assert np.abs(y - ref).max() <= 1e-4
+    # arena reuse must not change the result
+    prog2 = compiler.compile_csnet(cfg, sd, hw[0], hw[1], "fp32", reuse_arena=True)
+    assert prog2.arena_bytes_per_image < prog.arena_bytes_per_image
+    y2, _ = emu.run(prog2, x)
+    assert np.array_equal(y, y2)
+
+
+@pytest.mark.parametrize("tag", ["init-std", "init-3br"])
+def test_emulated_program_unpruned_architectures(tag):
+    cfg, sd, m = fixtures.synthetic_model(tag)
+    h, w = m["hw"]
+    x = synth.randn_images(1, h, w, 1240 + m["seed"])
+    prog = compiler.compile_csnet(cfg, sd, h, w, "fp32")
+    y, _ = emu.run(prog, x)
+    z, _ = fixtures.forward_golden()
+    ref = z[f"{tag}/randn"]
+    assert np.abs(y - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_size_must_be_multiple_of_16():
+    cfg, sd = fixtures.checkpoint("csnet-L-x1")
+    with pytest.raises(ValueError):
+        compiler.compile_csnet(cfg, sd, 100, 100)

@@ -1,0 +1,148 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import csnet_oracle as O
+from oracle import salmetric
+from sod100k_b200 import compiler, runtime, synth
+from sod100k_b200.model import csnet
+from tests import fixtures
+
+pytestmark = pytest.mark.gpu
+
+SIG_TOL_FP32 = 1e-3      # north_star gate: max|sigmoid(new) - sigmoid(ref)| <= 1e-3 in fp32
+LOGIT_TOL_FP32 = 1e-3    # what fp32 accumulation-order differences actually allow (observed ~1e-5)
+SIG_TOL_FP16 = 6e-3      # fp16 activation storage (SURVEY A.4 measured 1-2e-3 for naive fp16 of the reference)
+SIG_TOL_BF16 = 6e-2
+
+
+def _model(tag):
+    cfg, sd = fixtures.checkpoint(tag)
+    m = csnet.CSNet(cfg)
+    m.load_state_dict(sd)
+    return m.cuda().eval(), cfg, sd
+
+
+def _oracle(cfg, sd, x, taps=None):
+    with torch.no_grad():
+        return O.csnet_forward(cfg, sd, torch.from_numpy(x), taps=taps)
+
+
+@pytest.mark.parametrize("tag", ["csnet-L-x2", "csnet-L-x1"])
+def test_fp32_matches_reference_goldens(tag):
+    m, cfg, sd = _model(tag)
+    z, _ = fixtures.forward_golden()
+    with torch.no_grad():
+        y = m(torch.from_numpy(synth.randn_images(2, 224, 224, 1234)).cuda()).cpu().numpy()
+        ref = z[f"{tag}/randn224"]
+        assert np.abs(y - ref).max() <= LOGIT_TOL_FP32
+        assert np.abs(1 / (1 + np.exp(-y)) - 1 / (1 + np.exp(-ref))).max() <= SIG_TOL_FP32
+        xb, _ = synth.blob_images(2, 224, 224, 1235)
+        y = m(torch.from_numpy(xb).cuda()).cpu().numpy()
+        assert np.abs(y - z[f"{tag}/blobs224"]).max() <= LOGIT_TOL_FP32
+        y = m(torch.from_numpy(synth.randn_images(1, 96, 160, 1237)).cuda()).cpu().numpy()
+        assert np.abs(y - z[f"{tag}/randn96x160"]).max() <= LOGIT_TOL_FP32
+        y = m(torch.from_numpy(synth.randn_images(1, 512, 512, 1238)).cuda()).cpu().numpy().reshape(-1)
+        idx = np.random.default_rng(5).integers(0, y.size, 8192)
+        assert np.abs(y[idx] - z[f"{tag}/randn512/sample"]).max() <= LOGIT_TOL_FP32
+
+
+@pytest.mark.parametrize("tag", ["init-x2", "init-std", "init-3br"])
+def test_fp32_unpruned_architectures(tag):
+    cfg, sd, meta = fixtures.synthetic_model(tag)
+    m = csnet.CSNet(cfg)
+    m.load_state_dict(sd)
+    m.cuda().eval()
+    z, _ = fixtures.forward_golden()
+    h, w = meta["hw"]
+    with torch.no_grad():
+        y = m(torch.from_numpy(synth.randn_images(1, h, w, 1240 + meta["seed"])).cuda()).cpu().numpy()
+    ref = z[f"{tag}/randn"]
+    assert np.abs(y - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_per_block_taps_fp32():
+    cfg, sd = fixtures.checkpoint("csnet-L-x2")
+    x = synth.randn_images(2, 64, 96, 21)
+    prog = compiler.compile_csnet(cfg, sd, 64, 96, "fp32", reuse_arena=False)
+    plan = runtime.Plan(prog, max_batch=2)
+    y = plan.forward(torch.from_numpy(x).cuda())
+    taps = {}
+    ref = _oracle(cfg, sd, x, taps)
+    assert (y.cpu() - ref).abs().max().item() <= 1e-4
+    for name, tid in prog.taps.items():
+        blk, b = name.rsplit("/", 1)
+        r = taps[blk][int(b)]
+        got = plan.read_tensor(tid, 2).cpu()
+        assert (got - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item()), name
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp16", SIG_TOL_FP16), ("bf16", SIG_TOL_BF16)])
+def test_reduced_precision_storage(dtype, tol):
+    m, cfg, sd = _model("csnet-L-x2")
+    m.set_precision(dtype)
+    xr = synth.randn_images(2, 224, 224, 1234)
+    xb, masks = synth.blob_images(4, 224, 224, 1235)
+    with torch.no_grad():
+        for x in (xr, xb):
+            y = torch.sigmoid(m(torch.from_numpy(x).cuda())).cpu()
+            ref = torch.sigmoid(_oracle(cfg, sd, x))
+            assert (y - ref).abs().max().item() <= tol
+    # F-measure / MAE of the 8-bit maps against the synthetic ground truth (oracle/salmetric.py)
+    with torch.no_grad():
+        p_new = torch.sigmoid(m(torch.from_numpy(xb).cuda())).cpu().numpy()[:, 0]
+        p_ref = torch.sigmoid(_oracle(cfg, sd, xb)).numpy()[:, 0]
+    gts = [(g[0] * 255).astype(np.uint8) for g in masks]
+    e_new = salmetric.evaluate([salmetric.quantise(p) for p in p_new], gts)
+    e_ref = salmetric.evaluate([salmetric.quantise(p) for p in p_ref], gts)
+    ftol = 1e-3 if dtype == "fp16" else 2e-2
+    assert abs(e_new["max_f"] - e_ref["max_f"]) <= ftol and abs(e_new["mae"] - e_ref["mae"]) <= ftol
+
+
+def test_fmeasure_fp32_within_gate():
+    m, cfg, sd = _model("csnet-L-x2")
+    xb, masks = synth.blob_images(4, 224, 224, 1235)
+    with torch.no_grad():
+        p_new = torch.sigmoid(m(torch.from_numpy(xb).cuda())).cpu().numpy()[:, 0]
+        p_ref = torch.sigmoid(_oracle(cfg, sd, xb)).numpy()[:, 0]
+    gts = [(g[0] * 255).astype(np.uint8) for g in masks]
+    e_new = salmetric.evaluate([salmetric.quantise(p) for p in p_new], gts)
+    e_ref = salmetric.evaluate([salmetric.quantise(p) for p in p_ref], gts)
+    assert abs(e_new["max_f"] - e_ref["max_f"]) <= 1e-3 and abs(e_new["mae"] - e_ref["mae"]) <= 1e-3
+
+
+def test_host_buffer_call_and_batch_properties():
+    m, cfg, sd = _model("csnet-L-x1")
+    x = torch.from_numpy(synth.randn_images(5, 64, 64, 3))
+    with torch.no_grad():
+        y_dev = m(x.cuda()).cpu()
+        y_host = m.engine().forward_host(x.pin_memory())
+        assert torch.equal(y_dev, y_host)
+        # images are independent: a batch equals its per-image runs, in any order (size-independent property)
+        y1 = torch.cat([m(x[i:i + 1].cuda()).cpu() for i in (3, 0)])
+        assert torch.equal(y1, y_dev[[3, 0]])
+        # weights change -> program refreshes
+        with torch.no_grad():
+            m.cls_layer.bias.add_(1.0)
+        assert torch.allclose(m(x.cuda()).cpu(), y_dev + 1.0, atol=1e-5)
+
+
+def test_large_batch_full_size_properties():
+    """BASELINE config size (bs 256, 224x224, fp16): determinism + per-image independence."""
+    m, cfg, sd = _model("csnet-L-x2")
+    m.set_precision("fp16")
+    x = torch.from_numpy(synth.randn_images(8, 224, 224, 77)).cuda().repeat(32, 1, 1, 1)
+    with torch.no_grad():
+        y = m(x)
+        y2 = m(x)
+    assert torch.equal(y, y2)
+    assert torch.equal(y[:8], y[8 * 17:8 * 18])
+    assert torch.isfinite(y).all()
+
+
+def test_train_mode_is_loud_until_built():
+    m, _, _ = _model("csnet-L-x1")
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 32, 32).cuda())

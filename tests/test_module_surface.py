@@ -1,0 +1,114 @@
+"""Drop-in boundary checks that need no GPU: module tree / state_dict contract, initialisation parity,
+C-ABI library exports, loud failure without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from sod100k_b200 import runtime
+from sod100k_b200.model import csnet
+from tests import fixtures
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sod100k_b200 import build
+
+    build.build()
+    return runtime.load_library()
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, "include", "csnet_b200.h")).read()
+    declared = set(re.findall(r"\b(csnet_[a-z_]+)\s*\(", header))
+    assert declared == set(runtime.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.csnet_abi_version() == runtime.ABI_VERSION
+
+
+def test_ctypes_structs_match_header_layout():
+    from sod100k_b200 import ir
+
+    assert ctypes.sizeof(ir.TensorDesc) == 32
+    assert ctypes.sizeof(ir.PathDesc) == 56
+    assert ctypes.sizeof(ir.OpDesc) == 32 + 8 * 56
+
+
+def test_invalid_program_is_rejected_before_touching_the_device(lib):
+    from sod100k_b200 import ir
+
+    t = (ir.TensorDesc * 2)(ir.TensorDesc(3, 16, 16, 0, 0, 0, 0), ir.TensorDesc(4, 16, 16, 0, -1, 0, 0))
+    op = ir.OpDesc()
+    op.kind, op.dst, op.n_paths, op.bias_off, op.slope_off = ir.OP_MIX, 1, 1, -1, -1
+    op.paths[0] = ir.PathDesc(0, 0, 3, 0, 1, 1, 1, 1, 0, 1, 0, 4, 1000)      # weights outside the blob
+    h = ctypes.c_void_p()
+    rc = lib.csnet_plan_create(ctypes.byref(h), t, 2, (ir.OpDesc * 1)(op), 1, 16, 1, 0)
+    assert rc == -1 and b"weights outside blob" in lib.csnet_last_error()
+
+
+def test_no_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg, sd = fixtures.checkpoint("csnet-L-x1")
+    m = csnet.CSNet(cfg)
+    m.load_state_dict(sd)
+    m.eval()
+    with pytest.raises(runtime.EngineError):
+        m(torch.zeros(1, 3, 32, 32))
+
+
+@pytest.mark.parametrize("tag", ["csnet-L-x2", "csnet-L-x1"])
+def test_checkpoints_load_strict(tag):
+    cfg, sd = fixtures.checkpoint(tag)
+    m = csnet.CSNet(cfg)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert list(m.state_dict().keys()) == list(sd.keys())           # same ORDER as the reference too
+    _, meta = fixtures.forward_golden()
+    assert sum(p.numel() for p in m.parameters()) == meta[tag]["params"]
+
+
+def test_same_seed_same_initial_parameters_as_reference():
+    z, _ = fixtures.forward_golden()
+    torch.manual_seed(0)
+    m = csnet.build_model(basic_split=[0.5, 0.5], expand=2.0)
+    sd = m.state_dict()
+    n = 0
+    for k in z.files:
+        if k.startswith("seed0-init/"):
+            assert np.array_equal(sd[k.split("/", 1)[1]].numpy().reshape(-1)[:256], z[k]), k
+            n += 1
+    assert n == 6
+
+
+def test_module_tree_supports_reference_callers():
+    m = csnet.build_model(basic_split=[0.5, 0.5], expand=2.0)
+    # train.py:101-105 picks BN gammas by name
+    picked = [n for n, _ in m.named_parameters()
+              if "stage" in n and ("conv1x1.bns" in n or "conv3x3_1.bns" in n) and "weight" in n]
+    assert len(picked) == 15 * 4 + 3 * 2
+    # finetune / foo_bns walk isinstance targets
+    assert sum(isinstance(x, csnet.ILBlock) for x in m.modules()) == 18
+    assert sum(isinstance(x, csnet.gOctaveCBR) for x in m.modules()) == 20
+    assert sum(isinstance(x, nn.BatchNorm2d) for x in m.modules()) == 106
+    # bookkeeping surface
+    m.flops_hook(expandflop=1.0)
+    m.set_batchsize(24)
+    m.clear_flops()
+    assert m.get_flops() == 0
+    assert not any(x._forward_hooks for x in m.modules())
+
+
+def test_layer_config_pickle_roundtrip(tmp_path):
+    cfg = csnet.init_layers(40, [0.5, 0.5])
+    csnet.save_layer_config(cfg, str(tmp_path), 3, latest=True)
+    back = csnet.load_layer_config(str(tmp_path / "layer_config_latest.bin"))
+    m = csnet.build_model(predefine=str(tmp_path / "layer_config_3.bin"))
+    assert back[-1] == cfg[-1] and len(m.state_dict()) > 700
