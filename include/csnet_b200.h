@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CSNET_ABI_VERSION 1
+#define CSNET_ABI_VERSION 2
 
 enum { CSNET_F32 = 0, CSNET_F16 = 1, CSNET_BF16 = 2 };
 
@@ -44,6 +44,7 @@ enum {
 };
 
 #define CSNET_MAX_PATHS 8
+#define CSNET_MAX_EXT 24
 
 /* One activation tensor of the program (per image: [C,H,W]; a run adds the batch dimension). */
 typedef struct {
@@ -81,7 +82,17 @@ typedef struct {
 
 enum {
   CSNET_OP_MIX = 1,       /* dst = prelu(sum_paths + bias)   — gOctaveCBR / MSBlock / cls_layer */
-  CSNET_OP_DW = 2         /* dst = prelu(dw3x3(src) + bias)  — SimplifiedGOctConvBR branch */
+  CSNET_OP_DW = 2,        /* dst = prelu(dw3x3(src) + bias)  — SimplifiedGOctConvBR branch */
+  CSNET_OP_ILBLOCK = 3    /* whole ILBlock of the 1x1 kind in one kernel (ILBlock.forward, csnet.py:72-76):
+                             paths[0].src / paths[1].src = high / low resolution inputs (cin = channels),
+                             dst / dst2 = high / low resolution outputs (dst2 = -1 for a 2->1 block);
+                             16-bit activations only.  ext_off[] (blob offsets, floats):
+                               0 WH  packed 16-bit [ru16(Cho)][ru8(Chi)]           hi<-hi weights, BN scale folded
+                               1 WL  packed 16-bit [ru16(Clo+Cho)][ru8(P+Cli)]     rows <Clo: [W_hl | W_ll];
+                                     rows Clo..: [0 | W_lh];  P = Chi if Clo > 0 else 0 (pooled-input rows)
+                               2,3   conv bias / PReLU slope of the hi branch      4,5  of the lo branch
+                               6-8   conv3x3_1 hi: weights [C][9], bias, slope     9-11 conv3x3_1 lo
+                               12-14 conv3x3_2 hi                                  15-17 conv3x3_2 lo */
 };
 
 /*
@@ -95,10 +106,11 @@ typedef struct {
   int32_t kind;
   int32_t dst;            /* tensor id */
   int32_t n_paths;
-  int32_t _pad;
+  int32_t dst2;           /* second destination (CSNET_OP_ILBLOCK) or -1 */
   int64_t bias_off;       /* blob offset of bias[dst.C] or -1 */
   int64_t slope_off;      /* blob offset of PReLU slope[dst.C] or -1 */
   csnet_path_desc paths[CSNET_MAX_PATHS];
+  int64_t ext_off[CSNET_MAX_EXT];   /* kind-specific blob offsets, -1 when unused */
 } csnet_op_desc;
 
 typedef struct csnet_plan csnet_plan;

@@ -27,6 +27,35 @@ from . import ir, splits
 BN_EPS = 1e-5
 
 
+def to_bits16(a: np.ndarray, dtype: int) -> np.ndarray:
+    """float array -> raw fp16 / bf16 bit patterns (round to nearest even)."""
+    a = np.ascontiguousarray(a, np.float32)
+    if dtype == ir.F16:
+        return a.astype(np.float16).view(np.uint16)
+    u = a.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) >> 16
+    return u.astype(np.uint16)
+
+
+def _ru(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def _padded_region(n: int) -> int:
+    n = _ru(n, 8)
+    return n + 8 if (n // 8) % 2 == 0 else n
+
+
+def il_block_fits(Chi, Cli, Cho, Clo) -> bool:
+    """Mirror of make_il() in csrc/plan.cu: does the smallest candidate tile fit 227 KB of shared memory?"""
+    pool = Chi if Clo > 0 else 0
+    KH8, KL8, MH16, ML16 = _ru(Chi, 8), _ru(pool + Cli, 8), _ru(Cho, 16), _ru(Clo + Cho, 16)
+    TH, TW = 8, 8
+    NPH, NPL = _padded_region((TH + 8) * (TW + 8)), _padded_region((TH // 2 + 4) * (TW // 2 + 8))
+    halves = 16 + max(KH8, Cho) * NPH + Cho * NPH + max(KL8, Clo) * NPL + Clo * NPL + Cho * NPL + MH16 * KH8 + ML16 * KL8
+    return halves * 2 <= 227 * 1024
+
+
 def _np(v) -> np.ndarray:
     if hasattr(v, "detach"):
         v = v.detach().cpu().numpy()
@@ -34,7 +63,7 @@ def _np(v) -> np.ndarray:
 
 
 class _Lowering:
-    def __init__(self, layer_config, params: Mapping[str, object], H: int, W: int, act_dtype: int):
+    def __init__(self, layer_config, params: Mapping[str, object], H: int, W: int, act_dtype: int, fuse: bool = True):
         if H % 16 or W % 16:
             # the reference's own callers enforce this (CSNet/test.py:80-85); its branch sums fail otherwise
             raise ValueError(f"input size {H}x{W} must be a multiple of 16")
@@ -42,6 +71,8 @@ class _Lowering:
         self.P = params
         self.H, self.W = H, W
         self.dt = act_dtype
+        # fuse: True / False, or a collection of block prefixes to fuse (tests isolate one block that way)
+        self.fuse = fuse if act_dtype in (ir.F16, ir.BF16) else False
         self.b = ir.Builder()
 
     # ---- parameters -----------------------------------------------------------------------------
@@ -132,10 +163,61 @@ class _Lowering:
             outs.append(dst)
         return outs
 
+    def dw_params(self, prefix: str, b_: int):
+        s, t = self.bn_fold(f"{prefix}.bns.{b_}")
+        w = 100.0 * self.p(f"{prefix}.convs.{b_}.weight").reshape(-1, 9) * s[:, None]
+        return [self.b.param(w), self.b.param(t), self.b.param(self.p(f"{prefix}.prelus.{b_}.weight"))]
+
+    def il_block_fused(self, prefix, xs, a_in, a_out):
+        """Whole 1x1-kind ILBlock as one CSNET_OP_ILBLOCK (csrc/il_block.cuh); None if it does not qualify."""
+        if len(a_in) != 2 or len(a_out) not in (1, 2) or xs[0] is None or xs[1] is None:
+            return None
+        W4 = self.p(prefix + ".conv1x1.conv.weight")
+        ci, co = splits.cuts(W4.shape[1], a_in), splits.cuts(W4.shape[0], a_out)
+        Chi, Cli = ci[1] - ci[0], ci[2] - ci[1]
+        Cho, Clo = co[1] - co[0], (co[2] - co[1]) if len(a_out) == 2 else 0
+        (c_h, H_, W_), (c_l, Hl, Wl) = self.dims(xs[0]), self.dims(xs[1])
+        if min(Chi, Cli, Cho) <= 0 or (len(a_out) == 2 and Clo <= 0) or (c_h, c_l) != (Chi, Cli):
+            return None
+        if W_ % 8 or H_ % 2 or (Hl * 2, Wl * 2) != (H_, W_) or not il_block_fits(Chi, Cli, Cho, Clo):
+            return None
+        s_h, t_h = self.bn_fold(prefix + ".conv1x1.bns.0")
+        W2 = W4[:, :, 0, 0]
+        pool = Chi if Clo > 0 else 0
+        WH = np.zeros((_ru(Cho, 16), _ru(Chi, 8)))
+        WH[:Cho, :Chi] = W2[co[0]:co[1], ci[0]:ci[1]] * s_h[:, None]
+        WL = np.zeros((_ru(Clo + Cho, 16), _ru(pool + Cli, 8)))
+        WL[Clo:Clo + Cho, pool:pool + Cli] = W2[co[0]:co[1], ci[1]:ci[2]] * s_h[:, None]
+        ext = [0, 0, self.b.param(t_h), self.b.param(self.p(prefix + ".conv1x1.prelus.0.weight")), -1, -1]
+        if Clo > 0:
+            s_l, t_l = self.bn_fold(prefix + ".conv1x1.bns.1")
+            WL[:Clo, :Chi] = W2[co[1]:co[2], ci[0]:ci[1]] * s_l[:, None]
+            WL[:Clo, Chi:Chi + Cli] = W2[co[1]:co[2], ci[1]:ci[2]] * s_l[:, None]
+            ext[4], ext[5] = self.b.param(t_l), self.b.param(self.p(prefix + ".conv1x1.prelus.1.weight"))
+        lim = 6.0e4 if self.dt == ir.F16 else 3.0e38
+        if not (np.isfinite(WH).all() and np.isfinite(WL).all() and max(np.abs(WH).max(), np.abs(WL).max()) < lim):
+            return None
+        ext[0] = self.b.param_bits16(to_bits16(WH, self.dt))
+        ext[1] = self.b.param_bits16(to_bits16(WL, self.dt))
+        none3 = [-1, -1, -1]
+        ext += self.dw_params(prefix + ".conv3x3_1", 0) + (self.dw_params(prefix + ".conv3x3_1", 1) if Clo else none3)
+        ext += self.dw_params(prefix + ".conv3x3_2", 0) + (self.dw_params(prefix + ".conv3x3_2", 1) if Clo else none3)
+        yh = self.b.tensor(Cho, H_, W_, self.dt, name=f"{prefix}/0")
+        yl = self.b.tensor(Clo, Hl, Wl, self.dt, name=f"{prefix}/1") if Clo else -1
+        op = self.b.op(ir.OP_ILBLOCK, yh, [ir.Path(xs[0], Chi, Cho, ksize=1), ir.Path(xs[1], Cli, Cho, ksize=1)], name=prefix)
+        op.dst2, op.ext_off = yl, ext
+        return [yh] + ([yl] if Clo else [])
+
     def il_block(self, prefix, xs, in_split, out_split, stride, first):
         """ILBlock.forward (csnet.py:72-76)."""
         a_in, a_out = splits.alphas(in_split), splits.alphas(out_split)
         k = 3 if (first or stride == 2) else 1
+        if k == 1 and (self.fuse is True or (self.fuse and prefix in self.fuse)):
+            y = self.il_block_fused(prefix, xs, a_in, a_out)
+            if y is not None:
+                for b_, t in enumerate(y):
+                    self.b.prog.taps[f"{prefix}/{b_}"] = t
+                return y
         y = self.goct_cbr(prefix + ".conv1x1", xs, a_in, a_out, k, stride)
         y = self.dw_cbr(prefix + ".conv3x3_1", y)
         y = self.dw_cbr(prefix + ".conv3x3_2", y)
@@ -207,8 +289,8 @@ class _Lowering:
 
 
 def compile_csnet(layer_config, params: Mapping[str, object], H: int, W: int, dtype="fp32",
-                  reuse_arena: bool = True) -> ir.Program:
+                  reuse_arena: bool = True, fuse: bool = True) -> ir.Program:
     """layer_config: the reference's pickle structure (list of [in_split, out_split(, dil_split)] + stages);
     params: state_dict-like mapping (torch tensors or numpy arrays); returns the eval-mode program."""
     dt = ir.DTYPE_NAMES[dtype] if isinstance(dtype, str) else int(dtype)
-    return _Lowering(layer_config, params, H, W, dt).run(reuse_arena)
+    return _Lowering(layer_config, params, H, W, dt, fuse).run(reuse_arena)

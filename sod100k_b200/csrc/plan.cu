@@ -12,6 +12,7 @@
 
 #include "../../include/csnet_b200.h"
 #include "generic_ops.cuh"
+#include "il_block.cuh"
 
 namespace {
 
@@ -69,6 +70,7 @@ struct csnet_plan {
   int64_t arena_per_image = 0;   // bytes
   int n_ext = 0;
   size_t mix_smem_max = 0;
+  size_t il_smem_max = 0;
   std::vector<size_t> op_smem;
 
   void* tensor_ptr(int t, int N, const void* const* ext) const {
@@ -100,8 +102,33 @@ int validate(const csnet_plan& P) {
       snprintf(buf, sizeof buf, "op %zu: %s", i, why);
       return fail(CSNET_E_INVALID, buf);
     };
-    if (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_DW) return bad("unknown kind");
+    if (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_DW && op.kind != CSNET_OP_ILBLOCK) return bad("unknown kind");
     if (op.dst < 0 || op.dst >= nt) return bad("dst out of range");
+    if (op.kind == CSNET_OP_ILBLOCK) {
+      if (op.n_paths != 2) return bad("ILBLOCK takes two inputs");
+      if (op.dst2 >= nt) return bad("dst2 out of range");
+      const csnet_tensor_desc& Yh = P.tensors[op.dst];
+      const int a = op.paths[0].src, b = op.paths[1].src;
+      if (a < 0 || a >= nt || b < 0 || b >= nt) return bad("ILBLOCK input out of range");
+      const csnet_tensor_desc &Xh = P.tensors[a], &Xl = P.tensors[b];
+      if (a == op.dst || b == op.dst || a == op.dst2 || b == op.dst2) return bad("in-place op");
+      if (Yh.dtype == CSNET_F32 || Xh.dtype != Yh.dtype || Xl.dtype != Yh.dtype) return bad("ILBLOCK needs one 16-bit dtype");
+      if (Xh.H != Yh.H || Xh.W != Yh.W || Xl.H * 2 != Xh.H || Xl.W * 2 != Xh.W) return bad("ILBLOCK input/output resolutions");
+      if (Yh.W % 8 || Yh.H % 2) return bad("ILBLOCK needs W % 8 == 0 and H % 2 == 0");
+      if (op.paths[0].cin != Xh.C || op.paths[1].cin != Xl.C) return bad("ILBLOCK consumes whole input tensors");
+      int Clo = 0;
+      if (op.dst2 >= 0) {
+        const csnet_tensor_desc& Yl = P.tensors[op.dst2];
+        if (Yl.dtype != Yh.dtype || Yl.H != Xl.H || Yl.W != Xl.W) return bad("ILBLOCK lo output shape");
+        Clo = Yl.C;
+      }
+      const int nreq = Clo > 0 ? 18 : 15;
+      for (int e = 0; e < nreq; ++e) {
+        if (Clo == 0 && (e == 4 || e == 5 || (e >= 9 && e <= 11))) continue;
+        if (op.ext_off[e] < 0 || op.ext_off[e] >= P.blob_floats) return bad("ILBLOCK parameter offset outside blob");
+      }
+      continue;
+    }
     if (op.n_paths < 1 || op.n_paths > CSNET_MAX_PATHS) return bad("n_paths out of range");
     const csnet_tensor_desc& D = P.tensors[op.dst];
     if (op.bias_off >= 0 && op.bias_off + D.C > P.blob_floats) return bad("bias outside blob");
@@ -163,6 +190,52 @@ csnet::MixArgs make_mix(const csnet_plan& P, const csnet_op_desc& op, int N, con
     m.cout0 = q.cout0; m.cout = q.cout;
   }
   return A;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int padded_region(int n) {
+  int np = round_up(n, 8);
+  if (((np >> 3) & 1) == 0) np += 8;      // NP/8 odd: the 8 rows of an ldmatrix hit 8 distinct 16-byte bank groups
+  return np;
+}
+
+// Fill the kernel arguments of a fused ILBlock op and pick its tile; false if no tile fits shared memory.
+bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* const* ext, csnet::IlArgs* out) {
+  csnet::IlArgs A{};
+  const csnet_tensor_desc &Xh = P.tensors[op.paths[0].src], &Xl = P.tensors[op.paths[1].src], &Yh = P.tensors[op.dst];
+  A.xh = P.tensor_ptr(op.paths[0].src, N, ext);
+  A.xl = P.tensor_ptr(op.paths[1].src, N, ext);
+  A.yh = P.tensor_ptr(op.dst, N, ext);
+  A.yl = op.dst2 >= 0 ? P.tensor_ptr(op.dst2, N, ext) : nullptr;
+  A.H = Yh.H; A.W = Yh.W;
+  A.Chi = Xh.C; A.Cli = Xl.C; A.Cho = Yh.C; A.Clo = op.dst2 >= 0 ? P.tensors[op.dst2].C : 0;
+  auto f = [&](int e) { return op.ext_off[e] >= 0 ? P.blob + op.ext_off[e] : nullptr; };
+  A.wh = reinterpret_cast<const uint32_t*>(f(0));
+  A.wl = reinterpret_cast<const uint32_t*>(f(1));
+  A.bias_h = f(2); A.slope_h = f(3); A.bias_l = f(4); A.slope_l = f(5);
+  A.dw1h = {f(6), f(7), f(8)};   A.dw1l = {f(9), f(10), f(11)};
+  A.dw2h = {f(12), f(13), f(14)}; A.dw2l = {f(15), f(16), f(17)};
+  A.pool_rows = A.Clo > 0 ? A.Chi : 0;
+  A.KH8 = round_up(A.Chi, 8);
+  A.KL8 = round_up(A.pool_rows + A.Cli, 8);
+  A.MH16 = round_up(A.Cho, 16);
+  A.ML16 = round_up(A.Clo + A.Cho, 16);
+  A.rowsAh = A.KH8 > A.Cho ? A.KH8 : A.Cho;
+  A.rowsAl = A.KL8 > A.Clo ? A.KL8 : A.Clo;
+  static const int cand[][2] = {{32, 64}, {32, 32}, {16, 64}, {16, 32}, {16, 16}, {8, 16}, {8, 8}};
+  double best = -1;
+  for (auto& c : cand) {
+    csnet::IlArgs T = A;
+    T.TH = c[0]; T.TW = c[1];
+    T.NPH = padded_region((T.TH + 8) * (T.TW + 8));
+    T.NPL = padded_region((T.TH / 2 + 4) * (T.TW / 2 + 8));
+    if (csnet::il_smem_bytes(T) > 227 * 1024) continue;
+    const int ty = (A.H + T.TH - 1) / T.TH, tx = (A.W + T.TW - 1) / T.TW;
+    const double cost = (double)ty * tx * (T.TH + 8) * (T.TW + 8);
+    if (best < 0 || cost < best) { best = cost; T.tiles_x = tx; *out = T; }
+  }
+  return best >= 0;
 }
 
 size_t mix_smem_bytes(const csnet::MixArgs& A) {
@@ -237,6 +310,19 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     P->mix_smem_max = P->op_smem[i] > P->mix_smem_max ? P->op_smem[i] : P->mix_smem_max;
   }
   if (P->mix_smem_max > 227 * 1024) return cleanup(CSNET_E_UNSUPPORTED, "MIX op weights exceed shared memory");
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    if (P->ops[i].kind != CSNET_OP_ILBLOCK) continue;
+    csnet::IlArgs A;
+    if (!make_il(*P, P->ops[i], 1, nullptr, &A)) return cleanup(CSNET_E_UNSUPPORTED, "ILBLOCK op does not fit shared memory");
+    P->op_smem[i] = csnet::il_smem_bytes(A);
+    P->il_smem_max = P->op_smem[i] > P->il_smem_max ? P->op_smem[i] : P->il_smem_max;
+  }
+  if (P->il_smem_max > 0) {
+    e = cudaFuncSetAttribute(csnet::il_block_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->il_smem_max);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(csnet::il_block_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->il_smem_max);
+    if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(il_block): ") + cudaGetErrorString(e));
+  }
   if (P->mix_smem_max > 48 * 1024) {
     e = cudaFuncSetAttribute(mix_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->mix_smem_max);
     if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
@@ -269,6 +355,15 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     dim3 grid((D.H * D.W + kThreads - 1) / kThreads, (D.C + csnet::kMixCT - 1) / csnet::kMixCT, N);
     mix_generic_kernel<<<grid, kThreads, P->op_smem[i], stream>>>(A);
+  } else if (op.kind == CSNET_OP_ILBLOCK) {
+    csnet::IlArgs A;
+    if (!make_il(*P, op, N, ext_ptrs, &A)) return fail(CSNET_E_UNSUPPORTED, "ILBLOCK op does not fit shared memory");
+    const int tiles_y = (A.H + A.TH - 1) / A.TH;
+    dim3 grid(A.tiles_x * tiles_y, 1, N);
+    if (D.dtype == CSNET_F16)
+      csnet::il_block_kernel<__half><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A);
+    else
+      csnet::il_block_kernel<__nv_bfloat16><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A);
   } else {
     const csnet_path_desc& q = op.paths[0];
     const csnet_tensor_desc& S = P->tensors[q.src];

@@ -11,7 +11,8 @@ F32, F16, BF16 = 0, 1, 2
 DTYPE_BYTES = {F32: 4, F16: 2, BF16: 2}
 DTYPE_NAMES = {"fp32": F32, "float32": F32, "fp16": F16, "float16": F16, "half": F16, "bf16": BF16, "bfloat16": BF16}
 MAX_PATHS = 8
-OP_MIX, OP_DW = 1, 2
+MAX_EXT = 24
+OP_MIX, OP_DW, OP_ILBLOCK = 1, 2, 3
 
 
 class TensorDesc(C.Structure):
@@ -27,8 +28,9 @@ class PathDesc(C.Structure):
 
 
 class OpDesc(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("dst", C.c_int32), ("n_paths", C.c_int32), ("_pad", C.c_int32),
-                ("bias_off", C.c_int64), ("slope_off", C.c_int64), ("paths", PathDesc * MAX_PATHS)]
+    _fields_ = [("kind", C.c_int32), ("dst", C.c_int32), ("n_paths", C.c_int32), ("dst2", C.c_int32),
+                ("bias_off", C.c_int64), ("slope_off", C.c_int64), ("paths", PathDesc * MAX_PATHS),
+                ("ext_off", C.c_int64 * MAX_EXT)]
 
 
 @dataclass
@@ -56,6 +58,12 @@ class Op:
     bias_off: int = -1
     slope_off: int = -1
     name: str = ""
+    dst2: int = -1
+    ext_off: List[int] = field(default_factory=list)
+
+    @property
+    def dsts(self):
+        return [self.dst] + ([self.dst2] if self.dst2 >= 0 else [])
 
 
 @dataclass
@@ -94,6 +102,9 @@ class Program:
         for i, o in enumerate(self.ops):
             d = OpDesc()
             d.kind, d.dst, d.n_paths, d.bias_off, d.slope_off = o.kind, o.dst, len(o.paths), o.bias_off, o.slope_off
+            d.dst2 = o.dst2
+            for k in range(MAX_EXT):
+                d.ext_off[k] = o.ext_off[k] if k < len(o.ext_off) else -1
             for k, p in enumerate(o.paths):
                 d.paths[k] = PathDesc(p.src, p.c0, p.cin, p.pre_avg, p.pool, p.ksize, p.dil, p.stride, p.pad,
                                       p.up, p.cout0, p.cout, p.w_off)
@@ -128,6 +139,13 @@ class Builder:
         self._blob_len += a.size + pad
         return off
 
+    def param_bits16(self, arr_u16) -> int:
+        """Append a uint16 array (raw fp16/bf16 bits) packed two per blob word; returns its offset in floats."""
+        a = np.ascontiguousarray(np.asarray(arr_u16, dtype=np.uint16)).reshape(-1)
+        if a.size % 2:
+            a = np.concatenate([a, np.zeros(1, np.uint16)])
+        return self.param(a.view(np.float32))
+
     def op(self, kind, dst, paths, bias=None, slope=None, name="") -> Op:
         if len(paths) > MAX_PATHS:
             raise ValueError(f"{name}: {len(paths)} paths exceed CSNET_MAX_PATHS")
@@ -149,29 +167,31 @@ def plan_arena(p: Program, reuse: bool = True) -> None:
     last_use: Dict[int, int] = {}
     first_def: Dict[int, int] = {}
     for k, o in enumerate(p.ops):
-        first_def.setdefault(o.dst, k)
-        last_use[o.dst] = max(last_use.get(o.dst, k), k)
+        for d in o.dsts:
+            first_def.setdefault(d, k)
+            last_use[d] = max(last_use.get(d, k), k)
         for q in o.paths:
             last_use[q.src] = k
     align = lambda v: (v + 255) // 256 * 256
     live: List[tuple] = []          # (offset, size, tensor)
     top = 0
     for k, o in enumerate(p.ops):
-        t = p.tensors[o.dst]
-        if t.external < 0 and first_def[o.dst] == k:
+        for dst in o.dsts:
+            t = p.tensors[dst]
+            if t.external >= 0 or first_def[dst] != k:
+                continue
             size = align(t.bytes_per_image)
             if reuse:
                 live.sort()
-                off, placed = 0, False
+                off = 0
                 for lo, sz, _ in live:
                     if lo - off >= size:
-                        placed = True
                         break
                     off = max(off, lo + sz)
                 t.arena_offset = off
             else:
                 t.arena_offset = top
             top = max(top, t.arena_offset + size)
-            live.append((t.arena_offset, size, o.dst))
+            live.append((t.arena_offset, size, dst))
         if reuse:
             live = [e for e in live if last_use.get(e[2], k) > k]

@@ -13,7 +13,7 @@ from . import ir
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsnet_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 # every symbol include/csnet_b200.h declares (tests check the library exports exactly these)

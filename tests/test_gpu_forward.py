@@ -165,3 +165,44 @@ def test_train_mode_is_loud_until_built():
     m.train()
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 3, 32, 32).cuda())
+
+
+@pytest.mark.parametrize("tag,hw,dtype", [("csnet-L-x2", (224, 224), "fp16"), ("csnet-L-x2", (96, 160), "fp16"),
+                                          ("csnet-L-x1", (128, 64), "fp16"), ("csnet-L-x2", (64, 96), "bf16"),
+                                          ("init-x2", (96, 96), "fp16")])
+def test_fused_ilblock_kernel_matches_generic_ops(tag, hw, dtype):
+    """Each fused ILBlock kernel (csrc/il_block.cuh) in isolation: fuse exactly one block, so its inputs are
+    bit-identical to the all-generic program's, and compare the block outputs.  Differences come only from
+    16-bit weights / the 16-bit upsample operand / accumulation order inside that block."""
+    if tag.startswith("init"):
+        cfg, sd, _ = fixtures.synthetic_model(tag)
+    else:
+        cfg, sd = fixtures.checkpoint(tag)
+    h, w = hw
+    x = torch.from_numpy(synth.randn_images(3, h, w, 31)).cuda()
+    base = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse=False)
+    p0 = runtime.Plan(base, max_batch=3)
+    p0.forward(x)
+    full = compiler.compile_csnet(cfg, sd, h, w, dtype, fuse=True)
+    fused_names = [o.name for o in full.ops if o.kind == 3]
+    assert len(fused_names) >= 8
+    rel = 4e-3 if dtype == "fp16" else 3e-2       # a few 16-bit ulps of the tensor's max magnitude
+    for name in fused_names:
+        prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse={name})
+        assert sum(o.kind == 3 for o in prog.ops) == 1
+        p1 = runtime.Plan(prog, max_batch=3)
+        p1.forward(x)
+        for b in (0, 1):
+            key = f"{name}/{b}"
+            if key not in prog.taps:
+                continue
+            ref = p0.read_tensor(base.taps[key], 3)
+            got = p1.read_tensor(prog.taps[key], 3)
+            err = (got - ref).abs().max().item()
+            assert err <= rel * max(1.0, ref.abs().max().item()), (key, err, ref.abs().max().item())
+        p1.close()
+    # and the whole fused network against the oracle
+    pf = runtime.Plan(full, max_batch=3)
+    y = torch.sigmoid(pf.forward(x)).cpu()
+    ref = torch.sigmoid(_oracle(cfg, sd, x.cpu().numpy()))
+    assert (y - ref).abs().max().item() <= (SIG_TOL_FP16 if dtype == "fp16" else SIG_TOL_BF16)

@@ -38,7 +38,7 @@ def test_ctypes_structs_match_header_layout():
 
     assert ctypes.sizeof(ir.TensorDesc) == 32
     assert ctypes.sizeof(ir.PathDesc) == 56
-    assert ctypes.sizeof(ir.OpDesc) == 32 + 8 * 56
+    assert ctypes.sizeof(ir.OpDesc) == 32 + 8 * 56 + 24 * 8
 
 
 def test_invalid_program_is_rejected_before_touching_the_device(lib):
