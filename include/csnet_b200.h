@@ -87,9 +87,9 @@ enum {
                              paths[0].src / paths[1].src = high / low resolution inputs (cin = channels),
                              dst / dst2 = high / low resolution outputs (dst2 = -1 for a 2->1 block);
                              16-bit activations only.  ext_off[] (blob offsets, floats):
-                               0 WH  packed 16-bit [ru16(Cho)][ru8(Chi)]           hi<-hi weights, BN scale folded
-                               1 WL  packed 16-bit [ru16(Clo+Cho)][ru8(P+Cli)]     rows <Clo: [W_hl | W_ll];
-                                     rows Clo..: [0 | W_lh];  P = Chi if Clo > 0 else 0 (pooled-input rows)
+                               0 WH  packed 16-bit [ru16(Cho)][K8], K8 = ru8(Chi+Cli): columns [W_hh | W_lh]
+                                     (the kernel up-samples x_l before the conv: same linear map), BN scale folded
+                               1 WL  packed 16-bit [ru16(Clo)][K8]: columns [W_ll | W_hl] (x_l, then max-pooled x_h)
                                2,3   conv bias / PReLU slope of the hi branch      4,5  of the lo branch
                                6-8   conv3x3_1 hi: weights [C][9], bias, slope     9-11 conv3x3_1 lo
                                12-14 conv3x3_2 hi                                  15-17 conv3x3_2 lo */

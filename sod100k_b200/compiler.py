@@ -47,13 +47,16 @@ def _padded_region(n: int) -> int:
 
 
 def il_block_fits(Chi, Cli, Cho, Clo) -> bool:
-    """Mirror of make_il() in csrc/plan.cu: does the smallest candidate tile fit 227 KB of shared memory?"""
-    pool = Chi if Clo > 0 else 0
-    KH8, KL8, MH16, ML16 = _ru(Chi, 8), _ru(pool + Cli, 8), _ru(Cho, 16), _ru(Clo + Cho, 16)
-    TH, TW = 8, 8
-    NPH, NPL = _padded_region((TH + 8) * (TW + 8)), _padded_region((TH // 2 + 4) * (TW // 2 + 8))
-    halves = 16 + max(KH8, Cho) * NPH + Cho * NPH + max(KL8, Clo) * NPL + Clo * NPL + Cho * NPL + MH16 * KH8 + ML16 * KL8
-    return halves * 2 <= 227 * 1024
+    """Mirror of make_il() in csrc/plan.cu: K = Chi + Cli must fit the register-resident B fragments (<= 64) and the
+    smallest candidate tile (8 x 16) must fit 227 KB of shared memory."""
+    K8, MH16, ML16 = _ru(Chi + Cli, 8), _ru(Cho, 16), (_ru(Clo, 16) if Clo else 0)
+    if K8 > 64:
+        return False
+    TH, TW = 8, 16
+    NPH, NPL = ((TH + 8) | 1) * (TW + 8), ((TH // 2 + 4) | 1) * (TW // 2 + 8)
+    rows_l = max(K8, Clo) if Clo else Cli
+    halves = max(K8, Cho) * NPH + Cho * NPH + rows_l * NPL + Clo * NPL + MH16 * K8 + ML16 * K8
+    return halves * 2 + 512 <= 227 * 1024
 
 
 def _np(v) -> np.ndarray:
@@ -183,16 +186,16 @@ class _Lowering:
             return None
         s_h, t_h = self.bn_fold(prefix + ".conv1x1.bns.0")
         W2 = W4[:, :, 0, 0]
-        pool = Chi if Clo > 0 else 0
-        WH = np.zeros((_ru(Cho, 16), _ru(Chi, 8)))
+        K8 = _ru(Chi + Cli, 8)
+        WH = np.zeros((_ru(Cho, 16), K8))                    # columns: [x_h | bilinear_x2(x_l)]
         WH[:Cho, :Chi] = W2[co[0]:co[1], ci[0]:ci[1]] * s_h[:, None]
-        WL = np.zeros((_ru(Clo + Cho, 16), _ru(pool + Cli, 8)))
-        WL[Clo:Clo + Cho, pool:pool + Cli] = W2[co[0]:co[1], ci[1]:ci[2]] * s_h[:, None]
+        WH[:Cho, Chi:Chi + Cli] = W2[co[0]:co[1], ci[1]:ci[2]] * s_h[:, None]
+        WL = np.zeros((max(_ru(Clo, 16), 16), K8))           # columns: [x_l | maxpool2(x_h)]
         ext = [0, 0, self.b.param(t_h), self.b.param(self.p(prefix + ".conv1x1.prelus.0.weight")), -1, -1]
         if Clo > 0:
             s_l, t_l = self.bn_fold(prefix + ".conv1x1.bns.1")
-            WL[:Clo, :Chi] = W2[co[1]:co[2], ci[0]:ci[1]] * s_l[:, None]
-            WL[:Clo, Chi:Chi + Cli] = W2[co[1]:co[2], ci[1]:ci[2]] * s_l[:, None]
+            WL[:Clo, :Cli] = W2[co[1]:co[2], ci[1]:ci[2]] * s_l[:, None]
+            WL[:Clo, Cli:Cli + Chi] = W2[co[1]:co[2], ci[0]:ci[1]] * s_l[:, None]
             ext[4], ext[5] = self.b.param(t_l), self.b.param(self.p(prefix + ".conv1x1.prelus.1.weight"))
         lim = 6.0e4 if self.dt == ir.F16 else 3.0e38
         if not (np.isfinite(WH).all() and np.isfinite(WL).all() and max(np.abs(WH).max(), np.abs(WL).max()) < lim):

@@ -1,25 +1,28 @@
 // il_block.cuh — one kernel per ILBlock (1x1 kind): gOctaveCBR(1x1, 2 in-branches -> 1|2 out-branches)
-// + depthwise 3x3 BN PReLU + depthwise 3x3 BN PReLU, everything between the block's input and output
+// + depthwise 3x3 BN PReLU + depthwise 3x3 BN PReLU; everything between the block's input and output
 // tensors stays in shared memory (reference: ILBlock.forward, CSNet/model/csnet.py:72-76, calling
 // gOctaveConv.forward :664-726 and SimplifiedGOctConvBR.forward :838-851).
 //
 // One CTA owns a TH x TW tile of the high-resolution output branch and the co-located (TH/2 x TW/2) tile of
-// the low-resolution branch, 16-bit activations (fp16 or bf16), fp32 accumulation:
+// the low-resolution branch; 16-bit activations (fp16 or bf16), fp32 accumulation.
 //
-//   load     XH[Chi][hi region, halo 4]  XL[.. Cli][lo region]           global -> smem, zero outside the image
-//   pool     XL[0..Chi) = maxpool2x2(XH)                                   (hi -> lo path reads pooled input)
-//   lo GEMM  [T1L ; U] = WL . XL     tensor cores (mma.sync m16n8k8), pixels are the N dimension
-//            T1L = PReLU(. + b) (lo branch after conv+BN+PReLU),  U = W_lh . x_l (to be upsampled)
-//   hi GEMM  T1H = PReLU(WH . XH + bilinear_x2(U) + b)
-//   dw1      T2  = PReLU(dw3x3(T1) + b)      CUDA cores, fp32 accumulate, both branches
-//   dw2      out = PReLU(dw3x3(T2) + b)  ->  global (tile interior only)
+//   load      AH[0..Chi)   = x_h over the hi region (halo 4)       TMA (cp.async.bulk.tensor, zero fill outside
+//             AL[0..Cli)   = x_l over the lo region                 the image) or cp.async when W*2 % 16 != 0
+//   resample  AL[Cli..)    = maxpool2x2(AH[0..Chi))                 hi -> lo path reads the pooled input (:709-712)
+//             AH[Chi..)    = bilinear_x2(AL[0..Cli))                lo -> hi path; upsampling the conv INPUT is the
+//                                                                   same linear map as upsampling its output (:702-707)
+//   GEMMs     T1H = PReLU(WH . AH + b)   T1L = PReLU(WL . AL + b)   tensor cores (mma.sync m16n8k8), pixels are the
+//                                                                   N dimension, written IN PLACE over AH / AL
+//   dw1       T2  = PReLU(dw3x3(T1) + b)                            CUDA cores, fp32 accumulate, both branches
+//   dw2       out = PReLU(dw3x3(T2) + b)  ->  global (tile interior only)
 //
 // T1/T2 are forced to 0 outside the image so the depthwise convs see the reference's zero padding.
 // Region geometry (R = region-local coordinates):
-//   hi region origin (hy0-4, hx0-4), size (TH+8) x (TW+8)          [halo 4 = 2 (two dw layers) x 2 (pooling)]
-//   lo region origin (ly0-2, lx0-4), size (TH/2+4) x (TW/2+8)      [x origin kept a multiple of 4 for 8-byte I/O]
-//   lo R(ry, rx)  <->  hi R(2ry, 2rx-4)
+//   hi region origin (hy0-4, hx0-4), size RHh x RWh = (TH+8 [+1]) x (TW+8)    halo 4 = 2 (two dw layers) x 2 (pooling)
+//   lo region origin (ly0-2, lx0-4), size RHl x RWl = (TH/2+4 [+1]) x (TW/2+8) x origin kept a multiple of 4 (8-byte I/O)
+//   lo R(ry, rx)  <->  hi R(2ry, 2rx-4);  the optional +1 row only makes RH*RW/8 odd (conflict-free ldmatrix).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -27,7 +30,7 @@
 namespace csnet {
 
 constexpr int kIlThreads = 512;
-constexpr int kIlRowsPerTask = 8;
+constexpr int kIlMaxK8 = 8;         // K (input channels hi + lo) <= 64: all B fragments of 4 pixel tiles stay in registers
 
 struct DwParams {
   const float* w;      // [C][9]
@@ -35,28 +38,36 @@ struct DwParams {
   const float* s;      // [C] PReLU slope
 };
 
+struct FastDiv {       // q = i / d, exact for 2 <= d and 0 <= i < 2^32 / d
+  uint32_t d, m;
+  __device__ __forceinline__ uint32_t div(uint32_t i) const { return __umulhi(i, m); }
+};
+inline FastDiv make_fastdiv(uint32_t d) { return FastDiv{d, (uint32_t)((0x100000000ull + d - 1) / d)}; }
+
 struct IlArgs {
   const void* xh;
   const void* xl;
   void* yh;
   void* yl;                    // nullptr when Clo == 0
-  const uint32_t* wh;          // packed 16-bit [MH16][KH8]
-  const uint32_t* wl;          // packed 16-bit [ML16][KL8]
+  const uint32_t* wh;          // packed 16-bit [MH16][K8]   columns: [x_h (Chi) | up(x_l) (Cli)]
+  const uint32_t* wl;          // packed 16-bit [ML16][K8]   columns: [x_l (Cli) | pool(x_h) (Chi)]   (Clo > 0 only)
   const float *bias_h, *slope_h, *bias_l, *slope_l;
   DwParams dw1h, dw1l, dw2h, dw2l;
   int32_t H, W;                // hi resolution (lo = H/2 x W/2)
   int32_t Chi, Cli, Cho, Clo;
   int32_t TH, TW, tiles_x;
-  int32_t KH8, KL8, MH16, ML16, pool_rows;
-  int32_t NPH, NPL;            // padded flat region sizes (multiples of 8, NP/8 odd)
-  int32_t rowsAh, rowsAl;      // rows of the X/T2 buffers
+  int32_t K8, MH16, ML16;
+  int32_t RHh, RWh, RHl, RWl, NPH, NPL;
+  int32_t rowsAh, rowsAl;
+  int32_t tma_h, tma_l;        // 1: that input is loaded with TMA
+  FastDiv dRWh, dRWl, dPairsL, dQuadsH, dQuadPlaneH, dPairPlaneL;
 };
 
 // ---- 16-bit helpers -----------------------------------------------------------------------------------
 template <typename T> struct Pack;
 template <> struct Pack<__half> {
-  using T2 = __half2;
   static __device__ __forceinline__ float2 to_f2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+  static __device__ __forceinline__ float to_f(uint16_t v) { return __half2float(*reinterpret_cast<__half*>(&v)); }
   static __device__ __forceinline__ uint32_t from_f2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -71,8 +82,8 @@ template <> struct Pack<__half> {
   }
 };
 template <> struct Pack<__nv_bfloat16> {
-  using T2 = __nv_bfloat162;
   static __device__ __forceinline__ float2 to_f2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
+  static __device__ __forceinline__ float to_f(uint16_t v) { return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&v)); }
   static __device__ __forceinline__ uint32_t from_f2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -96,271 +107,363 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const void* p) {
 __device__ __forceinline__ void ldmatrix_x2(uint32_t* r, const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
 }
-
 __device__ __forceinline__ float prelu(float v, float s) { return v > 0.f ? v : s * v; }
 
-// D[M16 x NP] = Ws[M16 x K8] . X[K8 x NP]; epi(m, p, v0, v1) receives rows m and two adjacent pixels p, p+1.
-template <typename T, typename Epi>
-__device__ __forceinline__ void gemm_pixels(const uint16_t* Ws, int M16, int K8, const uint16_t* X, int NP, int warp,
-                                            int nwarps, int lane, Epi epi) {
-  const int ntiles = NP >> 3;
+// ---- TMA / mbarrier / cp.async ------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 8 : 0;       // src-size 0: the 8 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// D[M16 x NP] = Ws[M16 x K8] . X[K8 x NP], result handed to epi() pair-wise; X may be overwritten by epi() for the
+// SAME pixel columns (each warp owns its columns and holds all their B fragments in registers before writing).
+template <typename T, typename Coord, typename Epi>
+__device__ __forceinline__ void gemm_pixels_inplace(const uint16_t* Ws, int M16, int K8, uint16_t* X, int NP, int warp,
+                                                    int nwarps, int lane, Coord coord, Epi epi) {
+  const int ntiles = NP >> 3, ksteps = K8 >> 3;
   const int g = lane >> 2, t = lane & 3;
   for (int nt0 = warp * 4; nt0 < ntiles; nt0 += nwarps * 4) {
     int ntl = nt0 + (lane >> 3);
-    ntl = ntl < ntiles ? ntl : ntiles - 1;            // clamp: result of a clamped tile is discarded
-    for (int mt0 = 0; mt0 < (M16 >> 4); mt0 += 2) {
-      const int mts = ((M16 >> 4) - mt0) < 2 ? ((M16 >> 4) - mt0) : 2;
-      float acc[2][4][4];
+    ntl = ntl < ntiles ? ntl : ntiles - 1;            // clamp: the result of a clamped tile is discarded
+    uint32_t bf[kIlMaxK8][4];
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+    for (int ks = 0; ks < kIlMaxK8; ++ks)
+      if (ks < ksteps) ldmatrix_x4_trans(bf[ks], X + (size_t)(ks * 8 + (lane & 7)) * NP + ntl * 8);
+    __syncwarp();
+    int cy[4], cx[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+    for (int j = 0; j < 4; ++j) coord((nt0 + j) * 8 + 2 * t, cy[j], cx[j]);
+    for (int mt = 0; mt < (M16 >> 4); ++mt) {
+      float acc[4][4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-      for (int ks = 0; ks < (K8 >> 3); ++ks) {
-        uint32_t bf[4];
-        ldmatrix_x4_trans(bf, X + (size_t)(ks * 8 + (lane & 7)) * NP + ntl * 8);
+      for (int b = 0; b < 4; ++b)
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi) {
-          if (mi < mts) {
-            uint32_t af[2];
-            ldmatrix_x2(af, Ws + (size_t)((mt0 + mi) * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * K8 + ks * 8);
+        for (int c = 0; c < 4; ++c) acc[b][c] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) Pack<T>::mma(acc[mi][j], af, bf[j]);
-          }
+      for (int ks = 0; ks < kIlMaxK8; ++ks) {
+        if (ks < ksteps) {
+          uint32_t af[2];
+          ldmatrix_x2(af, Ws + (size_t)(mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * K8 + ks * 8);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Pack<T>::mma(acc[j], af, bf[ks][j]);
         }
       }
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        if (mi < mts) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int nt = nt0 + j;
-            if (nt < ntiles) {
-              const int p = nt * 8 + 2 * t;
-              epi((mt0 + mi) * 16 + g, p, acc[mi][j][0], acc[mi][j][1]);
-              epi((mt0 + mi) * 16 + g + 8, p, acc[mi][j][2], acc[mi][j][3]);
-            }
-          }
+      for (int j = 0; j < 4; ++j) {
+        if (nt0 + j < ntiles) {
+          const int p = (nt0 + j) * 8 + 2 * t;
+          epi(mt * 16 + g, p, cy[j], cx[j], acc[j][0], acc[j][1]);
+          epi(mt * 16 + g + 8, p, cy[j], cx[j], acc[j][2], acc[j][3]);
         }
       }
     }
   }
 }
 
-// Depthwise 3x3 + bias + PReLU over region rows [r0, r1), 4-pixel groups [g0, g1) of every channel.
+// Depthwise 3x3 + bias + PReLU over region rows [r0, r1), 4-pixel groups [g0, g1) of every channel of a plane set.
 // in/out: [C][NP] flat region planes with row stride RW.  Output pixels outside the image are written as 0
-// (smem destination) or skipped (global destination).
-template <typename T, bool kToGlobal>
-__device__ __forceinline__ void dw_pass(const uint16_t* in, uint16_t* out_s, uint16_t* out_g, int C, int RW, int NP,
-                                        int r0, int r1, int g0, int g1, DwParams P, int oy0, int ox0, int imgH,
-                                        int imgW, int tid, int nthreads) {
-  const int G = g1 - g0;
-  const int nruns = (r1 - r0 + kIlRowsPerTask - 1) / kIlRowsPerTask;
-  const int ntasks = C * nruns * G;
-  for (int task = tid; task < ntasks; task += nthreads) {
-    const int gi = task % G, run = (task / G) % nruns, c = task / (G * nruns);
-    const int x = 4 * (g0 + gi);
-    const int ra = r0 + run * kIlRowsPerTask;
-    const int rb = (ra + kIlRowsPerTask) < r1 ? (ra + kIlRowsPerTask) : r1;
+// (smem destination) or skipped (global destination).  A task = one channel, one 4-pixel column group, RUN rows;
+// the tasks of the hi and lo plane sets share one index space so the 512 threads stay evenly loaded.
+struct DwSet {
+  const uint16_t* in;
+  uint16_t* out;             // smem planes or the global tensor of this image
+  DwParams P;
+  int C, RW, NP, r0, r1, g0, g1, oy0, ox0, imgH, imgW;
+};
+
+template <typename T, bool kToGlobal, int RUN>
+__device__ __forceinline__ void dw_pass(const DwSet& SA, const DwSet& SB, int tid, int nthreads) {
+  const int nA = SA.C * ((SA.r1 - SA.r0 + RUN - 1) / RUN) * (SA.g1 - SA.g0);
+  const int nB = SB.C * ((SB.r1 - SB.r0 + RUN - 1) / RUN) * (SB.g1 - SB.g0);
+  for (int task0 = tid; task0 < nA + nB; task0 += nthreads) {
+    const bool second = task0 >= nA;
+    const DwSet& S = second ? SB : SA;
+    const int task = second ? task0 - nA : task0;
+    const int G = S.g1 - S.g0, nruns = (S.r1 - S.r0 + RUN - 1) / RUN;
+    const int gi = task % G, rest = task / G;
+    const int run = rest % nruns, c = rest / nruns;
+    const int x = 4 * (S.g0 + gi);
+    const int ra = S.r0 + run * RUN, r1 = S.r1, RW = S.RW;
     float w[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) w[i] = __ldg(P.w + c * 9 + i);
-    const float bias = __ldg(P.b + c), slope = __ldg(P.s + c);
-    const uint16_t* plane = in + (size_t)c * NP;
-    float rows[3][6];
-    auto load_row = [&](int r, float* dst) {
-      const uint32_t* q = reinterpret_cast<const uint32_t*>(plane + r * RW + x);   // 4-byte aligned (x, RW, NP even)
-      const float2 a = Pack<T>::to_f2(q[-1]), b = Pack<T>::to_f2(q[0]), c2 = Pack<T>::to_f2(q[1]), d = Pack<T>::to_f2(q[2]);
-      dst[0] = a.y; dst[1] = b.x; dst[2] = b.y; dst[3] = c2.x; dst[4] = c2.y; dst[5] = d.x;
-    };
-    load_row(ra - 1, rows[0]);
-    load_row(ra, rows[1]);
-    for (int r = ra; r < rb; ++r) {
-      load_row(r + 1, rows[2]);
-      float o[4];
+    for (int i = 0; i < 9; ++i) w[i] = __ldg(S.P.w + c * 9 + i);
+    const float bias = __ldg(S.P.b + c), slope = __ldg(S.P.s + c);
+    const uint16_t* plane = S.in + (size_t)c * S.NP + x;
+    const int gx = S.ox0 + x;
+    const bool col_in = gx >= 0 && gx < S.imgW;        // imgW % 4 == 0 and gx % 4 == 0: a group is all in or all out
+    float rows[RUN + 2][6];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float v = bias;
-        v = fmaf(rows[0][i], w[0], v); v = fmaf(rows[0][i + 1], w[1], v); v = fmaf(rows[0][i + 2], w[2], v);
-        v = fmaf(rows[1][i], w[3], v); v = fmaf(rows[1][i + 1], w[4], v); v = fmaf(rows[1][i + 2], w[5], v);
-        v = fmaf(rows[2][i], w[6], v); v = fmaf(rows[2][i + 1], w[7], v); v = fmaf(rows[2][i + 2], w[8], v);
-        o[i] = prelu(v, slope);
-      }
-      const int gy = oy0 + r, gx = ox0 + x;
-      const bool row_in = gy >= 0 && gy < imgH;
-      if (kToGlobal) {
-        if (row_in && gx >= 0 && gx < imgW) {          // imgW % 4 == 0 and gx % 4 == 0: the group is all in or all out
-          uint2 v;
-          v.x = Pack<T>::from_f2(o[0], o[1]);
-          v.y = Pack<T>::from_f2(o[2], o[3]);
-          *reinterpret_cast<uint2*>(out_g + ((size_t)c * imgH + gy) * imgW + gx) = v;
-        }
+    for (int i = 0; i < RUN + 2; ++i) {
+      const int r = ra - 1 + i;
+      if (r <= r1) {                                    // row r1 exists (r1 <= RH - 1)
+        const uint2 mid = *reinterpret_cast<const uint2*>(plane + r * RW);            // x .. x+3 (8-byte aligned)
+        const uint32_t lft = *reinterpret_cast<const uint32_t*>(plane + r * RW - 2);  // x-2, x-1
+        const uint32_t rgt = *reinterpret_cast<const uint32_t*>(plane + r * RW + 4);  // x+4, x+5
+        const float2 a = Pack<T>::to_f2(lft), b = Pack<T>::to_f2(mid.x), c2 = Pack<T>::to_f2(mid.y), d = Pack<T>::to_f2(rgt);
+        rows[i][0] = a.y; rows[i][1] = b.x; rows[i][2] = b.y; rows[i][3] = c2.x; rows[i][4] = c2.y; rows[i][5] = d.x;
       } else {
-        const bool in = row_in && gx >= 0 && gx < imgW;
-        uint2 v;
-        v.x = in ? Pack<T>::from_f2(o[0], o[1]) : 0u;
-        v.y = in ? Pack<T>::from_f2(o[2], o[3]) : 0u;
-        *reinterpret_cast<uint2*>(out_s + (size_t)c * NP + r * RW + x) = v;
-      }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { rows[0][i] = rows[1][i]; rows[1][i] = rows[2][i]; }
+        for (int k = 0; k < 6; ++k) rows[i][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) {
+      const int r = ra + i;
+      if (r < r1) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v = bias;
+          v = fmaf(rows[i][k], w[0], v); v = fmaf(rows[i][k + 1], w[1], v); v = fmaf(rows[i][k + 2], w[2], v);
+          v = fmaf(rows[i + 1][k], w[3], v); v = fmaf(rows[i + 1][k + 1], w[4], v); v = fmaf(rows[i + 1][k + 2], w[5], v);
+          v = fmaf(rows[i + 2][k], w[6], v); v = fmaf(rows[i + 2][k + 1], w[7], v); v = fmaf(rows[i + 2][k + 2], w[8], v);
+          o[k] = prelu(v, slope);
+        }
+        const int gy = S.oy0 + r;
+        const bool in_img = col_in && gy >= 0 && gy < S.imgH;
+        uint2 v;
+        v.x = Pack<T>::from_f2(o[0], o[1]);
+        v.y = Pack<T>::from_f2(o[2], o[3]);
+        if (kToGlobal) {
+          if (in_img) *reinterpret_cast<uint2*>(S.out + ((size_t)c * S.imgH + gy) * S.imgW + gx) = v;
+        } else {
+          if (!in_img) v = make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(S.out + (size_t)c * S.NP + r * RW + x) = v;
+        }
+      }
     }
   }
 }
 
 inline size_t il_smem_bytes(const IlArgs& A) {
-  size_t halves = 8 + (size_t)A.rowsAh * A.NPH + (size_t)A.Cho * A.NPH + (size_t)A.rowsAl * A.NPL +
-                  (size_t)A.Clo * A.NPL + (size_t)A.Cho * A.NPL + (size_t)A.MH16 * A.KH8 + (size_t)A.ML16 * A.KL8 + 8;
-  return halves * 2;
+  size_t halves = (size_t)A.rowsAh * A.NPH + (size_t)A.Cho * A.NPH + (size_t)A.rowsAl * A.NPL + (size_t)A.Clo * A.NPL +
+                  (size_t)A.MH16 * A.K8 + (size_t)A.ML16 * A.K8;
+  return halves * 2 + 128 /*base alignment*/ + 128 /*mbarrier + front guard*/ + 128 /*bufAh size round-up*/ + 128 /*tail guard*/;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kIlThreads, 1) il_block_kernel(const __grid_constant__ IlArgs A) {
-  extern __shared__ __align__(16) uint16_t smem[];
+__global__ void __launch_bounds__(kIlThreads, 1)
+il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL) {
+  extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kIlThreads >> 5;
   const int n = blockIdx.z;
   const int tile_y = blockIdx.x / A.tiles_x, tile_x = blockIdx.x % A.tiles_x;
   const int hy0 = tile_y * A.TH, hx0 = tile_x * A.TW, ly0 = hy0 >> 1, lx0 = hx0 >> 1;
   const int H = A.H, W = A.W, Hl = A.H >> 1, Wl = A.W >> 1;
-  const int RHh = A.TH + 8, RWh = A.TW + 8, RHl = (A.TH >> 1) + 4, RWl = (A.TW >> 1) + 8;
-  const int NPH = A.NPH, NPL = A.NPL;
+  const int RHh = A.RHh, RWh = A.RWh, RHl = A.RHl, RWl = A.RWl, NPH = A.NPH, NPL = A.NPL;
+  const int Chi = A.Chi, Cli = A.Cli, Cho = A.Cho, Clo = A.Clo;
 
-  uint16_t* bufAh = smem + 8;                          // XH, later T2H
-  uint16_t* bufBh = bufAh + (size_t)A.rowsAh * NPH;    // T1H
-  uint16_t* bufAl = bufBh + (size_t)A.Cho * NPH;       // XL, later T2L
-  uint16_t* bufBl = bufAl + (size_t)A.rowsAl * NPL;    // T1L
-  uint16_t* bufU = bufBl + (size_t)A.Clo * NPL;        // U = W_lh . x_l
-  uint16_t* wsH = bufU + (size_t)A.Cho * NPL;
-  uint16_t* wsL = wsH + A.MH16 * A.KH8;
-  uint16_t* guard1 = wsL + A.ML16 * A.KL8;
+  // carve (all sizes are multiples of 16 bytes; bufAh / bufAl are 128-byte aligned TMA destinations)
+  uint8_t* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(base);               // 8 bytes; bytes 16..63 = zero guard in front of bufAh
+  uint16_t* bufAh = reinterpret_cast<uint16_t*>(base + 128);        // [x_h | up(x_l)] -> T1H (in place)
+  size_t off = (size_t)A.rowsAh * NPH * 2;
+  off = (off + 127) & ~(size_t)127;
+  uint16_t* bufAl = bufAh + off / 2;                                // [x_l | pool(x_h)] -> T1L (in place)
+  uint16_t* bufBh = bufAl + (size_t)A.rowsAl * NPL;                 // T2H
+  uint16_t* bufBl = bufBh + (size_t)Cho * NPH;                      // T2L
+  uint16_t* wsH = bufBl + (size_t)Clo * NPL;
+  uint16_t* wsL = wsH + A.MH16 * A.K8;
+  uint16_t* tail = wsL + A.ML16 * A.K8;
 
-  // ---- phase 0/1: weights + input regions -> smem ------------------------------------------------------
-  if (tid < 4) {
-    reinterpret_cast<uint32_t*>(smem)[tid] = 0u;
-    reinterpret_cast<uint32_t*>(guard1)[tid] = 0u;
+  // ---- phase 0: barrier, weights, zero rows -----------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
-  for (int i = tid; i < (A.MH16 * A.KH8) >> 1; i += kIlThreads) reinterpret_cast<uint32_t*>(wsH)[i] = __ldg(A.wh + i);
-  for (int i = tid; i < (A.ML16 * A.KL8) >> 1; i += kIlThreads) reinterpret_cast<uint32_t*>(wsL)[i] = __ldg(A.wl + i);
+  if (tid >= 32 && tid < 32 + 28) reinterpret_cast<uint32_t*>(base + 16)[tid - 32] = 0u;   // guard in front of bufAh
+  if (tid >= 64 && tid < 64 + 8) reinterpret_cast<uint32_t*>(tail)[tid - 64] = 0u;          // tail guard
+  __syncthreads();
+
+  const uint32_t tx_bytes = (A.tma_h ? (uint32_t)Chi * NPH * 2u : 0u) + (A.tma_l ? (uint32_t)Cli * NPL * 2u : 0u);
+  if (tid == 0 && tx_bytes) {
+    mbar_expect_tx(mbar, tx_bytes);
+    if (A.tma_h) tma_load_4d(bufAh, &tmH, mbar, hx0 - 4, hy0 - 4, 0, n);
+    if (A.tma_l) tma_load_4d(bufAl, &tmL, mbar, lx0 - 4, ly0 - 2, 0, n);
+  }
+  // weights (tiny, L2-resident) and the zero K-padding rows, while the bulk copies fly
+  for (int i = tid; i < (A.MH16 * A.K8) >> 1; i += kIlThreads) reinterpret_cast<uint32_t*>(wsH)[i] = __ldg(A.wh + i);
+  if (Clo > 0)
+    for (int i = tid; i < (A.ML16 * A.K8) >> 1; i += kIlThreads) reinterpret_cast<uint32_t*>(wsL)[i] = __ldg(A.wl + i);
   {
-    const uint16_t* xh = reinterpret_cast<const uint16_t*>(A.xh) + (size_t)n * A.Chi * H * W;
-    const int halfW = NPH >> 1, pairs_row = RWh >> 1;
-    for (int i = tid; i < A.rowsAh * halfW; i += kIlThreads) {
-      const int c = i / halfW, pp = i % halfW;
-      const int ry = pp / pairs_row, rx = (pp % pairs_row) * 2;
+    const int z0 = (Chi + Cli) * (NPH >> 1), z1 = A.rowsAh * (NPH >> 1);
+    for (int i = z0 + tid; i < z1; i += kIlThreads) reinterpret_cast<uint32_t*>(bufAh)[i] = 0u;
+    const int kl = Clo > 0 ? (Chi + Cli) : Cli;
+    const int y0 = kl * (NPL >> 1), y1 = A.rowsAl * (NPL >> 1);
+    for (int i = y0 + tid; i < y1; i += kIlThreads) reinterpret_cast<uint32_t*>(bufAl)[i] = 0u;
+  }
+  // cp.async fallback loaders (8-byte chunks, zero fill outside the image)
+  if (!A.tma_h) {
+    const uint16_t* xh = reinterpret_cast<const uint16_t*>(A.xh) + (size_t)n * Chi * H * W;
+    const int quads_row = RWh >> 2, quads_plane = NPH >> 2;
+    for (int i = tid; i < Chi * quads_plane; i += kIlThreads) {
+      const int c = A.dQuadPlaneH.div(i), pq = i - c * quads_plane;
+      const int ry = A.dQuadsH.div(pq), rx = (pq - ry * quads_row) * 4;
       const int gy = hy0 - 4 + ry, gx = hx0 - 4 + rx;
-      uint32_t v = 0u;
-      if (c < A.Chi && ry < RHh && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = __ldg(reinterpret_cast<const uint32_t*>(xh + ((size_t)c * H + gy) * W + gx));
-      reinterpret_cast<uint32_t*>(bufAh + (size_t)c * NPH)[pp] = v;
+      const bool ok = ry < RHh && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      cp_async8(bufAh + (size_t)c * NPH + pq * 4, ok ? xh + ((size_t)c * H + gy) * W + gx : xh, ok);
     }
-    const uint16_t* xl = reinterpret_cast<const uint16_t*>(A.xl) + (size_t)n * A.Cli * Hl * Wl;
-    const int halfWl = NPL >> 1, pairs_rowl = RWl >> 1;
-    const int rows_lo = A.rowsAl - A.pool_rows;
-    for (int i = tid; i < rows_lo * halfWl; i += kIlThreads) {
-      const int c = i / halfWl, pp = i % halfWl;
-      const int ry = pp / pairs_rowl, rx = (pp % pairs_rowl) * 2;
+  }
+  if (!A.tma_l) {
+    const uint16_t* xl = reinterpret_cast<const uint16_t*>(A.xl) + (size_t)n * Cli * Hl * Wl;
+    const int quads_row = RWl >> 2, quads_plane = NPL >> 2;
+    for (int i = tid; i < Cli * quads_plane; i += kIlThreads) {
+      const int c = i / quads_plane, pq = i - c * quads_plane;
+      const int ry = pq / quads_row, rx = (pq - ry * quads_row) * 4;
       const int gy = ly0 - 2 + ry, gx = lx0 - 4 + rx;
-      uint32_t v = 0u;
-      if (c < A.Cli && ry < RHl && gy >= 0 && gy < Hl && gx >= 0 && gx < Wl)
-        v = __ldg(reinterpret_cast<const uint32_t*>(xl + ((size_t)c * Hl + gy) * Wl + gx));
-      reinterpret_cast<uint32_t*>(bufAl + (size_t)(A.pool_rows + c) * NPL)[pp] = v;
+      const bool ok = ry < RHl && gy >= 0 && gy < Hl && gx >= 0 && gx < Wl;
+      cp_async8(bufAl + (size_t)c * NPL + pq * 4, ok ? xl + ((size_t)c * Hl + gy) * Wl + gx : xl, ok);
+    }
+  }
+  cp_async_wait_all();
+  if (tx_bytes) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(mbar, 0)) {
+      if (++spins > (1u << 24)) __trap();            // a lost TMA must not hang the GPU
     }
   }
   __syncthreads();
 
-  // ---- phase 2: pooled rows of XL (max_pool2d 2x2 of the hi input, csnet.py:709-712) -------------------
-  if (A.pool_rows > 0) {
-    const int halfWl = NPL >> 1, pairs_rowl = RWl >> 1;
-    for (int i = tid; i < A.pool_rows * halfWl; i += kIlThreads) {
-      const int c = i / halfWl, pp = i % halfWl;
-      const int ry = pp / pairs_rowl, rx = (pp % pairs_rowl) * 2;          // lo region coords of the pair (rx, rx+1)
+  // ---- phase 1: resample both ways --------------------------------------------------------------------
+  // (a) max_pool2d 2x2 of x_h -> AL rows [Cli, Cli+Chi): two lo pixels per task from 2 hi rows x 4 hi pixels
+  if (Clo > 0) {
+    const int pairs_row = RWl >> 1, pairs_plane = NPL >> 1;
+    const int umax = RWh >> 2;
+    for (int i = tid; i < Chi * pairs_plane; i += kIlThreads) {
+      const int c = A.dPairPlaneL.div(i), pp = i - c * pairs_plane;
+      const int ry = A.dPairsL.div(pp), u = pp - ry * pairs_row;
       uint32_t v = 0u;
-      const int hx = 2 * rx - 4;                                           // hi region col of lo col rx
-      if (ry < RHl && hx >= 0 && hx + 3 < RWh) {
-        const uint16_t* r0 = bufAh + (size_t)c * NPH + (2 * ry) * RWh + hx;
-        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(r0), a1 = *reinterpret_cast<const uint32_t*>(r0 + 2);
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(r0 + RWh), b1 = *reinterpret_cast<const uint32_t*>(r0 + RWh + 2);
-        const uint32_t m0 = Pack<T>::max2(a0, b0), m1 = Pack<T>::max2(a1, b1);   // vertical max of 2 hi pixel pairs
+      if (ry < RHl && 2 * ry + 1 < RHh && u >= 1 && u <= umax) {
+        const uint16_t* r0 = bufAh + (size_t)c * NPH + (2 * ry) * RWh + 4 * u - 4;
+        const uint2 a = *reinterpret_cast<const uint2*>(r0), b = *reinterpret_cast<const uint2*>(r0 + RWh);
+        const uint32_t m0 = Pack<T>::max2(a.x, b.x), m1 = Pack<T>::max2(a.y, b.y);
         const float2 f0 = Pack<T>::to_f2(m0), f1 = Pack<T>::to_f2(m1);
         v = Pack<T>::from_f2(fmaxf(f0.x, f0.y), fmaxf(f1.x, f1.y));
       }
-      reinterpret_cast<uint32_t*>(bufAl + (size_t)c * NPL)[pp] = v;
+      reinterpret_cast<uint32_t*>(bufAl + (size_t)(Cli + c) * NPL)[pp] = v;
     }
-    __syncthreads();
   }
-
-  // ---- phase 3: lo GEMM -> T1L (rows < Clo) and U (rows Clo .. Clo+Cho) --------------------------------
+  // (b) bilinear x2 of x_l -> AH rows [Chi, Chi+Cli): F.interpolate(scale_factor=2, align_corners=False) has the
+  //     fixed taps dst 2j: (1/4, 3/4) of src (j-1, j); dst 2j+1: (3/4, 1/4) of src (j, j+1), indices clamped to the
+  //     image.  A task = 2 hi rows x 4 hi columns of one channel.
   {
-    const int Clo = A.Clo, Cho = A.Cho;
+    const int quads_row = RWh >> 2;
+    const int row_pairs = RHh >> 1;                   // hi rows (2a, 2a+1), a < RHh/2 (an odd last row stays zero-filled)
+    const int per_plane = row_pairs * quads_row;
+    for (int i = tid; i < Cli * per_plane; i += kIlThreads) {
+      const int c = i / per_plane, rem = i - c * per_plane;
+      const int a = rem / quads_row, q = rem - a * quads_row;
+      // hi rows (2a, 2a+1) <-> image rows gy = hy0-4+2a (even) and gy+1; lo image row of gy/2: li = ly0-2+a
+      const int li = ly0 - 2 + a;
+      auto clampy = [&](int y) { y = y < 0 ? 0 : (y > Hl - 1 ? Hl - 1 : y); int r = y - (ly0 - 2); return r < 0 ? 0 : (r > RHl - 1 ? RHl - 1 : r); };
+      const int ra = clampy(li - 1), rb = clampy(li), rc = clampy(li + 1);
+      // hi cols 4q..4q+3 <-> image cols gx0 = hx0-4+4q = 2*j0; lo image cols j0-1 .. j0+2
+      const int j0 = ((hx0 - 4) >> 1) + 2 * q;
+      auto clampx = [&](int xx) { xx = xx < 0 ? 0 : (xx > Wl - 1 ? Wl - 1 : xx); int r = xx - (lx0 - 4); return r < 0 ? 0 : (r > RWl - 1 ? RWl - 1 : r); };
+      const int c0 = clampx(j0 - 1), c1 = clampx(j0), c2 = clampx(j0 + 1), c3 = clampx(j0 + 2);
+      const uint16_t* src = bufAl + (size_t)c * NPL;
+      float h[3][4];                                  // horizontally blended rows a-1, a, a+1 at the 4 hi columns
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint16_t* r = src + (k == 0 ? ra : (k == 1 ? rb : rc)) * RWl;
+        const float v0 = Pack<T>::to_f(r[c0]), v1 = Pack<T>::to_f(r[c1]), v2 = Pack<T>::to_f(r[c2]), v3 = Pack<T>::to_f(r[c3]);
+        h[k][0] = 0.75f * v1 + 0.25f * v0;            // col 2*j0     : hx*v[x0=j0-1]... x0=j0-1 weight .25, x1=j0 weight .75
+        h[k][1] = 0.75f * v1 + 0.25f * v2;            // col 2*j0 + 1 : x0=j0 weight .75, x1=j0+1 weight .25
+        h[k][2] = 0.75f * v2 + 0.25f * v1;            // col 2*j0 + 2
+        h[k][3] = 0.75f * v2 + 0.25f * v3;            // col 2*j0 + 3
+      }
+      uint2 o0, o1;                                   // hi row 2a (even): rows (li-1, li) w (.25, .75); row 2a+1: (li, li+1) w (.75, .25)
+      o0.x = Pack<T>::from_f2(0.75f * h[1][0] + 0.25f * h[0][0], 0.75f * h[1][1] + 0.25f * h[0][1]);
+      o0.y = Pack<T>::from_f2(0.75f * h[1][2] + 0.25f * h[0][2], 0.75f * h[1][3] + 0.25f * h[0][3]);
+      o1.x = Pack<T>::from_f2(0.75f * h[1][0] + 0.25f * h[2][0], 0.75f * h[1][1] + 0.25f * h[2][1]);
+      o1.y = Pack<T>::from_f2(0.75f * h[1][2] + 0.25f * h[2][2], 0.75f * h[1][3] + 0.25f * h[2][3]);
+      uint16_t* dst = bufAh + (size_t)(Chi + c) * NPH + (2 * a) * RWh + 4 * q;
+      *reinterpret_cast<uint2*>(dst) = o0;
+      *reinterpret_cast<uint2*>(dst + RWh) = o1;
+    }
+    // rows of the hi planes not covered above (odd last row, padded tail): zero
+    const int covered = (RHh >> 1) * 2 * RWh;
+    const int tailh = (NPH - covered) >> 1;
+    for (int i = tid; i < Cli * tailh; i += kIlThreads) {
+      const int c = i / tailh, k = i - c * tailh;
+      reinterpret_cast<uint32_t*>(bufAh + (size_t)(Chi + c) * NPH + covered)[k] = 0u;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: the two 1x1 convolutions on tensor cores, in place ------------------------------------
+  if (Clo > 0) {
     const float* bl = A.bias_l;
     const float* sl = A.slope_l;
-    auto epi = [&](int m, int p, float v0, float v1) {
-      if (m < Clo) {
-        const int ry = p / RWl, rx = p % RWl;
-        const int gy = ly0 - 2 + ry, gx = lx0 - 4 + rx;
-        const bool rin = ry < RHl && gy >= 0 && gy < Hl;
-        const float b = __ldg(bl + m), s = __ldg(sl + m);
-        const float o0 = (rin && gx >= 0 && gx < Wl) ? prelu(v0 + b, s) : 0.f;
-        const float o1 = (rin && gx + 1 >= 0 && gx + 1 < Wl) ? prelu(v1 + b, s) : 0.f;
-        *reinterpret_cast<uint32_t*>(bufBl + (size_t)m * NPL + p) = Pack<T>::from_f2(o0, o1);
-      } else if (m - Clo < Cho) {
-        *reinterpret_cast<uint32_t*>(bufU + (size_t)(m - Clo) * NPL + p) = Pack<T>::from_f2(v0, v1);
-      }
+    auto coord = [&](int p, int& cy, int& cx) {
+      const int ry = A.dRWl.div(p);
+      cy = ly0 - 2 + ry; cx = lx0 - 4 + (p - ry * RWl);
+      if (ry >= RHl) cy = -1;
     };
-    gemm_pixels<T>(wsL, A.ML16, A.KL8, bufAl, NPL, warp, nwarps, lane, epi);
+    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1) {
+      if (m >= Clo) return;
+      const bool rin = gy >= 0 && gy < Hl;
+      const float b = __ldg(bl + m), s = __ldg(sl + m);
+      const float o0 = (rin && gx >= 0 && gx < Wl) ? prelu(v0 + b, s) : 0.f;
+      const float o1 = (rin && gx + 1 >= 0 && gx + 1 < Wl) ? prelu(v1 + b, s) : 0.f;
+      *reinterpret_cast<uint32_t*>(bufAl + (size_t)m * NPL + p) = Pack<T>::from_f2(o0, o1);
+    };
+    gemm_pixels_inplace<T>(wsL, A.ML16, A.K8, bufAl, NPL, warp, nwarps, lane, coord, epi);
   }
-  __syncthreads();
-
-  // ---- phase 4: hi GEMM + bilinear x2 of U + bias + PReLU -> T1H ---------------------------------------
   {
-    const int Cho = A.Cho;
     const float* bh = A.bias_h;
     const float* sh = A.slope_h;
-    auto epi = [&](int m, int p, float v0, float v1) {
-      if (m >= Cho) return;
-      const int ry = p / RWh, rx = p % RWh;                 // rx even, pixels rx and rx+1 share the row
-      const int gy = hy0 - 4 + ry, gx = hx0 - 4 + rx;
-      float o0 = 0.f, o1 = 0.f;
-      if (ry >= 2 && ry < RHh - 2 && rx >= 2 && rx < RWh - 2 && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        // F.interpolate(scale_factor=2, bilinear, align_corners=False): src = (dst + .5)/2 - .5 clamped at 0
-        float sy = ((float)gy + 0.5f) * 0.5f - 0.5f;
-        sy = sy < 0.f ? 0.f : sy;
-        const int y0 = (int)sy, y1 = y0 + (y0 < Hl - 1 ? 1 : 0);
-        const float wy1 = sy - (float)y0, wy0 = 1.f - wy1;
-        const uint16_t* u0 = bufU + (size_t)m * NPL + (y0 - (ly0 - 2)) * RWl - (lx0 - 4);
-        const uint16_t* u1 = bufU + (size_t)m * NPL + (y1 - (ly0 - 2)) * RWl - (lx0 - 4);
-        const float b = __ldg(bh + m), s = __ldg(sh + m);
-        auto sample = [&](int x) {
-          float sx = ((float)x + 0.5f) * 0.5f - 0.5f;
-          sx = sx < 0.f ? 0.f : sx;
-          const int x0 = (int)sx, x1 = x0 + (x0 < Wl - 1 ? 1 : 0);
-          const float wx1 = sx - (float)x0, wx0 = 1.f - wx1;
-          const float v00 = Pack<T>::to_f2((uint32_t)u0[x0]).x, v01 = Pack<T>::to_f2((uint32_t)u0[x1]).x;
-          const float v10 = Pack<T>::to_f2((uint32_t)u1[x0]).x, v11 = Pack<T>::to_f2((uint32_t)u1[x1]).x;
-          return wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
-        };
-        o0 = prelu(v0 + sample(gx) + b, s);
-        o1 = prelu(v1 + sample(gx + 1) + b, s);   // W even and gx even: gx+1 is inside the image too
-      }
-      *reinterpret_cast<uint32_t*>(bufBh + (size_t)m * NPH + p) = Pack<T>::from_f2(o0, o1);
+    auto coord = [&](int p, int& cy, int& cx) {
+      const int ry = A.dRWh.div(p);
+      cy = hy0 - 4 + ry; cx = hx0 - 4 + (p - ry * RWh);
+      if (ry >= RHh) cy = -1;
     };
-    gemm_pixels<T>(wsH, A.MH16, A.KH8, bufAh, NPH, warp, nwarps, lane, epi);
+    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1) {
+      if (m >= Cho) return;
+      const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;      // W even, gx even: gx+1 is inside too
+      const float b = __ldg(bh + m), s = __ldg(sh + m);
+      const float o0 = in ? prelu(v0 + b, s) : 0.f, o1 = in ? prelu(v1 + b, s) : 0.f;
+      *reinterpret_cast<uint32_t*>(bufAh + (size_t)m * NPH + p) = Pack<T>::from_f2(o0, o1);
+    };
+    gemm_pixels_inplace<T>(wsH, A.MH16, A.K8, bufAh, NPH, warp, nwarps, lane, coord, epi);
   }
   __syncthreads();
 
-  // ---- phase 5: dw1 (T1 -> T2, smem) --------------------------------------------------------------------
-  dw_pass<T, false>(bufBh, bufAh, nullptr, A.Cho, RWh, NPH, 3, RHh - 3, 0, RWh >> 2, A.dw1h, hy0 - 4, hx0 - 4, H, W, tid, kIlThreads);
-  if (A.Clo > 0)
-    dw_pass<T, false>(bufBl, bufAl, nullptr, A.Clo, RWl, NPL, 1, RHl - 1, 0, RWl >> 2, A.dw1l, ly0 - 2, lx0 - 4, Hl, Wl, tid, kIlThreads);
+  // ---- phase 3: dw1 (T1 -> T2, smem) ------------------------------------------------------------------
+  const int rh = A.TH + 8, rl = (A.TH >> 1) + 4;      // region rows that matter (without the padding row)
+  {
+    const DwSet sh{bufAh, bufBh, A.dw1h, Cho, RWh, NPH, 3, rh - 3, 0, RWh >> 2, hy0 - 4, hx0 - 4, H, W};
+    const DwSet sl{bufAl, bufBl, A.dw1l, Clo, RWl, NPL, 1, rl - 1, 0, RWl >> 2, ly0 - 2, lx0 - 4, Hl, Wl};
+    dw_pass<T, false, 6>(sh, sl, tid, kIlThreads);
+  }
   __syncthreads();
 
-  // ---- phase 6: dw2 (T2 -> global) ----------------------------------------------------------------------
-  dw_pass<T, true>(bufAh, nullptr, reinterpret_cast<uint16_t*>(A.yh) + (size_t)n * A.Cho * H * W, A.Cho, RWh, NPH, 4, RHh - 4,
-                   1, (RWh >> 2) - 1, A.dw2h, hy0 - 4, hx0 - 4, H, W, tid, kIlThreads);
-  if (A.Clo > 0)
-    dw_pass<T, true>(bufAl, nullptr, reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * A.Clo * Hl * Wl, A.Clo, RWl, NPL, 2,
-                     RHl - 2, 1, (RWl >> 2) - 1, A.dw2l, ly0 - 2, lx0 - 4, Hl, Wl, tid, kIlThreads);
+  // ---- phase 4: dw2 (T2 -> global) --------------------------------------------------------------------
+  {
+    const DwSet sh{bufBh, reinterpret_cast<uint16_t*>(A.yh) + (size_t)n * Cho * H * W, A.dw2h, Cho, RWh, NPH, 4, rh - 4, 1,
+                   (RWh >> 2) - 1, hy0 - 4, hx0 - 4, H, W};
+    const DwSet sl{bufBl, Clo > 0 ? reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * Clo * Hl * Wl : nullptr, A.dw2l, Clo, RWl, NPL,
+                   2, rl - 2, 1, (RWl >> 2) - 1, ly0 - 2, lx0 - 4, Hl, Wl};
+    dw_pass<T, true, 4>(sh, sl, tid, kIlThreads);
+  }
 }
 
 }  // namespace csnet

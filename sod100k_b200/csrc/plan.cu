@@ -2,6 +2,7 @@
 //
 // A plan holds: the validated program, the device copy of the parameter blob, and one activation arena.
 // csnet_plan_run() walks the op list and launches one fused kernel per op on the caller's stream.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -200,6 +201,37 @@ int padded_region(int n) {
   return np;
 }
 
+// cuTensorMapEncodeTiled comes from the driver; resolve it through the runtime so the library links against
+// cudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 4-D map over a planar [N][C][H][W] 16-bit tensor, box = (bw, bh, bc, 1) -> dense [bc][bh][bw] in shared memory,
+// out-of-bounds elements read as zero (the conv zero padding / "outside the image" of the fused kernels).
+bool encode_plane_map(CUtensorMap* tm, const void* base, int N, int C, int H, int W, int bw, int bh, int bc) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)C * H * W * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Fill the kernel arguments of a fused ILBlock op and pick its tile; false if no tile fits shared memory.
 bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* const* ext, csnet::IlArgs* out) {
   csnet::IlArgs A{};
@@ -216,26 +248,33 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   A.bias_h = f(2); A.slope_h = f(3); A.bias_l = f(4); A.slope_l = f(5);
   A.dw1h = {f(6), f(7), f(8)};   A.dw1l = {f(9), f(10), f(11)};
   A.dw2h = {f(12), f(13), f(14)}; A.dw2l = {f(15), f(16), f(17)};
-  A.pool_rows = A.Clo > 0 ? A.Chi : 0;
-  A.KH8 = round_up(A.Chi, 8);
-  A.KL8 = round_up(A.pool_rows + A.Cli, 8);
+  A.K8 = round_up(A.Chi + A.Cli, 8);
+  if (A.K8 > 8 * csnet::kIlMaxK8) return false;
   A.MH16 = round_up(A.Cho, 16);
-  A.ML16 = round_up(A.Clo + A.Cho, 16);
-  A.rowsAh = A.KH8 > A.Cho ? A.KH8 : A.Cho;
-  A.rowsAl = A.KL8 > A.Clo ? A.KL8 : A.Clo;
-  static const int cand[][2] = {{32, 64}, {32, 32}, {16, 64}, {16, 32}, {16, 16}, {8, 16}, {8, 8}};
+  A.ML16 = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
+  A.rowsAh = A.K8 > A.Cho ? A.K8 : A.Cho;
+  A.rowsAl = A.Clo > 0 ? (A.K8 > A.Clo ? A.K8 : A.Clo) : A.Cli;
+  A.tma_h = (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
+  A.tma_l = ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
+  static const int cand[][2] = {{32, 64}, {32, 32}, {16, 64}, {16, 32}, {16, 16}, {8, 16}};
   double best = -1;
   for (auto& c : cand) {
     csnet::IlArgs T = A;
     T.TH = c[0]; T.TW = c[1];
-    T.NPH = padded_region((T.TH + 8) * (T.TW + 8));
-    T.NPL = padded_region((T.TH / 2 + 4) * (T.TW / 2 + 8));
+    T.RWh = T.TW + 8; T.RHh = (T.TH + 8) | 1;            // odd row count: (RH * RW / 8) odd when RW / 8 is odd
+    T.RWl = T.TW / 2 + 8; T.RHl = (T.TH / 2 + 4) | 1;
+    T.NPH = T.RHh * T.RWh; T.NPL = T.RHl * T.RWl;
     if (csnet::il_smem_bytes(T) > 227 * 1024) continue;
     const int ty = (A.H + T.TH - 1) / T.TH, tx = (A.W + T.TW - 1) / T.TW;
-    const double cost = (double)ty * tx * (T.TH + 8) * (T.TW + 8);
+    const double cost = (double)ty * tx * T.NPH;
     if (best < 0 || cost < best) { best = cost; T.tiles_x = tx; *out = T; }
   }
-  return best >= 0;
+  if (best < 0) return false;
+  csnet::IlArgs& R = *out;
+  R.dRWh = csnet::make_fastdiv(R.RWh); R.dRWl = csnet::make_fastdiv(R.RWl);
+  R.dPairsL = csnet::make_fastdiv(R.RWl / 2); R.dQuadsH = csnet::make_fastdiv(R.RWh / 4);
+  R.dQuadPlaneH = csnet::make_fastdiv(R.NPH / 4); R.dPairPlaneL = csnet::make_fastdiv(R.NPL / 2);
+  return true;
 }
 
 size_t mix_smem_bytes(const csnet::MixArgs& A) {
@@ -360,10 +399,17 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     if (!make_il(*P, op, N, ext_ptrs, &A)) return fail(CSNET_E_UNSUPPORTED, "ILBLOCK op does not fit shared memory");
     const int tiles_y = (A.H + A.TH - 1) / A.TH;
     dim3 grid(A.tiles_x * tiles_y, 1, N);
+    CUtensorMap tmH, tmL;
+    memset(&tmH, 0, sizeof tmH);
+    memset(&tmL, 0, sizeof tmL);
+    if (A.tma_h && !encode_plane_map(&tmH, A.xh, N, A.Chi, A.H, A.W, A.RWh, A.RHh, A.Chi))
+      return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (hi input)");
+    if (A.tma_l && !encode_plane_map(&tmL, A.xl, N, A.Cli, A.H / 2, A.W / 2, A.RWl, A.RHl, A.Cli))
+      return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (lo input)");
     if (D.dtype == CSNET_F16)
-      csnet::il_block_kernel<__half><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A);
+      csnet::il_block_kernel<__half><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A, tmH, tmL);
     else
-      csnet::il_block_kernel<__nv_bfloat16><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A);
+      csnet::il_block_kernel<__nv_bfloat16><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A, tmH, tmL);
   } else {
     const csnet_path_desc& q = op.paths[0];
     const csnet_tensor_desc& S = P->tensors[q.src];
