@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -254,8 +255,9 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   A.ML16 = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
   A.rowsAh = A.K8 > A.Cho ? A.K8 : A.Cho;
   A.rowsAl = A.Clo > 0 ? (A.K8 > A.Clo ? A.K8 : A.Clo) : A.Cli;
-  A.tma_h = (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
-  A.tma_l = ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
+  static const bool use_tma = [] { const char* e = getenv("CSNET_TMA"); return e && e[0] == '1'; }();   // opt-in until the 16-byte start-alignment rule is met
+  A.tma_h = use_tma && (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
+  A.tma_l = use_tma && ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
   static const int cand[][2] = {{32, 64}, {32, 32}, {16, 64}, {16, 32}, {16, 16}, {8, 16}};
   double best = -1;
   for (auto& c : cand) {
