@@ -110,7 +110,8 @@ typedef struct {
   int64_t bias_off;       /* blob offset of bias[dst.C] or -1 */
   int64_t slope_off;      /* blob offset of PReLU slope[dst.C] or -1 */
   csnet_path_desc paths[CSNET_MAX_PATHS];
-  int64_t ext_off[CSNET_MAX_EXT];   /* kind-specific blob offsets, -1 when unused */
+  int64_t ext_off[CSNET_MAX_EXT];   /* kind-specific blob offsets, -1 when unused.  CSNET_OP_MIX: ext_off[23] == 1
+                                       forbids the tensor-core kernel (weights do not fit the 16-bit operand type) */
 } csnet_op_desc;
 
 typedef struct csnet_plan csnet_plan;

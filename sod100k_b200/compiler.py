@@ -66,7 +66,8 @@ def _np(v) -> np.ndarray:
 
 
 class _Lowering:
-    def __init__(self, layer_config, params: Mapping[str, object], H: int, W: int, act_dtype: int, fuse: bool = True):
+    def __init__(self, layer_config, params: Mapping[str, object], H: int, W: int, act_dtype: int, fuse=True,
+                 tensor_core=True):
         if H % 16 or W % 16:
             # the reference's own callers enforce this (CSNet/test.py:80-85); its branch sums fail otherwise
             raise ValueError(f"input size {H}x{W} must be a multiple of 16")
@@ -76,7 +77,21 @@ class _Lowering:
         self.dt = act_dtype
         # fuse: True / False, or a collection of block prefixes to fuse (tests isolate one block that way)
         self.fuse = fuse if act_dtype in (ir.F16, ir.BF16) else False
+        self.tensor_core = tensor_core       # True / False / collection of op-name prefixes allowed on mix_tc.cuh
         self.b = ir.Builder()
+        self._wmax: Dict[int, float] = {}
+
+    def finalize_flags(self, prog: ir.Program):
+        """ext_off[23] = 1 vetoes the tensor-core MIX kernel for an op: requested off, or folded weights that do
+        not fit the 16-bit operand type."""
+        lim = 6.0e4 if self.dt == ir.F16 else 3.0e38
+        for o in prog.ops:
+            if o.kind != ir.OP_MIX:
+                continue
+            allowed = self.tensor_core is True or (self.tensor_core and any(o.name.startswith(x) for x in self.tensor_core))
+            big = any(self._wmax.get(q.w_off, 0.0) >= lim for q in o.paths if q.ksize > 0)
+            if not allowed or big:
+                o.ext_off = [-1] * 23 + [1]
 
     # ---- parameters -----------------------------------------------------------------------------
     def p(self, key: str) -> np.ndarray:
@@ -92,7 +107,9 @@ class _Lowering:
     def conv_w(self, w: np.ndarray) -> int:
         """[cout][cin][k][k] -> blob layout [cin][k*k][cout]."""
         co, ci, kh, kw = w.shape
-        return self.b.param(np.transpose(w.reshape(co, ci, kh * kw), (1, 2, 0)))
+        off = self.b.param(np.transpose(w.reshape(co, ci, kh * kw), (1, 2, 0)))
+        self._wmax[off] = float(np.abs(w).max()) if w.size else 0.0
+        return off
 
     def dims(self, t: int):
         d = self.b.prog.tensors[t]
@@ -287,13 +304,14 @@ class _Lowering:
         out = b.tensor(cls_w.shape[0], self.H, self.W, ir.F32, external=1, name="logits")
         b.op(ir.OP_MIX, out, [ir.Path(low, cls_w.shape[0], cls_w.shape[0], ksize=0, up=self.H // Hf)], name="upsample")
         prog = b.finish(reuse=reuse)
+        self.finalize_flags(prog)
         prog.input, prog.output = x, out
         return prog
 
 
 def compile_csnet(layer_config, params: Mapping[str, object], H: int, W: int, dtype="fp32",
-                  reuse_arena: bool = True, fuse: bool = True) -> ir.Program:
+                  reuse_arena: bool = True, fuse=True, tensor_core=True) -> ir.Program:
     """layer_config: the reference's pickle structure (list of [in_split, out_split(, dil_split)] + stages);
     params: state_dict-like mapping (torch tensors or numpy arrays); returns the eval-mode program."""
     dt = ir.DTYPE_NAMES[dtype] if isinstance(dtype, str) else int(dtype)
-    return _Lowering(layer_config, params, H, W, dt, fuse).run(reuse_arena)
+    return _Lowering(layer_config, params, H, W, dt, fuse, tensor_core).run(reuse_arena)

@@ -15,6 +15,7 @@
 #include "../../include/csnet_b200.h"
 #include "generic_ops.cuh"
 #include "il_block.cuh"
+#include "mix_tc.cuh"
 
 namespace {
 
@@ -39,7 +40,7 @@ size_t dtype_size(int dt) { return dt == CSNET_F32 ? 4 : 2; }
 // ------------------------------------------------------------------------------------------------
 constexpr int kThreads = 256;
 
-__global__ void __launch_bounds__(kThreads) mix_generic_kernel(const __grid_constant__ csnet::MixArgs A) {
+__global__ void __launch_bounds__(kThreads, 2) mix_generic_kernel(const __grid_constant__ csnet::MixArgs A) {
   extern __shared__ float ws[];
   const int co_base = blockIdx.y * csnet::kMixCT;
   csnet::mix_stage_weights(A, co_base, ws, threadIdx.x, kThreads);
@@ -61,6 +62,12 @@ __global__ void __launch_bounds__(kThreads) dw_generic_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+struct TcChoice {
+  int mt = 0;            // 0: generic kernel; else number of m16 tiles of the tensor-core kernel
+  int dtype = 0;         // CSNET_F16 / CSNET_BF16 operand type
+  int xs_halves = 0;
+};
+
 struct csnet_plan {
   int device = 0;
   int max_batch = 0;
@@ -74,6 +81,7 @@ struct csnet_plan {
   size_t mix_smem_max = 0;
   size_t il_smem_max = 0;
   std::vector<size_t> op_smem;
+  std::vector<TcChoice> op_tc;
 
   void* tensor_ptr(int t, int N, const void* const* ext) const {
     const csnet_tensor_desc& d = tensors[t];
@@ -296,6 +304,57 @@ size_t mix_smem_bytes(const csnet::MixArgs& A) {
   return mx * sizeof(float);
 }
 
+// Can this MIX op run on the tensor-core kernel (mix_tc.cuh)?  Needs 16-bit operands somewhere, stride-1 conv
+// paths and at most 80 output channels; ext_off[23] == 1 is the compiler's veto (weights overflow 16 bits).
+TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
+  TcChoice c;
+  static const bool enabled = [] { const char* e = getenv("CSNET_TC"); return !(e && e[0] == '0'); }();
+  if (!enabled || op.kind != CSNET_OP_MIX || op.ext_off[23] == 1) return c;
+  const csnet_tensor_desc& D = P.tensors[op.dst];
+  int dt = D.dtype != CSNET_F32 ? D.dtype : -1, pad = 0, nconv = 0;
+  for (int p = 0; p < op.n_paths; ++p) {
+    const csnet_path_desc& q = op.paths[p];
+    if (q.ksize == 0) continue;
+    ++nconv;
+    if (q.stride != 1) return c;
+    if (dt < 0 && P.tensors[q.src].dtype != CSNET_F32) dt = P.tensors[q.src].dtype;
+    pad = q.pad > pad ? q.pad : pad;
+  }
+  if (dt < 0 || nconv == 0 || D.C > 80) return c;
+  c.mt = (D.C + 15) / 16;
+  c.dtype = dt;
+  c.xs_halves = csnet::tc_plane_halves(pad);
+  return c;
+}
+
+size_t tc_smem_bytes(const TcChoice& c) { return ((size_t)8 * c.xs_halves + (size_t)9 * c.mt * 16 * 8) * 2; }
+
+template <typename T>
+void launch_mix_tc_t(int mt, dim3 grid, size_t smem, cudaStream_t st, const csnet::MixArgs& A, const csnet::TcGeom& G) {
+  switch (mt) {
+    case 1: csnet::mix_tc_kernel<T, 1><<<grid, csnet::kTcThreads, smem, st>>>(A, G); break;
+    case 2: csnet::mix_tc_kernel<T, 2><<<grid, csnet::kTcThreads, smem, st>>>(A, G); break;
+    case 3: csnet::mix_tc_kernel<T, 3><<<grid, csnet::kTcThreads, smem, st>>>(A, G); break;
+    case 4: csnet::mix_tc_kernel<T, 4><<<grid, csnet::kTcThreads, smem, st>>>(A, G); break;
+    default: csnet::mix_tc_kernel<T, 5><<<grid, csnet::kTcThreads, smem, st>>>(A, G); break;
+  }
+}
+
+void launch_mix_tc(const TcChoice& c, dim3 grid, size_t smem, cudaStream_t st, const csnet::MixArgs& A, const csnet::TcGeom& G) {
+  if (c.dtype == CSNET_F16) launch_mix_tc_t<__half>(c.mt, grid, smem, st, A, G);
+  else launch_mix_tc_t<__nv_bfloat16>(c.mt, grid, smem, st, A, G);
+}
+
+template <typename T>
+cudaError_t set_tc_smem_t(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -344,11 +403,25 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   if (e != cudaSuccess) return cleanup(CSNET_E_NOMEM, std::string("cudaMalloc(arena): ") + cudaGetErrorString(e));
   // dynamic shared memory each MIX op needs (weights of one cout tile)
   P->op_smem.assign(P->ops.size(), 0);
+  P->op_tc.assign(P->ops.size(), TcChoice());
+  size_t tc_smem_max = 0;
   for (size_t i = 0; i < P->ops.size(); ++i) {
     if (P->ops[i].kind != CSNET_OP_MIX) continue;
+    P->op_tc[i] = choose_tc(*P, P->ops[i]);
+    if (P->op_tc[i].mt > 0 && tc_smem_bytes(P->op_tc[i]) <= 200 * 1024) {
+      P->op_smem[i] = tc_smem_bytes(P->op_tc[i]);
+      tc_smem_max = P->op_smem[i] > tc_smem_max ? P->op_smem[i] : tc_smem_max;
+      continue;
+    }
+    P->op_tc[i] = TcChoice();
     csnet::MixArgs A = make_mix(*P, P->ops[i], 1, nullptr);
     P->op_smem[i] = mix_smem_bytes(A);
     P->mix_smem_max = P->op_smem[i] > P->mix_smem_max ? P->op_smem[i] : P->mix_smem_max;
+  }
+  if (tc_smem_max > 48 * 1024) {
+    e = set_tc_smem_t<__half>((int)tc_smem_max);
+    if (e == cudaSuccess) e = set_tc_smem_t<__nv_bfloat16>((int)tc_smem_max);
+    if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(mix_tc): ") + cudaGetErrorString(e));
   }
   if (P->mix_smem_max > 227 * 1024) return cleanup(CSNET_E_UNSUPPORTED, "MIX op weights exceed shared memory");
   for (size_t i = 0; i < P->ops.size(); ++i) {
@@ -392,7 +465,13 @@ static int check_run_args(csnet_plan* P, int32_t N, const void* const* ext_ptrs,
 static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_ptrs, cudaStream_t stream) {
   const csnet_op_desc& op = P->ops[i];
   const csnet_tensor_desc& D = P->tensors[op.dst];
-  if (op.kind == CSNET_OP_MIX) {
+  if (op.kind == CSNET_OP_MIX && P->op_tc[i].mt > 0) {
+    csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
+    const TcChoice& tc = P->op_tc[i];
+    csnet::TcGeom G{(D.W + csnet::kTcTW - 1) / csnet::kTcTW, tc.xs_halves};
+    dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), 1, N);
+    launch_mix_tc(tc, grid, P->op_smem[i], stream, A, G);
+  } else if (op.kind == CSNET_OP_MIX) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     dim3 grid((D.H * D.W + kThreads - 1) / kThreads, (D.C + csnet::kMixCT - 1) / csnet::kMixCT, N);
     mix_generic_kernel<<<grid, kThreads, P->op_smem[i], stream>>>(A);

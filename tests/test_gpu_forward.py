@@ -180,7 +180,7 @@ def test_fused_ilblock_kernel_matches_generic_ops(tag, hw, dtype):
         cfg, sd = fixtures.checkpoint(tag)
     h, w = hw
     x = torch.from_numpy(synth.randn_images(3, h, w, 31)).cuda()
-    base = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse=False)
+    base = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse=False, tensor_core=False)
     p0 = runtime.Plan(base, max_batch=3)
     p0.forward(x)
     full = compiler.compile_csnet(cfg, sd, h, w, dtype, fuse=True)
@@ -188,7 +188,7 @@ def test_fused_ilblock_kernel_matches_generic_ops(tag, hw, dtype):
     assert len(fused_names) >= 3
     rel = 4e-3 if dtype == "fp16" else 3e-2       # a few 16-bit ulps of the tensor's max magnitude
     for name in fused_names:
-        prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse={name})
+        prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse={name}, tensor_core=False)
         assert sum(o.kind == 3 for o in prog.ops) == 1
         p1 = runtime.Plan(prog, max_batch=3)
         p1.forward(x)
@@ -204,5 +204,42 @@ def test_fused_ilblock_kernel_matches_generic_ops(tag, hw, dtype):
     # and the whole fused network against the oracle
     pf = runtime.Plan(full, max_batch=3)
     y = torch.sigmoid(pf.forward(x)).cpu()
+    ref = torch.sigmoid(_oracle(cfg, sd, x.cpu().numpy()))
+    assert (y - ref).abs().max().item() <= (SIG_TOL_FP16 if dtype == "fp16" else SIG_TOL_BF16)
+
+
+@pytest.mark.parametrize("tag,hw,dtype", [("csnet-L-x2", (224, 224), "fp16"), ("csnet-L-x2", (96, 160), "fp16"),
+                                          ("csnet-L-x1", (64, 64), "bf16"), ("init-3br", (128, 128), "fp16")])
+def test_tensor_core_mix_kernel_matches_generic_ops(tag, hw, dtype):
+    """mix_tc.cuh in isolation: enable it for the MIX ops of ONE module group at a time (everything upstream is the
+    generic path, so inputs are bit-identical) and compare the first tap downstream."""
+    if tag.startswith("init"):
+        cfg, sd, _ = fixtures.synthetic_model(tag)
+    else:
+        cfg, sd = fixtures.checkpoint(tag)
+    h, w = hw
+    x = torch.from_numpy(synth.randn_images(2, h, w, 41)).cuda()
+    base = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse=False, tensor_core=False)
+    p0 = runtime.Plan(base, max_batch=2)
+    y0 = p0.forward(x)
+    rel = 6e-3 if dtype == "fp16" else 4e-2
+    groups = [("stage0.0", "stage0.0/0"), ("stage1.1", "stage1.1/1"), ("stage2.0", "stage2.0/0"), ("stage2.0", "stage2.0/1"),
+              ("stage3.0", "stage3.0/1"), ("stage4.2", "stage4.2/0"), ("oct_fuse.fuse.", "oct_fuse.fuse/0"),
+              ("oct_fuse.ms", "oct_fuse.ms/1"), ("oct_fuse.ms", "oct_fuse.ms/2"), ("oct_fuse.fuse1x1", "oct_fuse.fuse1x1/0")]
+    for prefix, tap in groups:
+        prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse=False, tensor_core={prefix})
+        if tap not in prog.taps:
+            continue
+        p1 = runtime.Plan(prog, max_batch=2)
+        p1.forward(x)
+        ref, got = p0.read_tensor(base.taps[tap], 2), p1.read_tensor(prog.taps[tap], 2)
+        err = (got - ref).abs().max().item()
+        assert err <= rel * max(1.0, ref.abs().max().item()), (prefix, tap, err, ref.abs().max().item())
+        p1.close()
+    prog = compiler.compile_csnet(cfg, sd, h, w, dtype, fuse=False, tensor_core={"cls_layer", "upsample"})
+    y1 = runtime.Plan(prog, max_batch=2).forward(x)
+    assert (y1 - y0).abs().max().item() <= rel * max(1.0, y0.abs().max().item())
+    # everything on: fused ILBlocks + tensor-core MIX, against the oracle
+    y = torch.sigmoid(runtime.Plan(compiler.compile_csnet(cfg, sd, h, w, dtype), max_batch=2).forward(x)).cpu()
     ref = torch.sigmoid(_oracle(cfg, sd, x.cpu().numpy()))
     assert (y - ref).abs().max().item() <= (SIG_TOL_FP16 if dtype == "fp16" else SIG_TOL_BF16)
