@@ -65,6 +65,8 @@ typedef struct {
  *   into the read: pre_avg=1 applies avg_pool2d(2,2) first (csnet.py:679-680), pool=k applies
  *   max_pool2d(k,k) next (csnet.py:709-712); the convolution (cross-correlation, zero padding `pad`,
  *   dilation `dil`, stride `stride`) then runs on that pooled grid.
+ *   A plain 1x1 conv path may carry up > 1: the source is bilinearly up-sampled FIRST (same linear map as the
+ *   reference's conv-then-interpolate; used by 16-bit programs when cin <= cout).
  * ksize == 0 — resample-add path: channel c of src is bilinearly up-sampled by the integer factor
  *   `up` (align_corners=False, source index (dst+0.5)/up-0.5 clamped at 0 — F.interpolate at
  *   csnet.py:705-707 and :382-385) and added to out[cout0+c]; cin == cout.

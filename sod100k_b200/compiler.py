@@ -67,7 +67,7 @@ def _np(v) -> np.ndarray:
 
 class _Lowering:
     def __init__(self, layer_config, params: Mapping[str, object], H: int, W: int, act_dtype: int, fuse=True,
-                 tensor_core=True):
+                 tensor_core=True, upsample_inputs=None):
         if H % 16 or W % 16:
             # the reference's own callers enforce this (CSNet/test.py:80-85); its branch sums fail otherwise
             raise ValueError(f"input size {H}x{W} must be a multiple of 16")
@@ -77,7 +77,9 @@ class _Lowering:
         self.dt = act_dtype
         # fuse: True / False, or a collection of block prefixes to fuse (tests isolate one block that way)
         self.fuse = fuse if act_dtype in (ir.F16, ir.BF16) else False
-        self.tensor_core = tensor_core       # True / False / collection of op-name prefixes allowed on mix_tc.cuh
+        self.tensor_core = tensor_core       # True / False / collection of op-name prefixes allowed on the fast kernels
+        # 1x1 up-paths with cin <= cout: up-sample the conv input instead of its output (default: 16-bit programs)
+        self.upsample_inputs = (act_dtype != ir.F32) if upsample_inputs is None else upsample_inputs
         self.b = ir.Builder()
         self._wmax: Dict[int, float] = {}
 
@@ -86,10 +88,10 @@ class _Lowering:
         not fit the 16-bit operand type."""
         lim = 6.0e4 if self.dt == ir.F16 else 3.0e38
         for o in prog.ops:
-            if o.kind != ir.OP_MIX:
+            if o.kind not in (ir.OP_MIX, ir.OP_DW):
                 continue
             allowed = self.tensor_core is True or (self.tensor_core and any(o.name.startswith(x) for x in self.tensor_core))
-            big = any(self._wmax.get(q.w_off, 0.0) >= lim for q in o.paths if q.ksize > 0)
+            big = o.kind == ir.OP_MIX and any(self._wmax.get(q.w_off, 0.0) >= lim for q in o.paths if q.ksize > 0)
             if not allowed or big:
                 o.ext_off = [-1] * 23 + [1]
 
@@ -152,7 +154,11 @@ class _Lowering:
                 cin = ci[i + 1] - ci[i]
                 w = W4[co[j]:co[j + 1], ci[i]:ci[i + 1]] * s[:, None, None, None]
                 common = dict(pre_avg=int(stride == 2), ksize=ksize, pad=pad, w_off=self.conv_w(w))
-                if i > j:                                            # conv at low res, then bilinear (:702-707)
+                if i > j and ksize == 1 and stride == 1 and self.upsample_inputs and cin <= cj:
+                    # 16-bit programs, 1x1, fewer input than output channels: up-sample the conv INPUT instead of its
+                    # output (identical linear map, cin instead of cout bilinear evaluations, no scratch tensor)
+                    paths.append(ir.Path(x, cin, cj, ksize=1, up=2 ** (i - j), w_off=self.conv_w(w)))
+                elif i > j:                                          # conv at low res, then bilinear (:702-707)
                     _, Hi, Wi = self.dims(x)
                     low = self.b.tensor(cj, Hi // stride, Wi // stride, ir.F32, name=f"{prefix}/low{i}to{j}")
                     self.b.op(ir.OP_MIX, low, [ir.Path(x, cin, cj, **common)], name=f"{prefix}.low{i}to{j}")
@@ -310,8 +316,8 @@ class _Lowering:
 
 
 def compile_csnet(layer_config, params: Mapping[str, object], H: int, W: int, dtype="fp32",
-                  reuse_arena: bool = True, fuse=True, tensor_core=True) -> ir.Program:
+                  reuse_arena: bool = True, fuse=True, tensor_core=True, upsample_inputs=None) -> ir.Program:
     """layer_config: the reference's pickle structure (list of [in_split, out_split(, dil_split)] + stages);
     params: state_dict-like mapping (torch tensors or numpy arrays); returns the eval-mode program."""
     dt = ir.DTYPE_NAMES[dtype] if isinstance(dtype, str) else int(dtype)
-    return _Lowering(layer_config, params, H, W, dt, fuse, tensor_core).run(reuse_arena)
+    return _Lowering(layer_config, params, H, W, dt, fuse, tensor_core, upsample_inputs).run(reuse_arena)

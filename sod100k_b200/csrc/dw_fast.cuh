@@ -1,0 +1,67 @@
+// dw_fast.cuh — depthwise 3x3 (pad 1) + bias + PReLU on 16-bit planar tensors, W % 4 == 0
+// (SimplifiedGOctConvBR.forward, CSNet/model/csnet.py:838-851, for the blocks the fused ILBlock kernel does not cover).
+// A thread produces a 4-pixel-wide, RUN-row strip of one plane: all (RUN+2) x 3 loads are issued before any math,
+// 8-byte stores; fp32 accumulate.
+#pragma once
+#include "generic_ops.cuh"
+#include "il_block.cuh"
+
+namespace csnet {
+
+constexpr int kDwfThreads = 256;
+constexpr int kDwfRun = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kDwfThreads) dw_fast_kernel(const __grid_constant__ DwArgs A) {
+  const int G = A.W >> 2, nruns = (A.H + kDwfRun - 1) / kDwfRun;
+  const int task = blockIdx.x * kDwfThreads + threadIdx.x;
+  if (task >= G * nruns) return;
+  const int gi = task % G, run = task / G;
+  const int x = 4 * gi, ra = run * kDwfRun, c = blockIdx.y, H = A.H, W = A.W;
+  const size_t plane_off = ((size_t)blockIdx.z * A.C + c) * (size_t)H * W;
+  const uint16_t* plane = reinterpret_cast<const uint16_t*>(A.src) + plane_off + x;
+  uint2 mid[kDwfRun + 2];
+  uint32_t lft[kDwfRun + 2], rgt[kDwfRun + 2];
+#pragma unroll
+  for (int i = 0; i < kDwfRun + 2; ++i) {
+    const int r = ra - 1 + i;
+    const bool ok = r >= 0 && r < H;
+    mid[i] = ok ? *reinterpret_cast<const uint2*>(plane + (size_t)r * W) : make_uint2(0u, 0u);
+    lft[i] = (ok && x > 0) ? *reinterpret_cast<const uint32_t*>(plane + (size_t)r * W - 2) : 0u;
+    rgt[i] = (ok && x + 4 < W) ? *reinterpret_cast<const uint32_t*>(plane + (size_t)r * W + 4) : 0u;
+  }
+  float w[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) w[i] = __ldg(A.w + c * 9 + i);
+  const float bias = A.bias ? __ldg(A.bias + c) : 0.f;
+  const bool has_slope = A.slope != nullptr;
+  const float slope = has_slope ? __ldg(A.slope + c) : 1.f;
+  float rows[kDwfRun + 2][6];
+#pragma unroll
+  for (int i = 0; i < kDwfRun + 2; ++i) {
+    const float2 a = Pack<T>::to_f2(lft[i]), b = Pack<T>::to_f2(mid[i].x), c2 = Pack<T>::to_f2(mid[i].y), d = Pack<T>::to_f2(rgt[i]);
+    rows[i][0] = a.y; rows[i][1] = b.x; rows[i][2] = b.y; rows[i][3] = c2.x; rows[i][4] = c2.y; rows[i][5] = d.x;
+  }
+  uint16_t* out = reinterpret_cast<uint16_t*>(A.dst) + plane_off + x;
+#pragma unroll
+  for (int i = 0; i < kDwfRun; ++i) {
+    const int r = ra + i;
+    if (r < H) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v = bias;
+        v = fmaf(rows[i][k], w[0], v); v = fmaf(rows[i][k + 1], w[1], v); v = fmaf(rows[i][k + 2], w[2], v);
+        v = fmaf(rows[i + 1][k], w[3], v); v = fmaf(rows[i + 1][k + 1], w[4], v); v = fmaf(rows[i + 1][k + 2], w[5], v);
+        v = fmaf(rows[i + 2][k], w[6], v); v = fmaf(rows[i + 2][k + 1], w[7], v); v = fmaf(rows[i + 2][k + 2], w[8], v);
+        o[k] = has_slope ? prelu(v, slope) : v;
+      }
+      uint2 v;
+      v.x = Pack<T>::from_f2(o[0], o[1]);
+      v.y = Pack<T>::from_f2(o[2], o[3]);
+      *reinterpret_cast<uint2*>(out + (size_t)r * W) = v;
+    }
+  }
+}
+
+}  // namespace csnet

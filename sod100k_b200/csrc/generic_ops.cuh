@@ -161,7 +161,7 @@ CSNET_DEV void mix_thread(const MixArgs& A, const float* ws, int n, int oy, int 
     const int64_t plane_sz = (int64_t)P.H * P.W;
     if (P.ksize > 0) {
       const int div = (P.pre_avg ? 2 : 1) * P.pool;
-      const int Hc = P.H / div, Wc = P.W / div;
+      const int Hc = P.up > 1 ? P.H * P.up : P.H / div, Wc = P.up > 1 ? P.W * P.up : P.W / div;
       const int kk = P.ksize * P.ksize;
       for (int ci = 0; ci < P.cin; ++ci) {
         const int64_t plane = ((int64_t)n * P.C + P.c0 + ci) * plane_sz;
@@ -171,7 +171,9 @@ CSNET_DEV void mix_thread(const MixArgs& A, const float* ws, int n, int oy, int 
             const int x = ox * P.stride - P.pad + kx * P.dil;
             const float* wr = ws + off + (ci * kk + ky * P.ksize + kx) * kMixCT;
             if (y < 0 || y >= Hc || x < 0 || x >= Wc) continue;   // zero padding
-            const float v = fetch_pooled(P, plane, y, x);
+            // up > 1 on a (1x1) conv path: the source is bilinearly up-sampled BEFORE the conv (same linear map as
+            // the reference's conv-then-interpolate, csnet.py:702-707)
+            const float v = P.up > 1 ? bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, y, x) : fetch_pooled(P, plane, y, x);
 #pragma unroll
             for (int t = 0; t < kMixCT; ++t) acc[t] += v * wr[t];
           }

@@ -25,6 +25,7 @@ constexpr int kTcTH = 8, kTcTW = 32;
 struct TcGeom {
   int32_t tiles_x;
   int32_t xs_halves;      // allocated halves per staged channel plane (max over groups)
+  int32_t kc;             // input channels per staged chunk (8, 16 or 32)
 };
 
 __host__ __device__ inline int tc_plane_halves(int pad) {
@@ -32,12 +33,21 @@ __host__ __device__ inline int tc_plane_halves(int pad) {
   n = (n + 15) / 16 * 16 + 8;          // == 8 (mod 16): the four channel pairs of a B fragment hit distinct banks
   return n;
 }
+__host__ __device__ inline int tc_wrow(int kc) { return kc + 8; }   // padded Ws row: conflict-free A-fragment loads
+
+// Value a conv path sees at conv-grid position (cy, cx): pooled source, or (1x1 paths with up > 1) the source
+// bilinearly up-sampled first — conv1x1(up(x)) == up(conv1x1(x)), the order gOctaveConv uses (csnet.py:702-707).
+__device__ __forceinline__ float tc_fetch(const MixPath& P, int64_t plane, int cy, int cx) {
+  if (P.up > 1) return bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, cy, cx);
+  return fetch_pooled(P, plane, cy, cx);
+}
 
 template <typename T, int MT>
 __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_constant__ MixArgs A, const TcGeom G) {
   extern __shared__ __align__(16) uint16_t tc_smem[];
-  uint16_t* Xs = tc_smem;                                  // [8][xs_halves]
-  uint16_t* Ws = tc_smem + 8 * G.xs_halves;                // [9][MT*16][8]
+  const int KC = G.kc, WR = tc_wrow(KC);
+  uint16_t* Xs = tc_smem;                                  // [KC][xs_halves]
+  uint16_t* Ws = tc_smem + KC * G.xs_halves;               // [9][MT*16][WR]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int n = blockIdx.z;
@@ -59,28 +69,61 @@ __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_cons
     int p1 = p0 + 1, pad = P0.pad;
     while (p1 < A.n_paths) {
       const MixPath& Q = A.p[p1];
-      if (Q.ksize == 0 || Q.src != P0.src || Q.c0 != P0.c0 || Q.cin != P0.cin || Q.pre_avg != P0.pre_avg || Q.pool != P0.pool) break;
+      if (Q.ksize == 0 || Q.src != P0.src || Q.c0 != P0.c0 || Q.cin != P0.cin || Q.pre_avg != P0.pre_avg ||
+          Q.pool != P0.pool || Q.up != P0.up)
+        break;
       pad = Q.pad > pad ? Q.pad : pad;
       ++p1;
     }
     const int XH = kTcTH + 2 * pad, XW = kTcTW + 2 * pad, PS = tc_plane_halves(pad);
     const int div = (P0.pre_avg ? 2 : 1) * P0.pool;
-    const int Hc = P0.H / div, Wc = P0.W / div;
+    const int Hc = P0.up > 1 ? P0.H * P0.up : P0.H / div, Wc = P0.up > 1 ? P0.W * P0.up : P0.W / div;
     const int64_t plane_sz = (int64_t)P0.H * P0.W;
-    for (int c0 = 0; c0 < P0.cin; c0 += 8) {
+    const int xiters = (XW + 31) >> 5;
+    for (int c0 = 0; c0 < P0.cin; c0 += KC) {
+      const int kc_live = (P0.cin - c0) < KC ? (P0.cin - c0) : KC;
+      const int kc8 = (kc_live + 7) & ~7;                   // channels actually multiplied (multiple of 8, rest zero)
       __syncthreads();                                     // previous chunk's readers are done
-      // ---- stage the input window (8 channels) -------------------------------------------------------
-      for (int rt = warp; rt < 8 * XH; rt += kTcThreads / 32) {      // one (channel, window row) per warp pass
-        const int ch = rt / XH, y = rt - ch * XH;
-        const int cy = oy0 - pad + y;
-        const bool row_ok = c0 + ch < P0.cin && cy >= 0 && cy < Hc;
-        const int64_t plane = ((int64_t)n * P0.C + P0.c0 + c0 + ch) * plane_sz;
-        uint16_t* dst = Xs + ch * PS + y * XW;
-        for (int x = lane; x < XW; x += 32) {
-          const int cx = ox0 - pad + x;
-          float v = 0.f;
-          if (row_ok && cx >= 0 && cx < Wc) v = fetch_pooled(P0, plane, cy, cx);
-          dst[x] = (uint16_t)(Pack<T>::from_f2(v, 0.f) & 0xffffu);
+      // ---- stage the input window: 4 (channel, row) tasks per warp pass, loads batched before the stores ----
+      for (int rt0 = warp * 4; rt0 < kc8 * XH; rt0 += (kTcThreads / 32) * 4) {
+        float v[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int rt = rt0 + q;
+          const int ch = rt / XH, y = rt - ch * XH;
+          const int cy = oy0 - pad + y;
+          const bool row_ok = rt < kc8 * XH && ch < kc_live && cy >= 0 && cy < Hc;
+          const int64_t plane = ((int64_t)n * P0.C + P0.c0 + c0 + ch) * plane_sz;
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int x = lane + 32 * it, cx = ox0 - pad + x;
+            v[q][it] = (it < xiters && row_ok && x < XW && cx >= 0 && cx < Wc) ? tc_fetch(P0, plane, cy, cx) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int rt = rt0 + q;
+          if (rt < kc8 * XH) {
+            const int ch = rt / XH, y = rt - ch * XH;
+            uint16_t* dst = Xs + ch * PS + y * XW;
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int x = lane + 32 * it;
+              if (it < xiters && x < XW) dst[x] = (uint16_t)(Pack<T>::from_f2(v[q][it], 0.f) & 0xffffu);
+            }
+          }
+        }
+      }
+      if (XW > 64) {                                        // windows wider than 64 (pad > 16): plain tail loop
+        for (int rt = warp; rt < kc8 * XH; rt += kTcThreads / 32) {
+          const int ch = rt / XH, y = rt - ch * XH, cy = oy0 - pad + y;
+          const bool row_ok = ch < kc_live && cy >= 0 && cy < Hc;
+          const int64_t plane = ((int64_t)n * P0.C + P0.c0 + c0 + ch) * plane_sz;
+          for (int x = 64 + lane; x < XW; x += 32) {
+            const int cx = ox0 - pad + x;
+            const float val = (row_ok && cx >= 0 && cx < Wc) ? tc_fetch(P0, plane, cy, cx) : 0.f;
+            Xs[ch * PS + y * XW + x] = (uint16_t)(Pack<T>::from_f2(val, 0.f) & 0xffffu);
+          }
         }
       }
       for (int p = p0; p < p1; ++p) {
@@ -88,32 +131,35 @@ __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_cons
         const int kk = P.ksize * P.ksize;
         if (p > p0) __syncthreads();                       // Ws of the previous path is no longer read
         // ---- stage this path's weights for the chunk: Ws[tap][m][k] ----------------------------------
-        for (int i = tid; i < kk * M16 * 8; i += kTcThreads) {
-          const int k = i & 7, m = (i >> 3) % M16, tap = (i >> 3) / M16;
+        for (int i = tid; i < kk * M16 * kc8; i += kTcThreads) {
+          const int k = i % kc8, r = i / kc8;
+          const int m = r % M16, tap = r / M16;
           float w = 0.f;
-          if (m >= P.cout0 && m < P.cout0 + P.cout && c0 + k < P.cin)
+          if (m >= P.cout0 && m < P.cout0 + P.cout && k < kc_live)
             w = __ldg(P.w + ((int64_t)(c0 + k) * kk + tap) * P.cout + (m - P.cout0));
-          Ws[i] = (uint16_t)(Pack<T>::from_f2(w, 0.f) & 0xffffu);
+          Ws[(tap * M16 + m) * WR + k] = (uint16_t)(Pack<T>::from_f2(w, 0.f) & 0xffffu);
         }
         __syncthreads();
         // ---- tensor-core accumulate --------------------------------------------------------------------
         const int off = pad - P.pad;                        // this path's window sits `off` inside the staged one
-        const uint16_t* x0 = Xs + (2 * t) * PS + (warp + off) * XW + g + off;
-        for (int ky = 0; ky < P.ksize; ++ky) {
-          for (int kx = 0; kx < P.ksize; ++kx) {
-            const uint16_t* wt = Ws + (ky * P.ksize + kx) * M16 * 8 + g * 8 + 2 * t;
-            uint32_t af[MT][2];
+        for (int ks = 0; ks < kc8; ks += 8) {
+          const uint16_t* x0 = Xs + (ks + 2 * t) * PS + (warp + off) * XW + g + off;
+          for (int ky = 0; ky < P.ksize; ++ky) {
+            for (int kx = 0; kx < P.ksize; ++kx) {
+              const uint16_t* wt = Ws + ((ky * P.ksize + kx) * M16 + g) * WR + ks + 2 * t;
+              uint32_t af[MT][2];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              af[mt][0] = *reinterpret_cast<const uint32_t*>(wt + mt * 128);
-              af[mt][1] = *reinterpret_cast<const uint32_t*>(wt + mt * 128 + 64);
-            }
-            const uint16_t* xt = x0 + (ky * P.dil) * XW + kx * P.dil;
+              for (int mt = 0; mt < MT; ++mt) {
+                af[mt][0] = *reinterpret_cast<const uint32_t*>(wt + mt * 16 * WR);
+                af[mt][1] = *reinterpret_cast<const uint32_t*>(wt + (mt * 16 + 8) * WR);
+              }
+              const uint16_t* xt = x0 + (ky * P.dil) * XW + kx * P.dil;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t b = (uint32_t)xt[j * 8] | ((uint32_t)xt[PS + j * 8] << 16);
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t b = (uint32_t)xt[j * 8] | ((uint32_t)xt[PS + j * 8] << 16);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) Pack<T>::mma(acc[mt][j], af[mt], b);
+                for (int mt = 0; mt < MT; ++mt) Pack<T>::mma(acc[mt][j], af[mt], b);
+              }
             }
           }
         }

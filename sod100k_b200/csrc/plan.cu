@@ -16,6 +16,7 @@
 #include "generic_ops.cuh"
 #include "il_block.cuh"
 #include "mix_tc.cuh"
+#include "dw_fast.cuh"
 
 namespace {
 
@@ -66,7 +67,13 @@ struct TcChoice {
   int mt = 0;            // 0: generic kernel; else number of m16 tiles of the tensor-core kernel
   int dtype = 0;         // CSNET_F16 / CSNET_BF16 operand type
   int xs_halves = 0;
+  int kc = 8;            // input channels per staged chunk
+  int kk = 1;            // largest tap count among the conv paths
 };
+
+size_t tc_smem_bytes(const TcChoice& c) {
+  return ((size_t)c.kc * c.xs_halves + (size_t)c.kk * c.mt * 16 * (c.kc + 8)) * 2;
+}
 
 struct csnet_plan {
   int device = 0;
@@ -164,11 +171,13 @@ int validate(const csnet_plan& P) {
         if (S.H * q.up != D.H || S.W * q.up != D.W) return bad("resample path size");
       } else {
         if (q.ksize != 1 && q.ksize != 3) return bad("ksize must be 1 or 3");
-        if (q.up != 1) return bad("conv path with up != 1 (lower it to conv + resample)");
+        if (q.up < 1) return bad("conv path up < 1");
+        if (q.up > 1 && (q.ksize != 1 || q.pool != 1 || q.pre_avg || q.stride != 1 || q.pad != 0))
+          return bad("input-side up-sampling is only defined for plain 1x1 conv paths");
         if (q.pool < 1 || q.stride < 1 || q.dil < 1 || q.pad < 0) return bad("conv path params");
         const int div = (q.pre_avg ? 2 : 1) * q.pool;
         if (S.H % div || S.W % div) return bad("pooling does not divide the source");
-        const int Hc = S.H / div, Wc = S.W / div;
+        const int Hc = q.up > 1 ? S.H * q.up : S.H / div, Wc = q.up > 1 ? S.W * q.up : S.W / div;
         const int Ho = (Hc + 2 * q.pad - q.dil * (q.ksize - 1) - 1) / q.stride + 1;
         const int Wo = (Wc + 2 * q.pad - q.dil * (q.ksize - 1) - 1) / q.stride + 1;
         if (Ho != D.H || Wo != D.W) return bad("conv path output size != dst");
@@ -311,7 +320,7 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
   static const bool enabled = [] { const char* e = getenv("CSNET_TC"); return !(e && e[0] == '0'); }();
   if (!enabled || op.kind != CSNET_OP_MIX || op.ext_off[23] == 1) return c;
   const csnet_tensor_desc& D = P.tensors[op.dst];
-  int dt = D.dtype != CSNET_F32 ? D.dtype : -1, pad = 0, nconv = 0;
+  int dt = D.dtype != CSNET_F32 ? D.dtype : -1, pad = 0, nconv = 0, kk = 1, cin_max = 0;
   for (int p = 0; p < op.n_paths; ++p) {
     const csnet_path_desc& q = op.paths[p];
     if (q.ksize == 0) continue;
@@ -319,15 +328,22 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
     if (q.stride != 1) return c;
     if (dt < 0 && P.tensors[q.src].dtype != CSNET_F32) dt = P.tensors[q.src].dtype;
     pad = q.pad > pad ? q.pad : pad;
+    kk = q.ksize * q.ksize > kk ? q.ksize * q.ksize : kk;
+    cin_max = q.cin > cin_max ? q.cin : cin_max;
   }
   if (dt < 0 || nconv == 0 || D.C > 80) return c;
   c.mt = (D.C + 15) / 16;
   c.dtype = dt;
   c.xs_halves = csnet::tc_plane_halves(pad);
+  c.kk = kk;
+  c.kc = 8;
+  for (int kc : {32, 16}) {                       // the largest chunk that keeps two CTAs per SM resident
+    TcChoice t = c;
+    t.kc = kc;
+    if (kc <= ((cin_max + 7) & ~7) && tc_smem_bytes(t) <= 100 * 1024) { c.kc = kc; break; }
+  }
   return c;
 }
-
-size_t tc_smem_bytes(const TcChoice& c) { return ((size_t)8 * c.xs_halves + (size_t)9 * c.mt * 16 * 8) * 2; }
 
 template <typename T>
 void launch_mix_tc_t(int mt, dim3 grid, size_t smem, cudaStream_t st, const csnet::MixArgs& A, const csnet::TcGeom& G) {
@@ -468,7 +484,7 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
   if (op.kind == CSNET_OP_MIX && P->op_tc[i].mt > 0) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     const TcChoice& tc = P->op_tc[i];
-    csnet::TcGeom G{(D.W + csnet::kTcTW - 1) / csnet::kTcTW, tc.xs_halves};
+    csnet::TcGeom G{(D.W + csnet::kTcTW - 1) / csnet::kTcTW, tc.xs_halves, tc.kc};
     dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), 1, N);
     launch_mix_tc(tc, grid, P->op_smem[i], stream, A, G);
   } else if (op.kind == CSNET_OP_MIX) {
@@ -501,9 +517,16 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     A.bias = op.bias_off >= 0 ? P->blob + op.bias_off : nullptr;
     A.slope = op.slope_off >= 0 ? P->blob + op.slope_off : nullptr;
     A.src_dtype = S.dtype; A.dst_dtype = D.dtype; A.C = D.C; A.H = D.H; A.W = D.W;
-    const int strips = (D.H + csnet::kDwRows - 1) / csnet::kDwRows;
-    dim3 grid((strips * D.W + kThreads - 1) / kThreads, D.C, N);
-    dw_generic_kernel<<<grid, kThreads, 0, stream>>>(A);
+    if (op.ext_off[23] != 1 && S.dtype == D.dtype && D.dtype != CSNET_F32 && D.W % 4 == 0) {
+      const int tasks = (D.W / 4) * ((D.H + csnet::kDwfRun - 1) / csnet::kDwfRun);
+      dim3 grid((tasks + csnet::kDwfThreads - 1) / csnet::kDwfThreads, D.C, N);
+      if (D.dtype == CSNET_F16) csnet::dw_fast_kernel<__half><<<grid, csnet::kDwfThreads, 0, stream>>>(A);
+      else csnet::dw_fast_kernel<__nv_bfloat16><<<grid, csnet::kDwfThreads, 0, stream>>>(A);
+    } else {
+      const int strips = (D.H + csnet::kDwRows - 1) / csnet::kDwRows;
+      dim3 grid((strips * D.W + kThreads - 1) / kThreads, D.C, N);
+      dw_generic_kernel<<<grid, kThreads, 0, stream>>>(A);
+    }
   }
   CU_CHECK(cudaGetLastError());
   return CSNET_OK;

@@ -50,3 +50,13 @@ def test_size_must_be_multiple_of_16():
     cfg, sd = fixtures.checkpoint("csnet-L-x1")
     with pytest.raises(ValueError):
         compiler.compile_csnet(cfg, sd, 100, 100)
+
+
+def test_emulated_input_side_upsample_paths():
+    """1x1 up-paths lowered as `conv(up(x))` (what 16-bit programs use) equal the reference's `up(conv(x))`."""
+    cfg, sd = fixtures.checkpoint("csnet-L-x2")
+    x = synth.randn_images(1, 64, 64, 12)
+    prog = compiler.compile_csnet(cfg, sd, 64, 64, "fp32", upsample_inputs=True)
+    assert any(q.ksize == 1 and q.up > 1 for o in prog.ops for q in o.paths)
+    y, _ = emu.run(prog, x)
+    assert np.abs(y - _oracle(cfg, sd, x)).max() <= 1e-4
