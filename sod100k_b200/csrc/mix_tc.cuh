@@ -28,8 +28,12 @@ struct TcGeom {
   int32_t kc;             // input channels per staged chunk (8, 16 or 32)
 };
 
+// Staged window of a conv group with halo `pad`: rows [oy0-pad, oy0+8+pad), columns [ox0-padL, ox0-padL+XW) with the
+// left halo rounded up to 4 pixels so every row is a whole number of 8-byte chunks (cp.async / vector friendly).
+__host__ __device__ inline int tc_pad_left(int pad) { return (pad + 3) & ~3; }
+__host__ __device__ inline int tc_xw(int pad) { return (tc_pad_left(pad) + kTcTW + pad + 3) & ~3; }
 __host__ __device__ inline int tc_plane_halves(int pad) {
-  int n = (kTcTH + 2 * pad) * (kTcTW + 2 * pad);
+  int n = (kTcTH + 2 * pad) * tc_xw(pad);
   n = (n + 15) / 16 * 16 + 8;          // == 8 (mod 16): the four channel pairs of a B fragment hit distinct banks
   return n;
 }
@@ -75,54 +79,57 @@ __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_cons
       pad = Q.pad > pad ? Q.pad : pad;
       ++p1;
     }
-    const int XH = kTcTH + 2 * pad, XW = kTcTW + 2 * pad, PS = tc_plane_halves(pad);
+    const int XH = kTcTH + 2 * pad, XW = tc_xw(pad), padL = tc_pad_left(pad), PS = tc_plane_halves(pad);
     const int div = (P0.pre_avg ? 2 : 1) * P0.pool;
     const int Hc = P0.up > 1 ? P0.H * P0.up : P0.H / div, Wc = P0.up > 1 ? P0.W * P0.up : P0.W / div;
     const int64_t plane_sz = (int64_t)P0.H * P0.W;
-    const int xiters = (XW + 31) >> 5;
+    const bool plain = !P0.pre_avg && P0.pool == 1 && P0.up == 1 && P0.dtype != DT_F32;   // raw 16-bit copy
+    const bool vec = plain && (P0.W & 3) == 0;
     for (int c0 = 0; c0 < P0.cin; c0 += KC) {
       const int kc_live = (P0.cin - c0) < KC ? (P0.cin - c0) : KC;
       const int kc8 = (kc_live + 7) & ~7;                   // channels actually multiplied (multiple of 8, rest zero)
       __syncthreads();                                     // previous chunk's readers are done
-      // ---- stage the input window: 4 (channel, row) tasks per warp pass, loads batched before the stores ----
-      for (int rt0 = warp * 4; rt0 < kc8 * XH; rt0 += (kTcThreads / 32) * 4) {
-        float v[4][2];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int rt = rt0 + q;
-          const int ch = rt / XH, y = rt - ch * XH;
-          const int cy = oy0 - pad + y;
-          const bool row_ok = rt < kc8 * XH && ch < kc_live && cy >= 0 && cy < Hc;
-          const int64_t plane = ((int64_t)n * P0.C + P0.c0 + c0 + ch) * plane_sz;
-#pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int x = lane + 32 * it, cx = ox0 - pad + x;
-            v[q][it] = (it < xiters && row_ok && x < XW && cx >= 0 && cx < Wc) ? tc_fetch(P0, plane, cy, cx) : 0.f;
-          }
+      const uint16_t* src16 = reinterpret_cast<const uint16_t*>(P0.src) + ((int64_t)n * P0.C + P0.c0 + c0) * plane_sz;
+      if (vec) {
+        // ---- (a) 8-byte cp.async chunks, zero fill outside the image / beyond the live channels ----------------
+        const int cpr = XW >> 2, total = kc8 * XH * cpr;
+        int i = tid;
+        int row = i / cpr, col = i - row * cpr;            // one division per thread, then incremental
+        const int drow = kTcThreads / cpr, dcol = kTcThreads - drow * cpr;
+        for (; i < total; i += kTcThreads) {
+          const int ch = row / XH, y = row - ch * XH;
+          const int cy = oy0 - pad + y, cx = ox0 - padL + 4 * col;
+          const bool ok = ch < kc_live && cy >= 0 && cy < Hc && cx >= 0 && cx < Wc;
+          cp_async8(Xs + ch * PS + y * XW + 4 * col, ok ? src16 + (int64_t)ch * plane_sz + (int64_t)cy * P0.W + cx : src16, ok);
+          row += drow; col += dcol;
+          if (col >= cpr) { col -= cpr; ++row; }
         }
+        cp_async_wait_all();
+      } else {
+        // ---- (b)/(c) one (channel, row) per warp step, 4 steps batched so the loads overlap --------------------
+        const int nrows = kc8 * XH;
+        for (int rt0 = warp * 4; rt0 < nrows; rt0 += (kTcThreads / 32) * 4) {
+          for (int xb = 0; xb < XW; xb += 32) {
+            const int x = xb + lane, cx = ox0 - padL + x;
+            const bool col_ok = x < XW && cx >= 0 && cx < Wc;
+            float v[4];
+            uint16_t raw[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int rt = rt0 + q;
-          if (rt < kc8 * XH) {
-            const int ch = rt / XH, y = rt - ch * XH;
-            uint16_t* dst = Xs + ch * PS + y * XW;
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-              const int x = lane + 32 * it;
-              if (it < xiters && x < XW) dst[x] = (uint16_t)(Pack<T>::from_f2(v[q][it], 0.f) & 0xffffu);
+            for (int q = 0; q < 4; ++q) {
+              const int rt = rt0 + q, ch = rt / XH, y = rt - ch * XH, cy = oy0 - pad + y;
+              const bool ok = col_ok && rt < nrows && ch < kc_live && cy >= 0 && cy < Hc;
+              v[q] = 0.f; raw[q] = 0;
+              if (ok) {
+                if (plain) raw[q] = __ldg(src16 + (int64_t)ch * plane_sz + (int64_t)cy * P0.W + cx);
+                else v[q] = tc_fetch(P0, ((int64_t)n * P0.C + P0.c0 + c0 + ch) * plane_sz, cy, cx);
+              }
             }
-          }
-        }
-      }
-      if (XW > 64) {                                        // windows wider than 64 (pad > 16): plain tail loop
-        for (int rt = warp; rt < kc8 * XH; rt += kTcThreads / 32) {
-          const int ch = rt / XH, y = rt - ch * XH, cy = oy0 - pad + y;
-          const bool row_ok = ch < kc_live && cy >= 0 && cy < Hc;
-          const int64_t plane = ((int64_t)n * P0.C + P0.c0 + c0 + ch) * plane_sz;
-          for (int x = 64 + lane; x < XW; x += 32) {
-            const int cx = ox0 - pad + x;
-            const float val = (row_ok && cx >= 0 && cx < Wc) ? tc_fetch(P0, plane, cy, cx) : 0.f;
-            Xs[ch * PS + y * XW + x] = (uint16_t)(Pack<T>::from_f2(val, 0.f) & 0xffffu);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int rt = rt0 + q, ch = rt / XH, y = rt - ch * XH;
+              if (rt < nrows && x < XW)
+                Xs[ch * PS + y * XW + x] = plain ? raw[q] : (uint16_t)(Pack<T>::from_f2(v[q], 0.f) & 0xffffu);
+            }
           }
         }
       }
@@ -141,9 +148,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_cons
         }
         __syncthreads();
         // ---- tensor-core accumulate --------------------------------------------------------------------
-        const int off = pad - P.pad;                        // this path's window sits `off` inside the staged one
+        const int off = pad - P.pad, offx = padL - P.pad;   // this path's window sits inside the staged one
         for (int ks = 0; ks < kc8; ks += 8) {
-          const uint16_t* x0 = Xs + (ks + 2 * t) * PS + (warp + off) * XW + g + off;
+          const uint16_t* x0 = Xs + (ks + 2 * t) * PS + (warp + off) * XW + g + offx;
           for (int ky = 0; ky < P.ksize; ++ky) {
             for (int kx = 0; kx < P.ksize; ++kx) {
               const uint16_t* wt = Ws + ((ky * P.ksize + kx) * M16 + g) * WR + ks + 2 * t;
