@@ -4,12 +4,13 @@
 //
 // Implicit GEMM with the output pixels as the N dimension: D[cout][pixel] += W[cout][(ci,tap)] . X[(ci,tap)][pixel].
 // A CTA owns an 8 x 32 tile of output pixels of one image and ALL output channels (MT m16 tiles); each of its 8
-// warps owns one tile row (four n8 pixel tiles).  K is walked per conv path in chunks of 8 input channels:
-//   stage   Xs[8][XH x XW]  = the chunk's input window at CONV resolution: the reference's avg_pool2d / max_pool2d
-//           pre-ops are applied once per staged element (not per tap), zero outside the image (= conv padding);
-//           consecutive paths that read the same source slice with the same pre-ops (the five dilations of an
-//           MSBlock) share one staged window with the largest halo.
-//           Ws[tap][MT*16][8] = the chunk's weights, fp32 blob -> 16-bit, zero rows outside the path's cout slice
+// warps owns one tile row (four n8 pixel tiles).  K is walked per conv path in chunks of KC (8/16/32) input channels:
+//   stage   Xs[KC][XH x XW] = the chunk's input window at CONV resolution.  Plain 16-bit sources are copied with
+//           8-byte cp.async (zero fill outside the image = conv padding); pooled / averaged / up-sampled / fp32
+//           sources are computed once per staged element (not per tap).  Consecutive paths that read the same
+//           source slice with the same pre-ops (the five dilations of an MSBlock) share one window with the
+//           largest halo.  All staging loops are division-free: a warp owns whole channels, lanes run along rows.
+//           Ws[tap][MT*16][KC+8] = the chunk's weights, fp32 blob -> 16-bit, zero outside the path's cout slice
 //   mma     per tap: B fragment = two 16-bit loads (channels 2t, 2t+1 at pixel g, shifted by the tap offset — any
 //           dilation works since no ldmatrix alignment is involved), A fragment = two 32-bit loads, mma.sync m16n8k8
 //   epilogue resample-add paths (bilinear from the low-resolution scratch), bias, PReLU, store (16-bit or fp32).
@@ -20,6 +21,7 @@
 namespace csnet {
 
 constexpr int kTcThreads = 256;
+constexpr int kTcWarps = kTcThreads / 32;
 constexpr int kTcTH = 8, kTcTW = 32;
 
 struct TcGeom {
@@ -28,16 +30,19 @@ struct TcGeom {
   int32_t kc;             // input channels per staged chunk (8, 16 or 32)
 };
 
-// Staged window of a conv group with halo `pad`: rows [oy0-pad, oy0+8+pad), columns [ox0-padL, ox0-padL+XW) with the
-// left halo rounded up to 4 pixels so every row is a whole number of 8-byte chunks (cp.async / vector friendly).
+// Staged window of a conv group with halo `pad`: rows [oy0-pad, oy0+8+pad); columns start at ox0-padL with the left
+// halo rounded up to 4 pixels so every row is a whole number of 8-byte chunks.  cp.async windows are 32 or 64 wide
+// (power of two: shift/mask indexing); computed windows are exactly as wide as needed.
 __host__ __device__ inline int tc_pad_left(int pad) { return (pad + 3) & ~3; }
-__host__ __device__ inline int tc_xw(int pad) { return (tc_pad_left(pad) + kTcTW + pad + 3) & ~3; }
+__host__ __device__ inline int tc_xw_vec(int pad) { return pad == 0 ? 32 : 64; }
+__host__ __device__ inline int tc_xw_exact(int pad) { return (tc_pad_left(pad) + kTcTW + pad + 3) & ~3; }
 __host__ __device__ inline int tc_plane_halves(int pad) {
-  int n = (kTcTH + 2 * pad) * tc_xw(pad);
+  int n = (kTcTH + 2 * pad) * tc_xw_vec(pad);
   n = (n + 15) / 16 * 16 + 8;          // == 8 (mod 16): the four channel pairs of a B fragment hit distinct banks
   return n;
 }
 __host__ __device__ inline int tc_wrow(int kc) { return kc + 8; }   // padded Ws row: conflict-free A-fragment loads
+constexpr int kTcMaxPad = 16;                                          // 3x3 with dilation <= 16
 
 // Value a conv path sees at conv-grid position (cy, cx): pooled source, or (1x1 paths with up > 1) the source
 // bilinearly up-sampled first — conv1x1(up(x)) == up(conv1x1(x)), the order gOctaveConv uses (csnet.py:702-707).
@@ -47,7 +52,7 @@ __device__ __forceinline__ float tc_fetch(const MixPath& P, int64_t plane, int c
 }
 
 template <typename T, int MT>
-__global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_constant__ MixArgs A, const TcGeom G) {
+__global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(const __grid_constant__ MixArgs A, const TcGeom G) {
   extern __shared__ __align__(16) uint16_t tc_smem[];
   const int KC = G.kc, WR = tc_wrow(KC);
   uint16_t* Xs = tc_smem;                                  // [KC][xs_halves]
@@ -79,88 +84,90 @@ __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_cons
       pad = Q.pad > pad ? Q.pad : pad;
       ++p1;
     }
-    const int XH = kTcTH + 2 * pad, XW = tc_xw(pad), padL = tc_pad_left(pad), PS = tc_plane_halves(pad);
+    const int cin = P0.cin, srcW = P0.W;
     const int div = (P0.pre_avg ? 2 : 1) * P0.pool;
     const int Hc = P0.up > 1 ? P0.H * P0.up : P0.H / div, Wc = P0.up > 1 ? P0.W * P0.up : P0.W / div;
     const int64_t plane_sz = (int64_t)P0.H * P0.W;
     const bool plain = !P0.pre_avg && P0.pool == 1 && P0.up == 1 && P0.dtype != DT_F32;   // raw 16-bit copy
-    const bool vec = plain && (P0.W & 3) == 0;
-    for (int c0 = 0; c0 < P0.cin; c0 += KC) {
-      const int kc_live = (P0.cin - c0) < KC ? (P0.cin - c0) : KC;
+    const bool vec = plain && (srcW & 3) == 0;
+    const int XH = kTcTH + 2 * pad, padL = tc_pad_left(pad), PS = tc_plane_halves(pad);
+    const int XW = vec ? tc_xw_vec(pad) : tc_xw_exact(pad);
+    const int64_t src_base = ((int64_t)n * P0.C + P0.c0) * plane_sz;
+    for (int c0 = 0; c0 < cin; c0 += KC) {
+      const int kc_live = (cin - c0) < KC ? (cin - c0) : KC;
       const int kc8 = (kc_live + 7) & ~7;                   // channels actually multiplied (multiple of 8, rest zero)
       __syncthreads();                                     // previous chunk's readers are done
-      const uint16_t* src16 = reinterpret_cast<const uint16_t*>(P0.src) + ((int64_t)n * P0.C + P0.c0 + c0) * plane_sz;
       if (vec) {
-        // ---- (a) 8-byte cp.async chunks, zero fill outside the image / beyond the live channels ----------------
-        const int cpr = XW >> 2, total = kc8 * XH * cpr;
-        int i = tid;
-        int row = i / cpr, col = i - row * cpr;            // one division per thread, then incremental
-        const int drow = kTcThreads / cpr, dcol = kTcThreads - drow * cpr;
-        for (; i < total; i += kTcThreads) {
-          const int ch = row / XH, y = row - ch * XH;
-          const int cy = oy0 - pad + y, cx = ox0 - padL + 4 * col;
-          const bool ok = ch < kc_live && cy >= 0 && cy < Hc && cx >= 0 && cx < Wc;
-          cp_async8(Xs + ch * PS + y * XW + 4 * col, ok ? src16 + (int64_t)ch * plane_sz + (int64_t)cy * P0.W + cx : src16, ok);
-          row += drow; col += dcol;
-          if (col >= cpr) { col -= cpr; ++row; }
+        // ---- (a) 8-byte cp.async chunks; a warp owns channels warp, warp+8, ...; lanes walk (row, chunk) ---------
+        const int cs = pad == 0 ? 3 : 4, cmask = (1 << cs) - 1, items = XH << cs;
+        const uint16_t* src16 = reinterpret_cast<const uint16_t*>(P0.src) + src_base + (int64_t)c0 * plane_sz;
+        for (int ch = warp; ch < kc8; ch += kTcWarps) {
+          const bool ch_ok = ch < kc_live;
+          const uint16_t* sp = src16 + (int64_t)ch * plane_sz;
+          uint16_t* dp = Xs + ch * PS;
+          for (int i = lane; i < items; i += 32) {
+            const int y = i >> cs, col = i & cmask;
+            const int cy = oy0 - pad + y, cx = ox0 - padL + 4 * col;
+            const bool ok = ch_ok && cy >= 0 && cy < Hc && cx >= 0 && cx < Wc;
+            cp_async8(dp + y * XW + 4 * col, ok ? sp + (int64_t)cy * srcW + cx : sp, ok);
+          }
         }
         cp_async_wait_all();
       } else {
-        // ---- (b)/(c) one (channel, row) per warp step, 4 steps batched so the loads overlap --------------------
-        const int nrows = kc8 * XH;
-        for (int rt0 = warp * 4; rt0 < nrows; rt0 += (kTcThreads / 32) * 4) {
-          for (int xb = 0; xb < XW; xb += 32) {
-            const int x = xb + lane, cx = ox0 - padL + x;
-            const bool col_ok = x < XW && cx >= 0 && cx < Wc;
-            float v[4];
-            uint16_t raw[4];
+        // ---- (b)/(c) scalar copy or computed (pool / avg / up-sample / fp32 source): 4 rows in flight per step ----
+        for (int ch = warp; ch < kc8; ch += kTcWarps) {
+          const bool ch_ok = ch < kc_live;
+          const int64_t plane = src_base + (int64_t)(c0 + ch) * plane_sz;
+          uint16_t* dp = Xs + ch * PS;
+          for (int y0 = 0; y0 < XH; y0 += 4) {
+            for (int xb = 0; xb < XW; xb += 32) {
+              const int x = xb + lane, cx = ox0 - padL + x;
+              const bool col_ok = ch_ok && x < XW && cx >= 0 && cx < Wc;
+              float v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int rt = rt0 + q, ch = rt / XH, y = rt - ch * XH, cy = oy0 - pad + y;
-              const bool ok = col_ok && rt < nrows && ch < kc_live && cy >= 0 && cy < Hc;
-              v[q] = 0.f; raw[q] = 0;
-              if (ok) {
-                if (plain) raw[q] = __ldg(src16 + (int64_t)ch * plane_sz + (int64_t)cy * P0.W + cx);
-                else v[q] = tc_fetch(P0, ((int64_t)n * P0.C + P0.c0 + c0 + ch) * plane_sz, cy, cx);
+              for (int q = 0; q < 4; ++q) {
+                const int cy = oy0 - pad + y0 + q;
+                v[q] = (col_ok && y0 + q < XH && cy >= 0 && cy < Hc) ? tc_fetch(P0, plane, cy, cx) : 0.f;
               }
-            }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int rt = rt0 + q, ch = rt / XH, y = rt - ch * XH;
-              if (rt < nrows && x < XW)
-                Xs[ch * PS + y * XW + x] = plain ? raw[q] : (uint16_t)(Pack<T>::from_f2(v[q], 0.f) & 0xffffu);
+              for (int q = 0; q < 4; ++q)
+                if (x < XW && y0 + q < XH) dp[(y0 + q) * XW + x] = (uint16_t)(Pack<T>::from_f2(v[q], 0.f) & 0xffffu);
             }
           }
         }
       }
       for (int p = p0; p < p1; ++p) {
         const MixPath& P = A.p[p];
-        const int kk = P.ksize * P.ksize;
+        const int ksz = P.ksize, kk = ksz * ksz, dil = P.dil, pcout0 = P.cout0, pcout = P.cout;
+        const float* pw = P.w;
         if (p > p0) __syncthreads();                       // Ws of the previous path is no longer read
-        // ---- stage this path's weights for the chunk: Ws[tap][m][k] ----------------------------------
-        for (int i = tid; i < kk * M16 * kc8; i += kTcThreads) {
-          const int k = i % kc8, r = i / kc8;
-          const int m = r % M16, tap = r / M16;
-          float w = 0.f;
-          if (m >= P.cout0 && m < P.cout0 + P.cout && k < kc_live)
-            w = __ldg(P.w + ((int64_t)(c0 + k) * kk + tap) * P.cout + (m - P.cout0));
-          Ws[(tap * M16 + m) * WR + k] = (uint16_t)(Pack<T>::from_f2(w, 0.f) & 0xffffu);
+        // ---- stage this path's weights for the chunk: Ws[tap][m][k]; thread = (k = lane, m = warp, warp+8, ...) ----
+        if (lane < kc8) {
+          const bool k_ok = lane < kc_live;
+          for (int tap = 0; tap < kk; ++tap) {
+            const float* wsrc = pw + ((int64_t)(c0 + lane) * kk + tap) * pcout - pcout0;
+#pragma unroll
+            for (int m = warp; m < M16; m += kTcWarps) {
+              const float w = (k_ok && m >= pcout0 && m < pcout0 + pcout) ? __ldg(wsrc + m) : 0.f;
+              Ws[(tap * M16 + m) * WR + lane] = (uint16_t)(Pack<T>::from_f2(w, 0.f) & 0xffffu);
+            }
+          }
         }
         __syncthreads();
         // ---- tensor-core accumulate --------------------------------------------------------------------
         const int off = pad - P.pad, offx = padL - P.pad;   // this path's window sits inside the staged one
         for (int ks = 0; ks < kc8; ks += 8) {
           const uint16_t* x0 = Xs + (ks + 2 * t) * PS + (warp + off) * XW + g + offx;
-          for (int ky = 0; ky < P.ksize; ++ky) {
-            for (int kx = 0; kx < P.ksize; ++kx) {
-              const uint16_t* wt = Ws + ((ky * P.ksize + kx) * M16 + g) * WR + ks + 2 * t;
+          for (int ky = 0; ky < ksz; ++ky) {
+            for (int kx = 0; kx < ksz; ++kx) {
+              const uint16_t* wt = Ws + ((ky * ksz + kx) * M16 + g) * WR + ks + 2 * t;
               uint32_t af[MT][2];
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 af[mt][0] = *reinterpret_cast<const uint32_t*>(wt + mt * 16 * WR);
                 af[mt][1] = *reinterpret_cast<const uint32_t*>(wt + (mt * 16 + 8) * WR);
               }
-              const uint16_t* xt = x0 + (ky * P.dil) * XW + kx * P.dil;
+              const uint16_t* xt = x0 + (ky * dil) * XW + kx * dil;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint32_t b = (uint32_t)xt[j * 8] | ((uint32_t)xt[PS + j * 8] << 16);
@@ -178,7 +185,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_cons
   // ---- epilogue ------------------------------------------------------------------------------------------
   const int oy = oy0 + warp;
   if (oy >= A.H) return;
+  uint32_t rmask = 0;                                       // resample-add paths of this op
+  for (int p = 0; p < A.n_paths; ++p)
+    if (A.p[p].ksize == 0) rmask |= 1u << p;
   const int64_t out_plane = (int64_t)A.H * A.W;
+  const bool pair_store = A.dtype != DT_F32 && (A.W & 1) == 0;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -188,26 +199,25 @@ __global__ void __launch_bounds__(kTcThreads, 2) mix_tc_kernel(const __grid_cons
       const float bias = A.bias ? __ldg(A.bias + m) : 0.f;
       const bool has_slope = A.slope != nullptr;
       const float slope = has_slope ? __ldg(A.slope + m) : 1.f;
+      const int64_t orow = ((int64_t)n * A.C + m) * out_plane + (int64_t)oy * A.W;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int ox = ox0 + j * 8 + 2 * t;
         if (ox >= A.W) continue;
-        float v0 = acc[mt][j][2 * h], v1 = acc[mt][j][2 * h + 1];
-        for (int p = 0; p < A.n_paths; ++p) {
-          const MixPath& P = A.p[p];
-          if (P.ksize != 0 || m < P.cout0 || m >= P.cout0 + P.cout) continue;
+        float v0 = acc[mt][j][2 * h] + bias, v1 = acc[mt][j][2 * h + 1] + bias;
+        for (uint32_t mk = rmask; mk; mk &= mk - 1) {
+          const MixPath& P = A.p[__ffs(mk) - 1];
+          if (m < P.cout0 || m >= P.cout0 + P.cout) continue;
           const int64_t plane = ((int64_t)n * P.C + P.c0 + (m - P.cout0)) * (int64_t)P.H * P.W;
           v0 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
           if (ox + 1 < A.W) v1 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox + 1);
         }
-        v0 += bias; v1 += bias;
         if (has_slope) { v0 = prelu(v0, slope); v1 = prelu(v1, slope); }
-        const int64_t o = ((int64_t)n * A.C + m) * out_plane + (int64_t)oy * A.W + ox;
-        if (A.dtype != DT_F32 && (A.W & 1) == 0) {
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(A.dst) + o) = Pack<T>::from_f2(v0, v1);
+        if (pair_store) {
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(A.dst) + orow + ox) = Pack<T>::from_f2(v0, v1);
         } else {
-          st_elem(A.dst, A.dtype, o, v0);
-          if (ox + 1 < A.W) st_elem(A.dst, A.dtype, o + 1, v1);
+          st_elem(A.dst, A.dtype, orow + ox, v0);
+          if (ox + 1 < A.W) st_elem(A.dst, A.dtype, orow + ox + 1, v1);
         }
       }
     }

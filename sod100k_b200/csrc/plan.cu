@@ -331,7 +331,7 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
     kk = q.ksize * q.ksize > kk ? q.ksize * q.ksize : kk;
     cin_max = q.cin > cin_max ? q.cin : cin_max;
   }
-  if (dt < 0 || nconv == 0 || D.C > 80) return c;
+  if (dt < 0 || nconv == 0 || D.C > 80 || pad > csnet::kTcMaxPad) return c;
   c.mt = (D.C + 15) / 16;
   c.dtype = dt;
   c.xs_halves = csnet::tc_plane_halves(pad);
