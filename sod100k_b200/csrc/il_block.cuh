@@ -38,12 +38,6 @@ struct DwParams {
   const float* s;      // [C] PReLU slope
 };
 
-struct FastDiv {       // q = i / d, exact for 2 <= d and 0 <= i < 2^32 / d
-  uint32_t d, m;
-  __device__ __forceinline__ uint32_t div(uint32_t i) const { return __umulhi(i, m); }
-};
-inline FastDiv make_fastdiv(uint32_t d) { return FastDiv{d, (uint32_t)((0x100000000ull + d - 1) / d)}; }
-
 struct IlArgs {
   const void* xh;
   const void* xl;
@@ -55,12 +49,20 @@ struct IlArgs {
   DwParams dw1h, dw1l, dw2h, dw2l;
   int32_t H, W;                // hi resolution (lo = H/2 x W/2)
   int32_t Chi, Cli, Cho, Clo;
-  int32_t TH, TW, tiles_x;
+  int32_t TH, TW, tiles_x;     // tile (one of the instantiated geometries) and tiles per image row
   int32_t K8, MH16, ML16;
-  int32_t RHh, RWh, RHl, RWl, NPH, NPL;
   int32_t rowsAh, rowsAl;
   int32_t tma_h, tma_l;        // 1: that input is loaded with TMA
-  FastDiv dRWh, dRWl, dPairsL, dQuadsH, dQuadPlaneH, dPairPlaneL;
+};
+
+// Region geometry of a TH x TW tile (compile-time: every divisor / stride below is a constant).
+template <int TH_, int TW_>
+struct IlGeom {
+  static constexpr int TH = TH_, TW = TW_;
+  static constexpr int RWh = TW + 8, RHh = (TH + 8) | 1;       // odd row count: RH * RW / 8 is odd when RW / 8 is odd
+  static constexpr int RWl = TW / 2 + 8, RHl = (TH / 2 + 4) | 1;
+  static constexpr int NPH = RHh * RWh, NPL = RHl * RWl;
+  static_assert(TW % 16 == 0 && TH % 2 == 0, "tile shape");
 };
 
 // ---- 16-bit helpers -----------------------------------------------------------------------------------
@@ -134,9 +136,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // D[M16 x NP] = Ws[M16 x K8] . X[K8 x NP], result handed to epi() pair-wise; X may be overwritten by epi() for the
 // SAME pixel columns (each warp owns its columns and holds all their B fragments in registers before writing).
-template <typename T, typename Coord, typename Epi>
+template <typename T, typename Coord, typename RowP, typename Epi>
 __device__ __forceinline__ void gemm_pixels_inplace(const uint16_t* Ws, int M16, int K8, uint16_t* X, int NP, int warp,
-                                                    int nwarps, int lane, Coord coord, Epi epi) {
+                                                    int nwarps, int lane, Coord coord, RowP rowp, Epi epi) {
   const int ntiles = NP >> 3, ksteps = K8 >> 3;
   const int g = lane >> 2, t = lane & 3;
   for (int nt0 = warp * 4; nt0 < ntiles; nt0 += nwarps * 4) {
@@ -165,109 +167,117 @@ __device__ __forceinline__ void gemm_pixels_inplace(const uint16_t* Ws, int M16,
           for (int j = 0; j < 4; ++j) Pack<T>::mma(acc[j], af, bf[ks][j]);
         }
       }
+      float b0, s0, b1, s1;                               // per-row epilogue parameters, loaded once per m tile
+      const bool live0 = rowp(mt * 16 + g, b0, s0), live1 = rowp(mt * 16 + g + 8, b1, s1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (nt0 + j < ntiles) {
           const int p = (nt0 + j) * 8 + 2 * t;
-          epi(mt * 16 + g, p, cy[j], cx[j], acc[j][0], acc[j][1]);
-          epi(mt * 16 + g + 8, p, cy[j], cx[j], acc[j][2], acc[j][3]);
+          if (live0) epi(mt * 16 + g, p, cy[j], cx[j], acc[j][0], acc[j][1], b0, s0);
+          if (live1) epi(mt * 16 + g + 8, p, cy[j], cx[j], acc[j][2], acc[j][3], b1, s1);
         }
       }
     }
   }
 }
 
-// Depthwise 3x3 + bias + PReLU over region rows [r0, r1), 4-pixel groups [g0, g1) of every channel of a plane set.
-// in/out: [C][NP] flat region planes with row stride RW.  Output pixels outside the image are written as 0
-// (smem destination) or skipped (global destination).  A task = one channel, one 4-pixel column group, RUN rows;
-// the tasks of the hi and lo plane sets share one index space so the 512 threads stay evenly loaded.
-struct DwSet {
-  const uint16_t* in;
-  uint16_t* out;             // smem planes or the global tensor of this image
-  DwParams P;
-  int C, RW, NP, r0, r1, g0, g1, oy0, ox0, imgH, imgW;
+// Depthwise 3x3 + bias + PReLU of one plane set: region rows [R0, R1), 4-pixel column groups [G0, G1) of every
+// channel.  in/out: [C][NP] flat region planes with row stride RW (all compile-time).  Output pixels outside the
+// image are written as 0 (smem destination) or skipped (global destination).  A task = one channel, one 4-pixel
+// column group, RUN rows.
+template <int RW_, int NP_, int R0_, int R1_, int G0_, int G1_>
+struct DwGeom {
+  static constexpr int RW = RW_, NP = NP_, R0 = R0_, R1 = R1_, G0 = G0_, G1 = G1_;
 };
 
-template <typename T, bool kToGlobal, int RUN>
-__device__ __forceinline__ void dw_pass(const DwSet& SA, const DwSet& SB, int tid, int nthreads) {
-  const int nA = SA.C * ((SA.r1 - SA.r0 + RUN - 1) / RUN) * (SA.g1 - SA.g0);
-  const int nB = SB.C * ((SB.r1 - SB.r0 + RUN - 1) / RUN) * (SB.g1 - SB.g0);
-  for (int task0 = tid; task0 < nA + nB; task0 += nthreads) {
-    const bool second = task0 >= nA;
-    const DwSet& S = second ? SB : SA;
-    const int task = second ? task0 - nA : task0;
-    const int G = S.g1 - S.g0, nruns = (S.r1 - S.r0 + RUN - 1) / RUN;
-    const int gi = task % G, rest = task / G;
-    const int run = rest % nruns, c = rest / nruns;
-    const int x = 4 * (S.g0 + gi);
-    const int ra = S.r0 + run * RUN, r1 = S.r1, RW = S.RW;
-    float w[9];
+template <typename T, bool kToGlobal, int RUN, typename GEO>
+__device__ __forceinline__ void dw_task(int task, const uint16_t* in, uint16_t* out, const DwParams& P, int oy0, int ox0,
+                                        int imgH, int imgW) {
+  constexpr int G = GEO::G1 - GEO::G0, NR = (GEO::R1 - GEO::R0 + RUN - 1) / RUN, RW = GEO::RW, NP = GEO::NP, r1 = GEO::R1;
+  const int gi = task % G, rest = task / G;
+  const int run = rest % NR, c = rest / NR;
+  const int x = 4 * (GEO::G0 + gi), ra = GEO::R0 + run * RUN;
+  float w[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) w[i] = __ldg(S.P.w + c * 9 + i);
-    const float bias = __ldg(S.P.b + c), slope = __ldg(S.P.s + c);
-    const uint16_t* plane = S.in + (size_t)c * S.NP + x;
-    const int gx = S.ox0 + x;
-    const bool col_in = gx >= 0 && gx < S.imgW;        // imgW % 4 == 0 and gx % 4 == 0: a group is all in or all out
-    float rows[RUN + 2][6];
+  for (int i = 0; i < 9; ++i) w[i] = __ldg(P.w + c * 9 + i);
+  const float bias = __ldg(P.b + c), slope = __ldg(P.s + c);
+  const uint16_t* plane = in + c * NP + x;
+  const int gx = ox0 + x;
+  const bool col_in = gx >= 0 && gx < imgW;            // imgW % 4 == 0 and gx % 4 == 0: a group is all in or all out
+  float rows[RUN + 2][6];
 #pragma unroll
-    for (int i = 0; i < RUN + 2; ++i) {
-      const int r = ra - 1 + i;
-      if (r <= r1) {                                    // row r1 exists (r1 <= RH - 1)
-        const uint2 mid = *reinterpret_cast<const uint2*>(plane + r * RW);            // x .. x+3 (8-byte aligned)
-        const uint32_t lft = *reinterpret_cast<const uint32_t*>(plane + r * RW - 2);  // x-2, x-1
-        const uint32_t rgt = *reinterpret_cast<const uint32_t*>(plane + r * RW + 4);  // x+4, x+5
-        const float2 a = Pack<T>::to_f2(lft), b = Pack<T>::to_f2(mid.x), c2 = Pack<T>::to_f2(mid.y), d = Pack<T>::to_f2(rgt);
-        rows[i][0] = a.y; rows[i][1] = b.x; rows[i][2] = b.y; rows[i][3] = c2.x; rows[i][4] = c2.y; rows[i][5] = d.x;
-      } else {
+  for (int i = 0; i < RUN + 2; ++i) {
+    const int r = ra - 1 + i;
+    if (r <= r1) {                                      // row R1 exists (R1 <= RH - 1)
+      const uint2 mid = *reinterpret_cast<const uint2*>(plane + r * RW);            // x .. x+3 (8-byte aligned)
+      const uint32_t lft = *reinterpret_cast<const uint32_t*>(plane + r * RW - 2);  // x-2, x-1
+      const uint32_t rgt = *reinterpret_cast<const uint32_t*>(plane + r * RW + 4);  // x+4, x+5
+      const float2 a = Pack<T>::to_f2(lft), b = Pack<T>::to_f2(mid.x), c2 = Pack<T>::to_f2(mid.y), d = Pack<T>::to_f2(rgt);
+      rows[i][0] = a.y; rows[i][1] = b.x; rows[i][2] = b.y; rows[i][3] = c2.x; rows[i][4] = c2.y; rows[i][5] = d.x;
+    } else {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) rows[i][k] = 0.f;
-      }
+      for (int k = 0; k < 6; ++k) rows[i][k] = 0.f;
     }
+  }
 #pragma unroll
-    for (int i = 0; i < RUN; ++i) {
-      const int r = ra + i;
-      if (r < r1) {
-        float o[4];
+  for (int i = 0; i < RUN; ++i) {
+    const int r = ra + i;
+    if (r < r1) {
+      float o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float v = bias;
-          v = fmaf(rows[i][k], w[0], v); v = fmaf(rows[i][k + 1], w[1], v); v = fmaf(rows[i][k + 2], w[2], v);
-          v = fmaf(rows[i + 1][k], w[3], v); v = fmaf(rows[i + 1][k + 1], w[4], v); v = fmaf(rows[i + 1][k + 2], w[5], v);
-          v = fmaf(rows[i + 2][k], w[6], v); v = fmaf(rows[i + 2][k + 1], w[7], v); v = fmaf(rows[i + 2][k + 2], w[8], v);
-          o[k] = prelu(v, slope);
-        }
-        const int gy = S.oy0 + r;
-        const bool in_img = col_in && gy >= 0 && gy < S.imgH;
-        uint2 v;
-        v.x = Pack<T>::from_f2(o[0], o[1]);
-        v.y = Pack<T>::from_f2(o[2], o[3]);
-        if (kToGlobal) {
-          if (in_img) *reinterpret_cast<uint2*>(S.out + ((size_t)c * S.imgH + gy) * S.imgW + gx) = v;
-        } else {
-          if (!in_img) v = make_uint2(0u, 0u);
-          *reinterpret_cast<uint2*>(S.out + (size_t)c * S.NP + r * RW + x) = v;
-        }
+      for (int k = 0; k < 4; ++k) {
+        float v = bias;
+        v = fmaf(rows[i][k], w[0], v); v = fmaf(rows[i][k + 1], w[1], v); v = fmaf(rows[i][k + 2], w[2], v);
+        v = fmaf(rows[i + 1][k], w[3], v); v = fmaf(rows[i + 1][k + 1], w[4], v); v = fmaf(rows[i + 1][k + 2], w[5], v);
+        v = fmaf(rows[i + 2][k], w[6], v); v = fmaf(rows[i + 2][k + 1], w[7], v); v = fmaf(rows[i + 2][k + 2], w[8], v);
+        o[k] = prelu(v, slope);
+      }
+      const int gy = oy0 + r;
+      const bool in_img = col_in && gy >= 0 && gy < imgH;
+      uint2 v;
+      v.x = Pack<T>::from_f2(o[0], o[1]);
+      v.y = Pack<T>::from_f2(o[2], o[3]);
+      if (kToGlobal) {
+        if (in_img) *reinterpret_cast<uint2*>(out + ((size_t)c * imgH + gy) * imgW + gx) = v;
+      } else {
+        if (!in_img) v = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(out + c * NP + r * RW + x) = v;
       }
     }
   }
 }
 
-inline size_t il_smem_bytes(const IlArgs& A) {
-  size_t halves = (size_t)A.rowsAh * A.NPH + (size_t)A.Cho * A.NPH + (size_t)A.rowsAl * A.NPL + (size_t)A.Clo * A.NPL +
+// hi and lo plane sets share one task index space so the 512 threads stay evenly loaded
+template <typename T, bool kToGlobal, int RUN, typename GH, typename GL>
+__device__ __forceinline__ void dw_pass(const uint16_t* inH, uint16_t* outH, const DwParams& PH, int Ch, int hy, int hx, int H,
+                                        int W, const uint16_t* inL, uint16_t* outL, const DwParams& PL, int Cl, int ly, int lx,
+                                        int tid) {
+  constexpr int perH = ((GH::R1 - GH::R0 + RUN - 1) / RUN) * (GH::G1 - GH::G0);
+  constexpr int perL = ((GL::R1 - GL::R0 + RUN - 1) / RUN) * (GL::G1 - GL::G0);
+  const int nA = Ch * perH, nB = Cl * perL;
+  for (int task = tid; task < nA + nB; task += kIlThreads) {
+    if (task < nA) dw_task<T, kToGlobal, RUN, GH>(task, inH, outH, PH, hy, hx, H, W);
+    else dw_task<T, kToGlobal, RUN, GL>(task - nA, inL, outL, PL, ly, lx, H >> 1, W >> 1);
+  }
+}
+
+inline size_t il_smem_bytes(const IlArgs& A, int NPH, int NPL) {
+  size_t halves = (size_t)A.rowsAh * NPH + (size_t)A.Cho * NPH + (size_t)A.rowsAl * NPL + (size_t)A.Clo * NPL +
                   (size_t)A.MH16 * A.K8 + (size_t)A.ML16 * A.K8;
   return halves * 2 + 128 /*base alignment*/ + 128 /*mbarrier + front guard*/ + 128 /*bufAh size round-up*/ + 128 /*tail guard*/;
 }
 
-template <typename T>
+template <typename T, int TH, int TW>
 __global__ void __launch_bounds__(kIlThreads, 1)
 il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL) {
+  using GEO = IlGeom<TH, TW>;
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kIlThreads >> 5;
   const int n = blockIdx.z;
   const int tile_y = blockIdx.x / A.tiles_x, tile_x = blockIdx.x % A.tiles_x;
-  const int hy0 = tile_y * A.TH, hx0 = tile_x * A.TW, ly0 = hy0 >> 1, lx0 = hx0 >> 1;
+  const int hy0 = tile_y * TH, hx0 = tile_x * TW, ly0 = hy0 >> 1, lx0 = hx0 >> 1;
   const int H = A.H, W = A.W, Hl = A.H >> 1, Wl = A.W >> 1;
-  const int RHh = A.RHh, RWh = A.RWh, RHl = A.RHl, RWl = A.RWl, NPH = A.NPH, NPL = A.NPL;
+  constexpr int RHh = GEO::RHh, RWh = GEO::RWh, RHl = GEO::RHl, RWl = GEO::RWl, NPH = GEO::NPH, NPL = GEO::NPL;
   const int Chi = A.Chi, Cli = A.Cli, Cho = A.Cho, Clo = A.Clo;
 
   // carve (all sizes are multiples of 16 bytes; bufAh / bufAl are 128-byte aligned TMA destinations)
@@ -313,10 +323,10 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   // cp.async fallback loaders (8-byte chunks, zero fill outside the image)
   if (!A.tma_h) {
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(A.xh) + (size_t)n * Chi * H * W;
-    const int quads_row = RWh >> 2, quads_plane = NPH >> 2;
+    constexpr int quads_row = RWh >> 2, quads_plane = NPH >> 2;
     for (int i = tid; i < Chi * quads_plane; i += kIlThreads) {
-      const int c = A.dQuadPlaneH.div(i), pq = i - c * quads_plane;
-      const int ry = A.dQuadsH.div(pq), rx = (pq - ry * quads_row) * 4;
+      const int c = i / quads_plane, pq = i - c * quads_plane;
+      const int ry = pq / quads_row, rx = (pq - ry * quads_row) * 4;
       const int gy = hy0 - 4 + ry, gx = hx0 - 4 + rx;
       const bool ok = ry < RHh && gy >= 0 && gy < H && gx >= 0 && gx < W;
       cp_async8(bufAh + (size_t)c * NPH + pq * 4, ok ? xh + ((size_t)c * H + gy) * W + gx : xh, ok);
@@ -324,7 +334,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   }
   if (!A.tma_l) {
     const uint16_t* xl = reinterpret_cast<const uint16_t*>(A.xl) + (size_t)n * Cli * Hl * Wl;
-    const int quads_row = RWl >> 2, quads_plane = NPL >> 2;
+    constexpr int quads_row = RWl >> 2, quads_plane = NPL >> 2;
     for (int i = tid; i < Cli * quads_plane; i += kIlThreads) {
       const int c = i / quads_plane, pq = i - c * quads_plane;
       const int ry = pq / quads_row, rx = (pq - ry * quads_row) * 4;
@@ -345,11 +355,11 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   // ---- phase 1: resample both ways --------------------------------------------------------------------
   // (a) max_pool2d 2x2 of x_h -> AL rows [Cli, Cli+Chi): two lo pixels per task from 2 hi rows x 4 hi pixels
   if (Clo > 0) {
-    const int pairs_row = RWl >> 1, pairs_plane = NPL >> 1;
-    const int umax = RWh >> 2;
+    constexpr int pairs_row = RWl >> 1, pairs_plane = NPL >> 1;
+    constexpr int umax = RWh >> 2;
     for (int i = tid; i < Chi * pairs_plane; i += kIlThreads) {
-      const int c = A.dPairPlaneL.div(i), pp = i - c * pairs_plane;
-      const int ry = A.dPairsL.div(pp), u = pp - ry * pairs_row;
+      const int c = i / pairs_plane, pp = i - c * pairs_plane;
+      const int ry = pp / pairs_row, u = pp - ry * pairs_row;
       uint32_t v = 0u;
       if (ry < RHl && 2 * ry + 1 < RHh && u >= 1 && u <= umax) {
         const uint16_t* r0 = bufAh + (size_t)c * NPH + (2 * ry) * RWh + 4 * u - 4;
@@ -365,9 +375,9 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   //     fixed taps dst 2j: (1/4, 3/4) of src (j-1, j); dst 2j+1: (3/4, 1/4) of src (j, j+1), indices clamped to the
   //     image.  A task = 2 hi rows x 4 hi columns of one channel.
   {
-    const int quads_row = RWh >> 2;
-    const int row_pairs = RHh >> 1;                   // hi rows (2a, 2a+1), a < RHh/2 (an odd last row stays zero-filled)
-    const int per_plane = row_pairs * quads_row;
+    constexpr int quads_row = RWh >> 2;
+    constexpr int row_pairs = RHh >> 1;               // hi rows (2a, 2a+1), a < RHh/2 (an odd last row stays zero-filled)
+    constexpr int per_plane = row_pairs * quads_row;
     for (int i = tid; i < Cli * per_plane; i += kIlThreads) {
       const int c = i / per_plane, rem = i - c * per_plane;
       const int a = rem / quads_row, q = rem - a * quads_row;
@@ -400,8 +410,8 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
       *reinterpret_cast<uint2*>(dst + RWh) = o1;
     }
     // rows of the hi planes not covered above (odd last row, padded tail): zero
-    const int covered = (RHh >> 1) * 2 * RWh;
-    const int tailh = (NPH - covered) >> 1;
+    constexpr int covered = (RHh >> 1) * 2 * RWh;
+    constexpr int tailh = (NPH - covered) >> 1;
     for (int i = tid; i < Cli * tailh; i += kIlThreads) {
       const int c = i / tailh, k = i - c * tailh;
       reinterpret_cast<uint32_t*>(bufAh + (size_t)(Chi + c) * NPH + covered)[k] = 0u;
@@ -414,56 +424,55 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     const float* bl = A.bias_l;
     const float* sl = A.slope_l;
     auto coord = [&](int p, int& cy, int& cx) {
-      const int ry = A.dRWl.div(p);
+      const int ry = p / RWl;
       cy = ly0 - 2 + ry; cx = lx0 - 4 + (p - ry * RWl);
       if (ry >= RHl) cy = -1;
     };
-    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1) {
-      if (m >= Clo) return;
+    auto rowp = [&](int m, float& b, float& s) {
+      if (m >= Clo) return false;
+      b = __ldg(bl + m); s = __ldg(sl + m);
+      return true;
+    };
+    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1, float b, float s) {
       const bool rin = gy >= 0 && gy < Hl;
-      const float b = __ldg(bl + m), s = __ldg(sl + m);
       const float o0 = (rin && gx >= 0 && gx < Wl) ? prelu(v0 + b, s) : 0.f;
       const float o1 = (rin && gx + 1 >= 0 && gx + 1 < Wl) ? prelu(v1 + b, s) : 0.f;
       *reinterpret_cast<uint32_t*>(bufAl + (size_t)m * NPL + p) = Pack<T>::from_f2(o0, o1);
     };
-    gemm_pixels_inplace<T>(wsL, A.ML16, A.K8, bufAl, NPL, warp, nwarps, lane, coord, epi);
+    gemm_pixels_inplace<T>(wsL, A.ML16, A.K8, bufAl, NPL, warp, nwarps, lane, coord, rowp, epi);
   }
   {
     const float* bh = A.bias_h;
     const float* sh = A.slope_h;
     auto coord = [&](int p, int& cy, int& cx) {
-      const int ry = A.dRWh.div(p);
+      const int ry = p / RWh;
       cy = hy0 - 4 + ry; cx = hx0 - 4 + (p - ry * RWh);
       if (ry >= RHh) cy = -1;
     };
-    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1) {
-      if (m >= Cho) return;
+    auto rowp = [&](int m, float& b, float& s) {
+      if (m >= Cho) return false;
+      b = __ldg(bh + m); s = __ldg(sh + m);
+      return true;
+    };
+    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1, float b, float s) {
       const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;      // W even, gx even: gx+1 is inside too
-      const float b = __ldg(bh + m), s = __ldg(sh + m);
       const float o0 = in ? prelu(v0 + b, s) : 0.f, o1 = in ? prelu(v1 + b, s) : 0.f;
       *reinterpret_cast<uint32_t*>(bufAh + (size_t)m * NPH + p) = Pack<T>::from_f2(o0, o1);
     };
-    gemm_pixels_inplace<T>(wsH, A.MH16, A.K8, bufAh, NPH, warp, nwarps, lane, coord, epi);
+    gemm_pixels_inplace<T>(wsH, A.MH16, A.K8, bufAh, NPH, warp, nwarps, lane, coord, rowp, epi);
   }
   __syncthreads();
 
   // ---- phase 3: dw1 (T1 -> T2, smem) ------------------------------------------------------------------
-  const int rh = A.TH + 8, rl = (A.TH >> 1) + 4;      // region rows that matter (without the padding row)
-  {
-    const DwSet sh{bufAh, bufBh, A.dw1h, Cho, RWh, NPH, 3, rh - 3, 0, RWh >> 2, hy0 - 4, hx0 - 4, H, W};
-    const DwSet sl{bufAl, bufBl, A.dw1l, Clo, RWl, NPL, 1, rl - 1, 0, RWl >> 2, ly0 - 2, lx0 - 4, Hl, Wl};
-    dw_pass<T, false, 6>(sh, sl, tid, kIlThreads);
-  }
+  constexpr int rh = TH + 8, rl = TH / 2 + 4;         // region rows that matter (without the padding row)
+  dw_pass<T, false, 6, DwGeom<RWh, NPH, 3, rh - 3, 0, RWh / 4>, DwGeom<RWl, NPL, 1, rl - 1, 0, RWl / 4>>(
+      bufAh, bufBh, A.dw1h, Cho, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l, Clo, ly0 - 2, lx0 - 4, tid);
   __syncthreads();
 
   // ---- phase 4: dw2 (T2 -> global) --------------------------------------------------------------------
-  {
-    const DwSet sh{bufBh, reinterpret_cast<uint16_t*>(A.yh) + (size_t)n * Cho * H * W, A.dw2h, Cho, RWh, NPH, 4, rh - 4, 1,
-                   (RWh >> 2) - 1, hy0 - 4, hx0 - 4, H, W};
-    const DwSet sl{bufBl, Clo > 0 ? reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * Clo * Hl * Wl : nullptr, A.dw2l, Clo, RWl, NPL,
-                   2, rl - 2, 1, (RWl >> 2) - 1, ly0 - 2, lx0 - 4, Hl, Wl};
-    dw_pass<T, true, 4>(sh, sl, tid, kIlThreads);
-  }
+  dw_pass<T, true, 4, DwGeom<RWh, NPH, 4, rh - 4, 1, RWh / 4 - 1>, DwGeom<RWl, NPL, 2, rl - 2, 1, RWl / 4 - 1>>(
+      bufBh, reinterpret_cast<uint16_t*>(A.yh) + (size_t)n * Cho * H * W, A.dw2h, Cho, hy0 - 4, hx0 - 4, H, W, bufBl,
+      Clo > 0 ? reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * Clo * Hl * Wl : nullptr, A.dw2l, Clo, ly0 - 2, lx0 - 4, tid);
 }
 
 }  // namespace csnet

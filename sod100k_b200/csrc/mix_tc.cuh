@@ -51,6 +51,34 @@ __device__ __forceinline__ float tc_fetch(const MixPath& P, int64_t plane, int c
   return fetch_pooled(P, plane, cy, cx);
 }
 
+// Same as fetch_pooled() for a 16-bit source of type T with an even row length: pixel pairs come in as one
+// 32-bit load (a 2x2 average = 2 loads, a 2x2 max of plain pixels = 2 loads), no per-load dtype dispatch.
+template <typename T>
+__device__ __forceinline__ float fetch_pooled16(const MixPath& P, const uint16_t* plane, int y, int x) {
+  const int W = P.W, pool = P.pool;
+  float m = -INFINITY;
+  if (P.pre_avg) {
+    for (int py = 0; py < pool; ++py) {
+      const uint16_t* r = plane + (size_t)(2 * (y * pool + py)) * W + 2 * (x * pool);
+      for (int px = 0; px < pool; ++px) {
+        const float2 a = Pack<T>::to_f2(*reinterpret_cast<const uint32_t*>(r + 2 * px));
+        const float2 b = Pack<T>::to_f2(*reinterpret_cast<const uint32_t*>(r + W + 2 * px));
+        const float v = (((a.x + a.y) + b.x) + b.y) * 0.25f;
+        m = v > m ? v : m;
+      }
+    }
+  } else {                                                  // pool is 2, 4, 8: even, rows of pool pixels are 4-byte aligned
+    for (int py = 0; py < pool; ++py) {
+      const uint16_t* r = plane + (size_t)(y * pool + py) * W + x * pool;
+      for (int px = 0; px < pool; px += 2) {
+        const float2 a = Pack<T>::to_f2(*reinterpret_cast<const uint32_t*>(r + px));
+        m = fmaxf(m, fmaxf(a.x, a.y));
+      }
+    }
+  }
+  return m;
+}
+
 template <typename T, int MT>
 __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(const __grid_constant__ MixArgs A, const TcGeom G) {
   extern __shared__ __align__(16) uint16_t tc_smem[];
@@ -90,6 +118,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
     const int64_t plane_sz = (int64_t)P0.H * P0.W;
     const bool plain = !P0.pre_avg && P0.pool == 1 && P0.up == 1 && P0.dtype != DT_F32;   // raw 16-bit copy
     const bool vec = plain && (srcW & 3) == 0;
+    const bool pooled16 = P0.dtype != DT_F32 && P0.up == 1 && (P0.pre_avg || P0.pool > 1) && (srcW & 1) == 0;
     const int XH = kTcTH + 2 * pad, padL = tc_pad_left(pad), PS = tc_plane_halves(pad);
     const int XW = vec ? tc_xw_vec(pad) : tc_xw_exact(pad);
     const int64_t src_base = ((int64_t)n * P0.C + P0.c0) * plane_sz;
@@ -127,7 +156,10 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int cy = oy0 - pad + y0 + q;
-                v[q] = (col_ok && y0 + q < XH && cy >= 0 && cy < Hc) ? tc_fetch(P0, plane, cy, cx) : 0.f;
+                v[q] = 0.f;
+                if (col_ok && y0 + q < XH && cy >= 0 && cy < Hc)
+                  v[q] = pooled16 ? fetch_pooled16<T>(P0, reinterpret_cast<const uint16_t*>(P0.src) + plane, cy, cx)
+                                  : tc_fetch(P0, plane, cy, cx);
               }
 #pragma unroll
               for (int q = 0; q < 4; ++q)

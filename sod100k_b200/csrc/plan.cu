@@ -275,25 +275,37 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   static const bool use_tma = [] { const char* e = getenv("CSNET_TMA"); return e && e[0] == '1'; }();   // opt-in until the 16-byte start-alignment rule is met
   A.tma_h = use_tma && (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
   A.tma_l = use_tma && ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
-  static const int cand[][2] = {{32, 64}, {32, 32}, {16, 64}, {16, 32}, {16, 16}, {8, 16}};
+  static const int cand[][2] = {{32, 32}, {16, 32}, {8, 16}};        // the instantiated tile geometries
   double best = -1;
   for (auto& c : cand) {
     csnet::IlArgs T = A;
     T.TH = c[0]; T.TW = c[1];
-    T.RWh = T.TW + 8; T.RHh = (T.TH + 8) | 1;            // odd row count: (RH * RW / 8) odd when RW / 8 is odd
-    T.RWl = T.TW / 2 + 8; T.RHl = (T.TH / 2 + 4) | 1;
-    T.NPH = T.RHh * T.RWh; T.NPL = T.RHl * T.RWl;
-    if (csnet::il_smem_bytes(T) > 227 * 1024) continue;
+    const int NPH = ((T.TH + 8) | 1) * (T.TW + 8), NPL = ((T.TH / 2 + 4) | 1) * (T.TW / 2 + 8);
+    if (csnet::il_smem_bytes(T, NPH, NPL) > 227 * 1024) continue;
     const int ty = (A.H + T.TH - 1) / T.TH, tx = (A.W + T.TW - 1) / T.TW;
-    const double cost = (double)ty * tx * T.NPH;
+    const double cost = (double)ty * tx * NPH;
     if (best < 0 || cost < best) { best = cost; T.tiles_x = tx; *out = T; }
   }
-  if (best < 0) return false;
-  csnet::IlArgs& R = *out;
-  R.dRWh = csnet::make_fastdiv(R.RWh); R.dRWl = csnet::make_fastdiv(R.RWl);
-  R.dPairsL = csnet::make_fastdiv(R.RWl / 2); R.dQuadsH = csnet::make_fastdiv(R.RWh / 4);
-  R.dQuadPlaneH = csnet::make_fastdiv(R.NPH / 4); R.dPairPlaneL = csnet::make_fastdiv(R.NPL / 2);
-  return true;
+  return best >= 0;
+}
+
+size_t il_smem_of(const csnet::IlArgs& A) {
+  return csnet::il_smem_bytes(A, ((A.TH + 8) | 1) * (A.TW + 8), ((A.TH / 2 + 4) | 1) * (A.TW / 2 + 8));
+}
+
+template <typename T>
+void launch_il_t(const csnet::IlArgs& A, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& h, const CUtensorMap& l) {
+  if (A.TH == 32) csnet::il_block_kernel<T, 32, 32><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
+  else if (A.TH == 16) csnet::il_block_kernel<T, 16, 32><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
+  else csnet::il_block_kernel<T, 8, 16><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
+}
+
+template <typename T>
+cudaError_t set_il_smem_t(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(csnet::il_block_kernel<T, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_block_kernel<T, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_block_kernel<T, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e;
 }
 
 size_t mix_smem_bytes(const csnet::MixArgs& A) {
@@ -444,13 +456,12 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     if (P->ops[i].kind != CSNET_OP_ILBLOCK) continue;
     csnet::IlArgs A;
     if (!make_il(*P, P->ops[i], 1, nullptr, &A)) return cleanup(CSNET_E_UNSUPPORTED, "ILBLOCK op does not fit shared memory");
-    P->op_smem[i] = csnet::il_smem_bytes(A);
+    P->op_smem[i] = il_smem_of(A);
     P->il_smem_max = P->op_smem[i] > P->il_smem_max ? P->op_smem[i] : P->il_smem_max;
   }
   if (P->il_smem_max > 0) {
-    e = cudaFuncSetAttribute(csnet::il_block_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->il_smem_max);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(csnet::il_block_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->il_smem_max);
+    e = set_il_smem_t<__half>((int)P->il_smem_max);
+    if (e == cudaSuccess) e = set_il_smem_t<__nv_bfloat16>((int)P->il_smem_max);
     if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(il_block): ") + cudaGetErrorString(e));
   }
   if (P->mix_smem_max > 48 * 1024) {
@@ -499,14 +510,12 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     CUtensorMap tmH, tmL;
     memset(&tmH, 0, sizeof tmH);
     memset(&tmL, 0, sizeof tmL);
-    if (A.tma_h && !encode_plane_map(&tmH, A.xh, N, A.Chi, A.H, A.W, A.RWh, A.RHh, A.Chi))
+    if (A.tma_h && !encode_plane_map(&tmH, A.xh, N, A.Chi, A.H, A.W, A.TW + 8, (A.TH + 8) | 1, A.Chi))
       return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (hi input)");
-    if (A.tma_l && !encode_plane_map(&tmL, A.xl, N, A.Cli, A.H / 2, A.W / 2, A.RWl, A.RHl, A.Cli))
+    if (A.tma_l && !encode_plane_map(&tmL, A.xl, N, A.Cli, A.H / 2, A.W / 2, A.TW / 2 + 8, (A.TH / 2 + 4) | 1, A.Cli))
       return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (lo input)");
-    if (D.dtype == CSNET_F16)
-      csnet::il_block_kernel<__half><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A, tmH, tmL);
-    else
-      csnet::il_block_kernel<__nv_bfloat16><<<grid, csnet::kIlThreads, P->op_smem[i], stream>>>(A, tmH, tmL);
+    if (D.dtype == CSNET_F16) launch_il_t<__half>(A, grid, P->op_smem[i], stream, tmH, tmL);
+    else launch_il_t<__nv_bfloat16>(A, grid, P->op_smem[i], stream, tmH, tmL);
   } else {
     const csnet_path_desc& q = op.paths[0];
     const csnet_tensor_desc& S = P->tensors[q.src];
