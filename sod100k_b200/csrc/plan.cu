@@ -89,6 +89,12 @@ struct csnet_plan {
   size_t il_smem_max = 0;
   std::vector<size_t> op_smem;
   std::vector<TcChoice> op_tc;
+  // host-buffer pipeline (csnet_plan_run_host): copy streams, ping-pong staging, ordering events
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  void* h_in[2] = {nullptr, nullptr};
+  void* h_out[2] = {nullptr, nullptr};
+  size_t h_in_bytes = 0, h_out_bytes = 0;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
 
   void* tensor_ptr(int t, int N, const void* const* ext) const {
     const csnet_tensor_desc& d = tensors[t];
@@ -600,11 +606,21 @@ void csnet_plan_destroy(csnet_plan* P) {
   if (P->blob || P->arena) cudaSetDevice(P->device);
   if (P->blob) cudaFree(P->blob);
   if (P->arena) cudaFree(P->arena);
+  for (int b = 0; b < 2; ++b) {
+    if (P->h_in[b]) cudaFree(P->h_in[b]);
+    if (P->h_out[b]) cudaFree(P->h_out[b]);
+    if (P->ev_h2d[b]) cudaEventDestroy(P->ev_h2d[b]);
+    if (P->ev_comp[b]) cudaEventDestroy(P->ev_comp[b]);
+    if (P->ev_d2h[b]) cudaEventDestroy(P->ev_d2h[b]);
+  }
+  if (P->s_h2d) cudaStreamDestroy(P->s_h2d);
+  if (P->s_d2h) cudaStreamDestroy(P->s_d2h);
   delete P;
 }
 
 int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_host, void* stream_) {
   if (!P || !x_host || !y_host) return fail(CSNET_E_INVALID, "null argument");
+  if (N <= 0 || N > P->max_batch) return fail(CSNET_E_INVALID, "batch size outside [1, max_batch]");
   if (P->n_ext != 2) return fail(CSNET_E_INVALID, "run_host needs a plan with externals {0: input, 1: logits}");
   const csnet_tensor_desc *in = nullptr, *lo = nullptr;
   for (const auto& d : P->tensors) {
@@ -615,22 +631,49 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
     return fail(CSNET_E_INVALID, "run_host: externals must be fp32");
   cudaStream_t stream = (cudaStream_t)stream_;
   CU_CHECK(cudaSetDevice(P->device));
-  const size_t xb = (size_t)N * in->C * in->H * in->W * sizeof(float);
-  const size_t yb = (size_t)N * lo->C * lo->H * lo->W * sizeof(float);
-  void *dx = nullptr, *dy = nullptr;
-  CU_CHECK(cudaMallocAsync(&dx, xb, stream));
-  CU_CHECK(cudaMallocAsync(&dy, yb, stream));
-  CU_CHECK(cudaMemcpyAsync(dx, x_host, xb, cudaMemcpyHostToDevice, stream));
-  const void* ext[2] = {dx, dy};
-  int rc = csnet_plan_run(P, N, ext, 2, stream_);
-  if (rc == CSNET_OK) {
-    cudaError_t e = cudaMemcpyAsync(y_host, dy, yb, cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) rc = fail(CSNET_E_CUDA, std::string("D2H: ") + cudaGetErrorString(e));
+  // The batch is cut into chunks that flow through a three-stage pipeline: H2D copy (own stream) -> program
+  // (caller's stream) -> D2H copy (own stream), with ping-pong device staging, so the PCIe copies of chunk i+1 / i-1
+  // overlap the kernels of chunk i.  Pinned host memory is needed for the copies to be truly asynchronous.
+  const int chunk = N >= 64 ? (N + 3) / 4 : N;
+  const size_t xin = (size_t)in->C * in->H * in->W * sizeof(float), yout = (size_t)lo->C * lo->H * lo->W * sizeof(float);
+  if (!P->s_h2d) {
+    CU_CHECK(cudaStreamCreateWithFlags(&P->s_h2d, cudaStreamNonBlocking));
+    CU_CHECK(cudaStreamCreateWithFlags(&P->s_d2h, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CU_CHECK(cudaEventCreateWithFlags(&P->ev_h2d[b], cudaEventDisableTiming));
+      CU_CHECK(cudaEventCreateWithFlags(&P->ev_comp[b], cudaEventDisableTiming));
+      CU_CHECK(cudaEventCreateWithFlags(&P->ev_d2h[b], cudaEventDisableTiming));
+    }
   }
-  cudaFreeAsync(dx, stream);
-  cudaFreeAsync(dy, stream);
-  cudaError_t e = cudaStreamSynchronize(stream);
-  if (rc == CSNET_OK && e != cudaSuccess) rc = fail(CSNET_E_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+  if (P->h_in_bytes < (size_t)chunk * xin) {
+    for (int b = 0; b < 2; ++b) {
+      if (P->h_in[b]) cudaFree(P->h_in[b]);
+      if (P->h_out[b]) cudaFree(P->h_out[b]);
+      CU_CHECK(cudaMalloc(&P->h_in[b], (size_t)chunk * xin));
+      CU_CHECK(cudaMalloc(&P->h_out[b], (size_t)chunk * yout));
+    }
+    P->h_in_bytes = (size_t)chunk * xin;
+    P->h_out_bytes = (size_t)chunk * yout;
+  }
+  int rc = CSNET_OK, it = 0;
+  for (int n0 = 0; n0 < N && rc == CSNET_OK; n0 += chunk, ++it) {
+    const int b = it & 1, nb = (N - n0) < chunk ? (N - n0) : chunk;
+    if (it >= 2) CU_CHECK(cudaStreamWaitEvent(P->s_h2d, P->ev_comp[b], 0));     // staging input b was consumed
+    CU_CHECK(cudaMemcpyAsync(P->h_in[b], x_host + (size_t)n0 * (xin / sizeof(float)), (size_t)nb * xin, cudaMemcpyHostToDevice, P->s_h2d));
+    CU_CHECK(cudaEventRecord(P->ev_h2d[b], P->s_h2d));
+    CU_CHECK(cudaStreamWaitEvent(stream, P->ev_h2d[b], 0));
+    if (it >= 2) CU_CHECK(cudaStreamWaitEvent(stream, P->ev_d2h[b], 0));         // staging output b was drained
+    const void* ext[2] = {P->h_in[b], P->h_out[b]};
+    rc = csnet_plan_run(P, nb, ext, 2, stream_);
+    if (rc != CSNET_OK) break;
+    CU_CHECK(cudaEventRecord(P->ev_comp[b], stream));
+    CU_CHECK(cudaStreamWaitEvent(P->s_d2h, P->ev_comp[b], 0));
+    CU_CHECK(cudaMemcpyAsync(y_host + (size_t)n0 * (yout / sizeof(float)), P->h_out[b], (size_t)nb * yout, cudaMemcpyDeviceToHost, P->s_d2h));
+    CU_CHECK(cudaEventRecord(P->ev_d2h[b], P->s_d2h));
+  }
+  cudaError_t e1 = cudaStreamSynchronize(P->s_d2h), e2 = cudaStreamSynchronize(stream), e3 = cudaStreamSynchronize(P->s_h2d);
+  if (rc == CSNET_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
+    rc = fail(CSNET_E_CUDA, std::string("run_host sync: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
   return rc;
 }
 

@@ -147,6 +147,18 @@ def test_host_buffer_call_and_batch_properties():
         assert torch.allclose(m(x.cuda()).cpu(), y_dev + 1.0, atol=1e-5)
 
 
+def test_pipelined_host_call_equals_device_call():
+    """csnet_plan_run_host cuts batches >= 64 into chunks that overlap copies and kernels; results must be identical."""
+    m, cfg, sd = _model("csnet-L-x1")
+    m.set_precision("fp16")
+    x = torch.from_numpy(synth.randn_images(70, 64, 96, 9))
+    with torch.no_grad():
+        y_dev = m(x.cuda()).cpu()
+        y_host = m.engine().forward_host(x.pin_memory())
+        y_host2 = m.engine().forward_host(x)                 # pageable memory: slower, still correct
+    assert torch.equal(y_dev, y_host) and torch.equal(y_dev, y_host2)
+
+
 def test_large_batch_full_size_properties():
     """BASELINE config size (bs 256, 224x224, fp16): determinism + per-image independence."""
     m, cfg, sd = _model("csnet-L-x2")
