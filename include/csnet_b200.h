@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CSNET_ABI_VERSION 2
+#define CSNET_ABI_VERSION 3
 
 enum { CSNET_F32 = 0, CSNET_F16 = 1, CSNET_BF16 = 2 };
 
@@ -176,6 +176,60 @@ void csnet_plan_destroy(csnet_plan* plan);
  * The plan must bind external 0 = input, external 1 = logits.
  */
 int csnet_plan_run_host(csnet_plan* plan, int32_t N, const float* x_host, float* y_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training primitives (fp32 planar NCHW device tensors).  The reference trains through torch autograd
+ * (CSNet_training/train.py:203-216); train-mode BatchNorm makes the reference MODULE the closed unit, so the
+ * boundary is one call per module piece.  sod100k_b200/train_ops.py wraps them in torch.autograd.Function s.
+ * All return 0 / CSNET_E_*; csnet_train_last_error() holds the message.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* One path of a raw (pre-BN) conv mix, device pointers resolved.  Same semantics as csnet_path_desc; `w` is the
+ * path's weight in kernel layout [cin][ksize*ksize][cout] (fp32), NULL for resample-add paths (ksize == 0). */
+typedef struct {
+  const void* src;        /* fp32 [N, C, H, W] */
+  const float* w;
+  int32_t C, H, W;
+  int32_t c0, cin;
+  int32_t pre_avg, pool;
+  int32_t ksize, dil, stride, pad;
+  int32_t up;
+  int32_t cout0, cout;
+} csnet_train_path;
+
+const char* csnet_train_last_error(void);
+
+/* F.batch_norm(training=True) statistics: per-channel mean and BIASED variance over (N, H*W)  (csnet.py:786,846). */
+int csnet_train_bn_stats(const float* z, int32_t N, int32_t C, int32_t HW, float* mean, float* var, void* stream);
+/* y = PReLU(gamma*(z-mean)/sqrt(var+eps)+beta); gap (optional, [N*C]) = per-image channel means of y, the quantity
+ * Oct_bn_hook pools (csnet.py:403-404). */
+int csnet_train_bn_prelu_fwd(const float* z, float* y, int32_t N, int32_t C, int32_t HW, const float* mean, const float* var,
+                             const float* gamma, const float* beta, const float* slope, float eps, float* gap, void* stream);
+/* autograd of the above: dz plus dgamma / dbeta / dslope ([C] each). */
+int csnet_train_bn_prelu_bwd(const float* z, const float* dy, float* dz, int32_t N, int32_t C, int32_t HW, const float* mean,
+                             const float* var, const float* gamma, const float* beta, const float* slope, float eps,
+                             float* dgamma, float* dbeta, float* dslope, void* stream);
+/* Depthwise 3x3 pad 1 with effective weight scale*w (Conv2dX100, conv2d.py:104); transposed=1 gives the data gradient. */
+int csnet_train_dw_conv(const float* x, const float* w, float* y, int32_t N, int32_t C, int32_t H, int32_t W, float scale,
+                        int32_t transposed, void* stream);
+int csnet_train_dw_wgrad(const float* x, const float* dy, float* dw, int32_t N, int32_t C, int32_t H, int32_t W, float scale,
+                         void* stream);
+/* Raw conv mix (gOctaveConv.forward csnet.py:664-726 for one output branch; MSBlock :141-146): dst = sum of paths. */
+int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* paths, int32_t n_paths,
+                        void* stream);
+/* Gradient of one path w.r.t. its source slice: dsrc is [N, cin, path.H, path.W] (through max/avg pooling, the conv,
+ * or the bilinear up-sample for resample paths). */
+int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dsrc,
+                          void* stream);
+/* Gradient of one conv path w.r.t. its weight, kernel layout [cin][k*k][cout]. */
+int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dw,
+                          void* stream);
+/* F.binary_cross_entropy_with_logits (mean) and its gradient * grad_scale (train.py:209). */
+int csnet_train_bce(const float* logits, const float* target, float* dlogits, float* loss, int64_t n, float grad_scale, void* stream);
+/* torch.optim.Adam step (train.py:108-123) over many tensors: `chunk_table_device` = n_chunks records
+ * {float* p; const float* g; float* m; float* v; int32 n; float weight_decay} (40 bytes each). */
+int csnet_train_adam(const void* chunk_table_device, int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step,
+                     float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

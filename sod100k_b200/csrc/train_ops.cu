@@ -1,0 +1,444 @@
+// train_ops.cu — module-granular training primitives (fp32 activations), C ABI `csnet_train_*`.
+//
+// The reference trains with torch autograd over F.conv2d / F.batch_norm / F.prelu / pooling / F.interpolate
+// (CSNet_training/train.py:203-216).  Train-mode BatchNorm puts a batch-wide reduction between every conv and its
+// PReLU, so the closed unit here is the reference MODULE: raw conv mix -> batch statistics -> normalise + PReLU,
+// and the matching backward pieces.  These kernels are generic (any shape) and correctness-first; they reuse the
+// per-thread bodies of generic_ops.cuh for the forward mix.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <string>
+
+#include "../../include/csnet_b200.h"
+#include "generic_ops.cuh"
+
+namespace {
+
+int tfail(int code, const char* what, cudaError_t e);
+#define TR_CHECK(expr)                                              \
+  do {                                                              \
+    cudaError_t e_ = (expr);                                        \
+    if (e_ != cudaSuccess) return tfail(CSNET_E_CUDA, #expr, e_);   \
+  } while (0)
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of up to 3 values; result valid in thread 0
+__device__ __forceinline__ void block_sum3(float& a, float& b, float& c) {
+  __shared__ float sh[3][kT / 32];
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = a; sh[1][w] = b; sh[2][w] = c; }
+  __syncthreads();
+  if (w == 0) {
+    a = l < kT / 32 ? sh[0][l] : 0.f; b = l < kT / 32 ? sh[1][l] : 0.f; c = l < kT / 32 ? sh[2][l] : 0.f;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  }
+  __syncthreads();
+}
+
+// ---- BatchNorm (train) + PReLU ---------------------------------------------------------------------------
+// stats: per channel mean and biased variance over (N, H*W), two-pass (mean first) for accuracy.
+__global__ void __launch_bounds__(kT) bn_stats_kernel(const float* __restrict__ z, int N, int C, int HW, float* mean, float* var) {
+  const int c = blockIdx.x;
+  float s = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = z + ((size_t)n * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += kT) s += p[i];
+  }
+  block_sum3(s, d0, d1);
+  __shared__ float mu_s;
+  if (threadIdx.x == 0) mu_s = s / ((float)N * (float)HW);
+  __syncthreads();
+  const float mu = mu_s;
+  float q = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = z + ((size_t)n * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += kT) { const float d = p[i] - mu; q += d * d; }
+  }
+  block_sum3(q, d0, d1);
+  if (threadIdx.x == 0) { mean[c] = mu; var[c] = q / ((float)N * (float)HW); }
+}
+
+// y = prelu(gamma * (z - mean) * rsqrt(var + eps) + beta);  gap[n*C+c] = mean over HW of y (optional)
+__global__ void __launch_bounds__(kT) bn_prelu_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, int C, int HW,
+                                                          const float* mean, const float* var, const float* gamma,
+                                                          const float* beta, const float* slope, float eps, float* gap) {
+  const int c = blockIdx.x, n = blockIdx.y;
+  const float r = rsqrtf(var[c] + eps), g = gamma[c] * r, b = beta[c] - mean[c] * g, a = slope[c];
+  const float* p = z + ((size_t)n * C + c) * HW;
+  float* o = y + ((size_t)n * C + c) * HW;
+  float s = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int i = threadIdx.x; i < HW; i += kT) {
+    const float u = p[i] * g + b;
+    const float v = u > 0.f ? u : a * u;
+    o[i] = v;
+    s += v;
+  }
+  if (gap) {
+    block_sum3(s, d0, d1);
+    if (threadIdx.x == 0) gap[(size_t)n * C + c] = s / (float)HW;
+  }
+}
+
+// backward reductions per channel: S1 = sum du, S2 = sum du * xhat, S3 = sum dy * u * [u <= 0]   (du = dy * prelu'(u))
+__global__ void __launch_bounds__(kT) bn_prelu_bwd_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, int N,
+                                                                 int C, int HW, const float* mean, const float* var,
+                                                                 const float* gamma, const float* beta, const float* slope,
+                                                                 float eps, float* dgamma, float* dbeta, float* dslope) {
+  const int c = blockIdx.x;
+  const float mu = mean[c], r = rsqrtf(var[c] + eps), g = gamma[c], b = beta[c], a = slope[c];
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = z + ((size_t)n * C + c) * HW;
+    const float* q = dy + ((size_t)n * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += kT) {
+      const float xh = (p[i] - mu) * r, u = g * xh + b, d = q[i];
+      const float du = u > 0.f ? d : a * d;
+      s1 += du; s2 += du * xh;
+      if (!(u > 0.f)) s3 += d * u;
+    }
+  }
+  block_sum3(s1, s2, s3);
+  if (threadIdx.x == 0) { dbeta[c] = s1; dgamma[c] = s2; dslope[c] = s3; }
+}
+
+// dz = gamma * r * (du - S1/M - xhat * S2/M)
+__global__ void __launch_bounds__(kT) bn_prelu_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ dy,
+                                                                float* __restrict__ dz, int N, int C, int HW, const float* mean,
+                                                                const float* var, const float* gamma, const float* beta,
+                                                                const float* slope, float eps, const float* dgamma,
+                                                                const float* dbeta) {
+  const int c = blockIdx.x, n = blockIdx.y;
+  const float mu = mean[c], r = rsqrtf(var[c] + eps), g = gamma[c], b = beta[c], a = slope[c];
+  const float invM = 1.f / ((float)N * (float)HW), m1 = dbeta[c] * invM, m2 = dgamma[c] * invM;
+  const size_t off = ((size_t)n * C + c) * HW;
+  for (int i = threadIdx.x; i < HW; i += kT) {
+    const float xh = (z[off + i] - mu) * r, u = g * xh + b, d = dy[off + i];
+    const float du = u > 0.f ? d : a * d;
+    dz[off + i] = g * r * (du - m1 - xh * m2);
+  }
+}
+
+// ---- depthwise 3x3 (Conv2dX100: effective weight = scale * w) ---------------------------------------------
+__global__ void __launch_bounds__(kT) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                                    int C, int H, int W, float scale, int flip) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const int pix = blockIdx.x * kT + threadIdx.x;
+  if (pix >= H * W) return;
+  const int oy = pix / W, ox = pix % W;
+  const float* p = x + ((size_t)n * C + c) * H * W;
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = oy + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = ox + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const int t = flip ? (2 - ky) * 3 + (2 - kx) : ky * 3 + kx;   // flip: transposed conv = data gradient
+      acc += p[(size_t)yy * W + xx] * w[c * 9 + t];
+    }
+  }
+  y[((size_t)n * C + c) * H * W + pix] = acc * scale;
+}
+
+// dw[c][tap] = scale * sum_{n,y,x} dy[y,x] * x[y+ky-1, x+kx-1]
+__global__ void __launch_bounds__(kT) dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dw, int N,
+                                                      int C, int H, int W, float scale) {
+  const int c = blockIdx.x, tap = blockIdx.y, ky = tap / 3, kx = tap % 3;
+  float s = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = x + ((size_t)n * C + c) * H * W;
+    const float* q = dy + ((size_t)n * C + c) * H * W;
+    for (int i = threadIdx.x; i < H * W; i += kT) {
+      const int oy = i / W, ox = i % W, yy = oy + ky - 1, xx = ox + kx - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) s += q[i] * p[(size_t)yy * W + xx];
+    }
+  }
+  block_sum3(s, d0, d1);
+  if (threadIdx.x == 0) dw[c * 9 + tap] = s * scale;
+}
+
+// ---- MIX forward (raw: no bias / slope) -----------------------------------------------------------------------
+__global__ void __launch_bounds__(kT, 2) tr_mix_fwd_kernel(const __grid_constant__ csnet::MixArgs A) {
+  extern __shared__ float ws[];
+  const int co_base = blockIdx.y * csnet::kMixCT;
+  csnet::mix_stage_weights(A, co_base, ws, threadIdx.x, kT);
+  __syncthreads();
+  const int pix = blockIdx.x * kT + threadIdx.x;
+  if (pix >= A.H * A.W) return;
+  csnet::mix_thread(A, ws, blockIdx.z, pix / A.W, pix % A.W, co_base);
+}
+
+// ---- MIX backward: data gradient of ONE path, gather over source elements -------------------------------------
+// dsrc[n][ci][ys][xs] for the source slice [c0, c0+cin) (dsrc holds exactly cin channels).
+__global__ void __launch_bounds__(kT) tr_mix_dgrad_kernel(const float* __restrict__ ddst, int C, int H, int W, const csnet::MixPath P,
+                                                          float* __restrict__ dsrc) {
+  const int ci = blockIdx.y, n = blockIdx.z;
+  const int pix = blockIdx.x * kT + threadIdx.x;
+  if (pix >= P.H * P.W) return;
+  const int ys = pix / P.W, xs = pix % P.W;
+  const size_t dplane = (size_t)H * W;
+  const float* dd = ddst + ((size_t)n * C + P.cout0) * dplane;
+  float g = 0.f;
+  if (P.ksize == 0) {
+    // adjoint of the bilinear up-sample by `up` (align_corners=False, source index clamped at 0)
+    const int up = P.up;
+    const float inv = 1.f / (float)up;
+    const float* d = dd + (size_t)ci * dplane;                 // resample paths map channel c -> cout0 + c
+    const int y_lo = ys * up - up < 0 ? 0 : ys * up - up, y_hi = (ys * up + 2 * up) > H ? H : ys * up + 2 * up;
+    const int x_lo = xs * up - up < 0 ? 0 : xs * up - up, x_hi = (xs * up + 2 * up) > W ? W : xs * up + 2 * up;
+    for (int oy = y_lo; oy < y_hi; ++oy) {
+      float sy = ((float)oy + 0.5f) * inv - 0.5f;
+      sy = sy < 0.f ? 0.f : sy;
+      const int y0 = (int)sy, y1 = y0 + (y0 < P.H - 1 ? 1 : 0);
+      const float ly = sy - (float)y0, wy = (y0 == ys ? 1.f - ly : 0.f) + (y1 == ys ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = x_lo; ox < x_hi; ++ox) {
+        float sx = ((float)ox + 0.5f) * inv - 0.5f;
+        sx = sx < 0.f ? 0.f : sx;
+        const int x0 = (int)sx, x1 = x0 + (x0 < P.W - 1 ? 1 : 0);
+        const float lx = sx - (float)x0, wx = (x0 == xs ? 1.f - lx : 0.f) + (x1 == xs ? lx : 0.f);
+        if (wx != 0.f) g += wy * wx * d[(size_t)oy * W + ox];
+      }
+    }
+    dsrc[((size_t)n * P.cin + ci) * P.H * P.W + pix] = g;
+    return;
+  }
+  // conv path: which conv-grid cell does this source element feed, and with which factor?
+  int yc = ys, xc = xs;
+  float factor = 1.f;
+  const int64_t plane = ((int64_t)n * P.C + P.c0 + ci) * (int64_t)P.H * P.W;
+  if (P.pre_avg) { yc >>= 1; xc >>= 1; factor = 0.25f; }
+  if (P.pool > 1) {
+    // max_pool2d backward routes the gradient to the FIRST maximum of the window (row-major scan, strict >)
+    const int ym = yc / P.pool, xm = xc / P.pool;
+    float best = -INFINITY;
+    int by = -1, bx = -1;
+    for (int py = 0; py < P.pool; ++py)
+      for (int px = 0; px < P.pool; ++px) {
+        const int ya = ym * P.pool + py, xa = xm * P.pool + px;
+        float v;
+        if (P.pre_avg) {
+          const int64_t b = plane + (int64_t)(2 * ya) * P.W + 2 * xa;
+          const float* s = reinterpret_cast<const float*>(P.src);
+          v = (((s[b] + s[b + 1]) + s[b + P.W]) + s[b + P.W + 1]) * 0.25f;
+        } else {
+          v = reinterpret_cast<const float*>(P.src)[plane + (int64_t)ya * P.W + xa];
+        }
+        if (v > best) { best = v; by = ya; bx = xa; }
+      }
+    if (by != yc || bx != xc) { dsrc[((size_t)n * P.cin + ci) * P.H * P.W + pix] = 0.f; return; }
+    yc = ym; xc = xm;
+  }
+  const int kk = P.ksize * P.ksize;
+  for (int ky = 0; ky < P.ksize; ++ky) {
+    const int ty = yc + P.pad - ky * P.dil;
+    if (ty < 0 || ty % P.stride) continue;
+    const int oy = ty / P.stride;
+    if (oy >= H) continue;
+    for (int kx = 0; kx < P.ksize; ++kx) {
+      const int tx = xc + P.pad - kx * P.dil;
+      if (tx < 0 || tx % P.stride) continue;
+      const int ox = tx / P.stride;
+      if (ox >= W) continue;
+      const float* wr = P.w + ((size_t)ci * kk + ky * P.ksize + kx) * P.cout;
+      const float* d = dd + (size_t)oy * W + ox;
+      for (int co = 0; co < P.cout; ++co) g += wr[co] * d[(size_t)co * dplane];
+    }
+  }
+  dsrc[((size_t)n * P.cin + ci) * P.H * P.W + pix] = g * factor;
+}
+
+// ---- MIX backward: weight gradient of ONE conv path: dw[ci][tap][co] (kernel layout), batch split over grid.z ----
+__global__ void __launch_bounds__(kT) tr_mix_wgrad_kernel(const float* __restrict__ ddst, int N, int C, int H, int W,
+                                                          const csnet::MixPath P, float* dw) {
+  constexpr int COT = 8;
+  const int ci = blockIdx.x, kk = P.ksize * P.ksize, tap = blockIdx.y % kk, cot = blockIdx.y / kk;
+  const int ky = tap / P.ksize, kx = tap % P.ksize, co0 = cot * COT;
+  const int div = (P.pre_avg ? 2 : 1) * P.pool, Hc = P.H / div, Wc = P.W / div;
+  float acc[COT];
+#pragma unroll
+  for (int t = 0; t < COT; ++t) acc[t] = 0.f;
+  const size_t dplane = (size_t)H * W;
+  for (int n = blockIdx.z; n < N; n += gridDim.z) {
+    const int64_t plane = ((int64_t)n * P.C + P.c0 + ci) * (int64_t)P.H * P.W;
+    const float* dd = ddst + ((size_t)n * C + P.cout0 + co0) * dplane;
+    for (int i = threadIdx.x; i < H * W; i += kT) {
+      const int oy = i / W, ox = i % W;
+      const int y = oy * P.stride - P.pad + ky * P.dil, x = ox * P.stride - P.pad + kx * P.dil;
+      if (y < 0 || y >= Hc || x < 0 || x >= Wc) continue;
+      const float v = csnet::fetch_pooled(P, plane, y, x);
+#pragma unroll
+      for (int t = 0; t < COT; ++t)
+        if (co0 + t < P.cout) acc[t] += v * dd[(size_t)t * dplane + i];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < COT; t += 3) {
+    float a = acc[t], b = t + 1 < COT ? acc[t + 1] : 0.f, c = t + 2 < COT ? acc[t + 2] : 0.f;
+    block_sum3(a, b, c);
+    if (threadIdx.x == 0) {
+      float* o = dw + ((size_t)ci * kk + tap) * P.cout + co0;
+      if (co0 + t < P.cout) atomicAdd(o + t, a);
+      if (t + 1 < COT && co0 + t + 1 < P.cout) atomicAdd(o + t + 1, b);
+      if (t + 2 < COT && co0 + t + 2 < P.cout) atomicAdd(o + t + 2, c);
+    }
+  }
+}
+
+// ---- loss, optimiser ---------------------------------------------------------------------------------------
+// F.binary_cross_entropy_with_logits(mean): loss = mean(max(z,0) - z*t + log1p(exp(-|z|))), dz = (sigmoid(z) - t) / n
+__global__ void __launch_bounds__(kT) bce_kernel(const float* __restrict__ z, const float* __restrict__ t, float* dz, float* loss,
+                                                 int64_t n, float inv_n, float grad_scale) {
+  float s = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
+    const float v = z[i], y = t[i];
+    s += fmaxf(v, 0.f) - v * y + log1pf(expf(-fabsf(v)));
+    if (dz) dz[i] = (1.f / (1.f + expf(-v)) - y) * inv_n * grad_scale;
+  }
+  block_sum3(s, d0, d1);
+  if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
+}
+
+// torch.optim.Adam (L2 weight decay folded into the gradient), many tensors per launch via a chunk table
+struct AdamChunk { float* p; const float* g; float* m; float* v; int32_t n; float wd; };
+__global__ void __launch_bounds__(kT) adam_kernel(const AdamChunk* chunks, float lr, float b1, float b2, float eps, float bc1,
+                                                  float bc2_sqrt, float grad_scale) {
+  const AdamChunk ch = chunks[blockIdx.x];
+  for (int i = threadIdx.x; i < ch.n; i += kT) {
+    const float p = ch.p[i];
+    const float g = ch.g[i] * grad_scale + ch.wd * p;
+    const float m = b1 * ch.m[i] + (1.f - b1) * g, v = b2 * ch.v[i] + (1.f - b2) * g * g;
+    ch.m[i] = m; ch.v[i] = v;
+    ch.p[i] = p - (lr / bc1) * (m / (sqrtf(v) / bc2_sqrt + eps));
+  }
+}
+
+thread_local std::string t_err;
+int tfail(int code, const char* what, cudaError_t e) {
+  t_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return code;
+}
+
+csnet::MixPath to_path(const csnet_train_path& q) {
+  csnet::MixPath m{};
+  m.src = q.src; m.w = q.w; m.dtype = CSNET_F32; m.C = q.C; m.H = q.H; m.W = q.W; m.c0 = q.c0; m.cin = q.cin;
+  m.pre_avg = q.pre_avg; m.pool = q.pool; m.ksize = q.ksize; m.dil = q.dil; m.stride = q.stride; m.pad = q.pad; m.up = q.up;
+  m.cout0 = q.cout0; m.cout = q.cout;
+  return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* csnet_train_last_error(void) { return t_err.c_str(); }
+
+int csnet_train_bn_stats(const float* z, int32_t N, int32_t C, int32_t HW, float* mean, float* var, void* stream) {
+  bn_stats_kernel<<<C, kT, 0, (cudaStream_t)stream>>>(z, N, C, HW, mean, var);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_bn_prelu_fwd(const float* z, float* y, int32_t N, int32_t C, int32_t HW, const float* mean, const float* var,
+                             const float* gamma, const float* beta, const float* slope, float eps, float* gap, void* stream) {
+  bn_prelu_fwd_kernel<<<dim3(C, N), kT, 0, (cudaStream_t)stream>>>(z, y, C, HW, mean, var, gamma, beta, slope, eps, gap);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_bn_prelu_bwd(const float* z, const float* dy, float* dz, int32_t N, int32_t C, int32_t HW, const float* mean,
+                             const float* var, const float* gamma, const float* beta, const float* slope, float eps,
+                             float* dgamma, float* dbeta, float* dslope, void* stream) {
+  bn_prelu_bwd_reduce_kernel<<<C, kT, 0, (cudaStream_t)stream>>>(z, dy, N, C, HW, mean, var, gamma, beta, slope, eps, dgamma, dbeta, dslope);
+  TR_CHECK(cudaGetLastError());
+  bn_prelu_bwd_apply_kernel<<<dim3(C, N), kT, 0, (cudaStream_t)stream>>>(z, dy, dz, N, C, HW, mean, var, gamma, beta, slope, eps, dgamma, dbeta);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_dw_conv(const float* x, const float* w, float* y, int32_t N, int32_t C, int32_t H, int32_t W, float scale,
+                        int32_t transposed, void* stream) {
+  dw_fwd_kernel<<<dim3((H * W + kT - 1) / kT, C, N), kT, 0, (cudaStream_t)stream>>>(x, w, y, C, H, W, scale, transposed);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_dw_wgrad(const float* x, const float* dy, float* dw, int32_t N, int32_t C, int32_t H, int32_t W, float scale, void* stream) {
+  dw_wgrad_kernel<<<dim3(C, 9), kT, 0, (cudaStream_t)stream>>>(x, dy, dw, N, C, H, W, scale);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* paths, int32_t n_paths, void* stream) {
+  if (n_paths < 1 || n_paths > CSNET_MAX_PATHS) { t_err = "csnet_train_mix_fwd: n_paths"; return CSNET_E_INVALID; }
+  csnet::MixArgs A{};
+  A.dst = dst; A.bias = nullptr; A.slope = nullptr; A.dtype = CSNET_F32; A.C = C; A.H = H; A.W = W; A.n_paths = n_paths;
+  size_t smem = 0;
+  for (int p = 0; p < n_paths; ++p) A.p[p] = to_path(paths[p]);
+  for (int co = 0; co < C; co += csnet::kMixCT) {
+    size_t f = 0;
+    for (int p = 0; p < n_paths; ++p) {
+      const csnet::MixPath& q = A.p[p];
+      if (q.ksize == 0) continue;
+      const int lo = co > q.cout0 ? co : q.cout0;
+      const int hi = (co + csnet::kMixCT) < (q.cout0 + q.cout) ? (co + csnet::kMixCT) : (q.cout0 + q.cout);
+      if (lo < hi) f += (size_t)q.cin * q.ksize * q.ksize * csnet::kMixCT;
+    }
+    smem = f > smem ? f : smem;
+  }
+  smem *= sizeof(float);
+  if (smem > 200 * 1024) { t_err = "csnet_train_mix_fwd: weights exceed shared memory"; return CSNET_E_UNSUPPORTED; }
+  if (smem > 48 * 1024) TR_CHECK(cudaFuncSetAttribute(tr_mix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tr_mix_fwd_kernel<<<dim3((H * W + kT - 1) / kT, (C + csnet::kMixCT - 1) / csnet::kMixCT, N), kT, smem, (cudaStream_t)stream>>>(A);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dsrc, void* stream) {
+  const csnet::MixPath P = to_path(*path);
+  tr_mix_dgrad_kernel<<<dim3((P.H * P.W + kT - 1) / kT, P.cin, N), kT, 0, (cudaStream_t)stream>>>(ddst, C, H, W, P, dsrc);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dw, void* stream) {
+  const csnet::MixPath P = to_path(*path);
+  if (P.ksize == 0) { t_err = "csnet_train_mix_wgrad: resample paths have no weights"; return CSNET_E_INVALID; }
+  const int kk = P.ksize * P.ksize;
+  TR_CHECK(cudaMemsetAsync(dw, 0, (size_t)P.cin * kk * P.cout * sizeof(float), (cudaStream_t)stream));
+  const int split = N < 32 ? N : 32;
+  tr_mix_wgrad_kernel<<<dim3(P.cin, kk * ((P.cout + 7) / 8), split), kT, 0, (cudaStream_t)stream>>>(ddst, N, C, H, W, P, dw);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_bce(const float* logits, const float* target, float* dlogits, float* loss, int64_t n, float grad_scale, void* stream) {
+  TR_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  const int blocks = (int)((n + kT * 8 - 1) / (kT * 8) < 1184 ? (n + kT * 8 - 1) / (kT * 8) : 1184);
+  bce_kernel<<<blocks < 1 ? 1 : blocks, kT, 0, (cudaStream_t)stream>>>(logits, target, dlogits, loss, n, 1.f / (float)n, grad_scale);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_adam(const void* chunk_table_device, int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step,
+                     float grad_scale, void* stream) {
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<n_chunks, kT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamChunk*>(chunk_table_device), lr, beta1, beta2,
+                                                        eps, bc1, sqrtf(bc2), grad_scale);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+}  // extern "C"

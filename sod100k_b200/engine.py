@@ -38,7 +38,7 @@ class ModelEngine:
         self.frozen = flag
 
     def _version(self) -> int:
-        h = 0
+        h = runtime.PARAM_EPOCH
         for t in list(self.model.parameters()) + list(self.model.buffers()):
             h = (h * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFF
         return h
@@ -70,10 +70,13 @@ class ModelEngine:
         if not x.is_cuda:
             raise runtime.EngineError("CSNet (B200 engine) needs a CUDA input; call model.cuda() / input.cuda() "
                                       "as the reference's test.py does — there is no CPU path")
-        if self.model.training or _has_hooks(self.model) or torch.is_grad_enabled() and x.requires_grad:
+        if self.model.training:
             from . import modular
 
             return modular.csnet_forward(self.model, x)
+        if _has_hooks(self.model) or (torch.is_grad_enabled() and x.requires_grad):
+            raise NotImplementedError("eval-mode module-granular execution (sub-module hooks / input gradients) is not "
+                                      "built; inference runs the fused program, training runs model.train()")
         N, _, H, W = x.shape
         return self.plan_for(N, H, W, x.device).forward(x)
 

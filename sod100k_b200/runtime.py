@@ -13,13 +13,17 @@ from . import ir
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsnet_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
+PARAM_EPOCH = 0      # bumped by in-place parameter updates that bypass torch's version counters (FusedAdam)
 _lib = None
 
 # every symbol include/csnet_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ("csnet_abi_version", "csnet_last_error", "csnet_device_count", "csnet_plan_create",
            "csnet_plan_set_blob", "csnet_plan_run", "csnet_plan_profile", "csnet_plan_tensor_ptr", "csnet_plan_read_tensor", "csnet_plan_launches",
-           "csnet_plan_arena_bytes", "csnet_plan_destroy", "csnet_plan_run_host")
+           "csnet_plan_arena_bytes", "csnet_plan_destroy", "csnet_plan_run_host",
+           "csnet_train_last_error", "csnet_train_bn_stats", "csnet_train_bn_prelu_fwd", "csnet_train_bn_prelu_bwd",
+           "csnet_train_dw_conv", "csnet_train_dw_wgrad", "csnet_train_mix_fwd", "csnet_train_mix_dgrad",
+           "csnet_train_mix_wgrad", "csnet_train_bce", "csnet_train_adam")
 
 
 class EngineError(RuntimeError):
