@@ -29,15 +29,26 @@ def _setup(tag, n, hw, seed):
     return m, cfg, params, buffers, x, t
 
 
-def _check_grads(m, ref_grads):
+def _oracle_fp64_grads(cfg, params, buffers, x, t, **kw):
+    """The same oracle in float64: the yardstick for how well-conditioned each gradient is.  Pruned checkpoints with
+    near-zero BN gammas / max-pool near-ties make some fp32 gradients noisy in ANY implementation (the fp32 oracle
+    itself is off by up to 2e-2 there), so the tolerance per tensor is max(1e-3, 3 x the fp32 oracle's own error)."""
+    p64 = {k: v.double() for k, v in params.items()}
+    b64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in buffers.items()}
+    _, g64, *_ = O.train_step(cfg, p64, b64, {}, torch.from_numpy(x).double(), torch.from_numpy(t).double(), **kw)
+    return g64
+
+
+def _check_grads(m, ref_grads, g64):
     worst = ("", 0.0)
     for name, p in m.named_parameters():
-        g, r = p.grad.detach().cpu(), ref_grads[name]
-        scale = max(r.abs().max().item(), 1e-6)
-        err = (g - r).abs().max().item() / scale
+        g, r, r64 = p.grad.detach().cpu().double(), ref_grads[name].double(), g64[name]
+        scale = max(r64.abs().max().item(), 1e-6)
+        noise = (r - r64).abs().max().item() / scale
+        err = (g - r64).abs().max().item() / scale
         if err > worst[1]:
             worst = (name, err)
-        assert err <= GRAD_TOL, (name, err, scale)
+        assert err <= max(GRAD_TOL, 3.0 * noise), (name, err, noise, scale)
     return worst
 
 
@@ -49,7 +60,7 @@ def test_forward_backward_matches_oracle(tag, hw):
     loss.backward()
     ref_loss, ref_grads, _, ref_buffers, _ = O.train_step(cfg, params, buffers, {}, torch.from_numpy(x), torch.from_numpy(t))
     assert abs(loss.item() - ref_loss.item()) <= 1e-5 * max(1.0, abs(ref_loss.item()))
-    _check_grads(m, ref_grads)
+    _check_grads(m, ref_grads, _oracle_fp64_grads(cfg, params, buffers, x, t))
     for k, v in m.state_dict().items():                      # running statistics / num_batches_tracked
         if k in ref_buffers:
             r = ref_buffers[k]
@@ -62,13 +73,14 @@ def test_two_trainer_steps_with_flops_regulariser_match_oracle():
     assert len(reference_param_groups(m)[1]) == 15 * 4 + 3 * 2
     opt = {}
     xt, tt = torch.from_numpy(x), torch.from_numpy(t)
+    g64 = _oracle_fp64_grads(cfg, params, buffers, x, t, flops_weight=3.0, flops_expand=1.0)
     for step in range(2):
         loss = tr.step(xt.cuda(), tt.cuda())
         ref_loss, ref_grads, params, buffers, opt = O.train_step(cfg, params, buffers, opt, xt, tt, lr=1e-4, weight_decay=5e-3,
                                                                  flops_weight=3.0, flops_expand=1.0)
         assert abs(loss.item() - ref_loss.item()) <= 2e-5 * max(1.0, abs(ref_loss.item())), step
         if step == 0:
-            _check_grads(m, ref_grads)
+            _check_grads(m, ref_grads, g64)
         for name, p in m.named_parameters():
             r = params[name]
             # Adam's first steps move every weight by ~lr * sign(g): an element whose gradient is numerically zero may
