@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer (default, BASELINE configs[1]) or train: fwd+bwd+Adam step, fp32 module-granular kernels")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--dtype", default="fp16", choices=["fp32", "fp16", "bf16"])
@@ -290,11 +292,88 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_train(a):
+    """Train step throughput (configs 3-4 shape, fp32 activations for now): images/s of forward + BCE + backward +
+    [DP: one flat-bucket all-reduce] + fused Adam, inputs resident in HBM; e2e adds the pinned H2D of images + masks
+    and the D2H of the loss."""
+    import torch
+    import torch.distributed as dist
+
+    from sod100k_b200 import checkpoints, roofline, synth
+    from sod100k_b200.trainer import Trainer
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, cfg, _ = checkpoints.build_from_npz(a.model)
+    model.cuda(local)
+    tr = Trainer(model, lr=1e-4, weight_decay=5e-3)
+    B, S = a.batch, a.size
+    xh = torch.from_numpy(synth.randn_images(B, S, S, 1234 + rank)).pin_memory()
+    th = torch.from_numpy(synth.random_masks(B, S, S, 1236 + rank)).pin_memory()
+    xd, td = xh.to(dev), th.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    step = lambda: tr.step(xd, td)
+    e2e = lambda: tr.step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)).item()
+    for _ in range(a.warmup):
+        step()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms = timed(step, a.steps)
+    clk = clocks.stop() if clocks else None
+    e2e()
+    ms_e2e = timed(e2e, a.steps)
+    if rank == 0:
+        peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+        el = roofline.forward_elements(cfg, S, S)
+        ips, ips_e2e = B * world * a.steps / (ms * 1e-3), B * world * a.steps / (ms_e2e * 1e-3)
+        train_bytes = int(2.51 * el["module"]) * 4          # 3*sum(I) + 2*sum(O) over modules (SURVEY 8d), fp32
+        print(json.dumps({
+            "metric": "images/sec CSNet fwd+bwd+Adam 224x224", "value": ips, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"{a.model} train step, {B} img/GPU x {S}x{S}, fp32 module-granular kernels",
+                       "global_batch": B * world, "parallelism": f"dp{world}: local BN, one flat-bucket all-reduce of "
+                       f"{tr.flat.bucket.numel()} fp32 gradients", "l2": "activations exceed L2"},
+            "clocks": clk,
+            "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": int((xh.numel() + th.numel()) * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": None,
+            "roofline": {"bound": "hbm", "achieved": ips / world * train_bytes / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": ips / world * train_bytes / 1e9 / peak, "traffic": None,
+                         "kernel": "whole train step (module-fused algorithmic bytes, fp32)"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     if a.impl == "reference":
         run_reference(a, rank)
+    elif a.mode == "train":
+        if a.batch == 256:
+            a.batch = 32
+        run_train(a)
     else:
         run_ours(a)
 

@@ -205,10 +205,11 @@ int csnet_train_bn_stats(const float* z, int32_t N, int32_t C, int32_t HW, float
  * Oct_bn_hook pools (csnet.py:403-404). */
 int csnet_train_bn_prelu_fwd(const float* z, float* y, int32_t N, int32_t C, int32_t HW, const float* mean, const float* var,
                              const float* gamma, const float* beta, const float* slope, float eps, float* gap, void* stream);
-/* autograd of the above: dz plus dgamma / dbeta / dslope ([C] each). */
+/* autograd of the above: dz plus dgamma / dbeta / dslope ([C] each).  frozen=1: mean / var were constants (eval-mode
+ * BatchNorm inside a training graph, as CSF+Res2Net/solver.py keeps its net), so the batch-statistic terms vanish. */
 int csnet_train_bn_prelu_bwd(const float* z, const float* dy, float* dz, int32_t N, int32_t C, int32_t HW, const float* mean,
                              const float* var, const float* gamma, const float* beta, const float* slope, float eps,
-                             float* dgamma, float* dbeta, float* dslope, void* stream);
+                             float* dgamma, float* dbeta, float* dslope, int32_t frozen, void* stream);
 /* Depthwise 3x3 pad 1 with effective weight scale*w (Conv2dX100, conv2d.py:104); transposed=1 gives the data gradient. */
 int csnet_train_dw_conv(const float* x, const float* w, float* y, int32_t N, int32_t C, int32_t H, int32_t W, float scale,
                         int32_t transposed, void* stream);

@@ -116,10 +116,11 @@ __global__ void __launch_bounds__(kT) bn_prelu_bwd_apply_kernel(const float* __r
                                                                 float* __restrict__ dz, int N, int C, int HW, const float* mean,
                                                                 const float* var, const float* gamma, const float* beta,
                                                                 const float* slope, float eps, const float* dgamma,
-                                                                const float* dbeta) {
+                                                                const float* dbeta, int frozen) {
   const int c = blockIdx.x, n = blockIdx.y;
   const float mu = mean[c], r = rsqrtf(var[c] + eps), g = gamma[c], b = beta[c], a = slope[c];
-  const float invM = 1.f / ((float)N * (float)HW), m1 = dbeta[c] * invM, m2 = dgamma[c] * invM;
+  // frozen statistics (eval-mode BN inside a training graph): mean / var are constants, no batch terms
+  const float invM = frozen ? 0.f : 1.f / ((float)N * (float)HW), m1 = dbeta[c] * invM, m2 = dgamma[c] * invM;
   const size_t off = ((size_t)n * C + c) * HW;
   for (int i = threadIdx.x; i < HW; i += kT) {
     const float xh = (z[off + i] - mu) * r, u = g * xh + b, d = dy[off + i];
@@ -360,10 +361,10 @@ int csnet_train_bn_prelu_fwd(const float* z, float* y, int32_t N, int32_t C, int
 
 int csnet_train_bn_prelu_bwd(const float* z, const float* dy, float* dz, int32_t N, int32_t C, int32_t HW, const float* mean,
                              const float* var, const float* gamma, const float* beta, const float* slope, float eps,
-                             float* dgamma, float* dbeta, float* dslope, void* stream) {
+                             float* dgamma, float* dbeta, float* dslope, int32_t frozen, void* stream) {
   bn_prelu_bwd_reduce_kernel<<<C, kT, 0, (cudaStream_t)stream>>>(z, dy, N, C, HW, mean, var, gamma, beta, slope, eps, dgamma, dbeta, dslope);
   TR_CHECK(cudaGetLastError());
-  bn_prelu_bwd_apply_kernel<<<dim3(C, N), kT, 0, (cudaStream_t)stream>>>(z, dy, dz, N, C, HW, mean, var, gamma, beta, slope, eps, dgamma, dbeta);
+  bn_prelu_bwd_apply_kernel<<<dim3(C, N), kT, 0, (cudaStream_t)stream>>>(z, dy, dz, N, C, HW, mean, var, gamma, beta, slope, eps, dgamma, dbeta, frozen);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }

@@ -74,9 +74,13 @@ class ModelEngine:
             from . import modular
 
             return modular.csnet_forward(self.model, x)
-        if _has_hooks(self.model) or (torch.is_grad_enabled() and x.requires_grad):
-            raise NotImplementedError("eval-mode module-granular execution (sub-module hooks / input gradients) is not "
-                                      "built; inference runs the fused program, training runs model.train()")
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.model.parameters()))
+        if _has_hooks(self.model) or (needs_graph and getattr(self.model, "frozen_bn_training", False)):
+            # sub-module hooks, or training with the net kept in eval mode (frozen BatchNorm, as CSF+Res2Net/solver.py
+            # does): run module by module so hooks fire and autograd sees every piece
+            from . import modular
+
+            return modular.csnet_forward(self.model, x)
         N, _, H, W = x.shape
         return self.plan_for(N, H, W, x.device).forward(x)
 

@@ -25,11 +25,8 @@ def _as_list(xset):
 
 
 def _bn_act(m_bn, m_prelu, z):
-    if m_bn.training:
-        return T.bn_prelu_train(z, m_bn, m_prelu)
-    # eval-mode statistics inside a training graph (frozen BN): same kernels, running statistics as the "batch" ones
-    raise NotImplementedError("module-granular execution with eval-mode BatchNorm is not built; use model.eval() inference "
-                              "(fused program) or model.train()")
+    """train mode: batch statistics (+ running-stat update); eval mode inside a graph: frozen running statistics."""
+    return T.bn_prelu_train(z, m_bn, m_prelu)
 
 
 def _flops_term(module, gaps, bns):

@@ -35,7 +35,7 @@ def lib():
         f32p, vp, i32, i64, f = C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float
         l.csnet_train_bn_stats.argtypes = [f32p, i32, i32, i32, f32p, f32p, vp]
         l.csnet_train_bn_prelu_fwd.argtypes = [f32p, f32p, i32, i32, i32, f32p, f32p, f32p, f32p, f32p, f, f32p, vp]
-        l.csnet_train_bn_prelu_bwd.argtypes = [f32p, f32p, f32p, i32, i32, i32, f32p, f32p, f32p, f32p, f32p, f, f32p, f32p, f32p, vp]
+        l.csnet_train_bn_prelu_bwd.argtypes = [f32p, f32p, f32p, i32, i32, i32, f32p, f32p, f32p, f32p, f32p, f, f32p, f32p, f32p, i32, vp]
         l.csnet_train_dw_conv.argtypes = [f32p, f32p, f32p, i32, i32, i32, i32, f, i32, vp]
         l.csnet_train_dw_wgrad.argtypes = [f32p, f32p, f32p, i32, i32, i32, i32, f, vp]
         l.csnet_train_mix_fwd.argtypes = [f32p, i32, i32, i32, i32, C.POINTER(TrainPath), i32, vp]
@@ -140,16 +140,20 @@ class BnPreluFn(torch.autograd.Function):
     biased variance (for the running-stat update) and the per-image channel means of the output (Oct_bn_hook's GAP)."""
 
     @staticmethod
-    def forward(ctx, z, gamma, beta, slope):
+    def forward(ctx, z, gamma, beta, slope, frozen_mean=None, frozen_var=None):
         z = _f32(z)
         n, c, h, w = z.shape
-        mean = torch.empty(c, dtype=torch.float32, device=z.device)
-        var = torch.empty_like(mean)
         y = torch.empty_like(z)
         gap = torch.empty((n, c), dtype=torch.float32, device=z.device)
         st = _stream(z)
         g, b, a = _f32(gamma.detach()), _f32(beta.detach()), _f32(slope.detach())
-        _ck(lib().csnet_train_bn_stats(z.data_ptr(), n, c, h * w, mean.data_ptr(), var.data_ptr(), st), "csnet_train_bn_stats")
+        ctx.frozen = frozen_mean is not None
+        if ctx.frozen:                                   # eval-mode BN: running statistics, treated as constants
+            mean, var = _f32(frozen_mean.detach()).clone(), _f32(frozen_var.detach()).clone()
+        else:
+            mean = torch.empty(c, dtype=torch.float32, device=z.device)
+            var = torch.empty_like(mean)
+            _ck(lib().csnet_train_bn_stats(z.data_ptr(), n, c, h * w, mean.data_ptr(), var.data_ptr(), st), "csnet_train_bn_stats")
         _ck(lib().csnet_train_bn_prelu_fwd(z.data_ptr(), y.data_ptr(), n, c, h * w, mean.data_ptr(), var.data_ptr(), g.data_ptr(),
                                            b.data_ptr(), a.data_ptr(), BN_EPS, gap.data_ptr(), st), "csnet_train_bn_prelu_fwd")
         ctx.save_for_backward(z, mean, var, g, b, a)
@@ -165,12 +169,15 @@ class BnPreluFn(torch.autograd.Function):
         dgamma, dbeta, dslope = (torch.empty(c, dtype=torch.float32, device=z.device) for _ in range(3))
         _ck(lib().csnet_train_bn_prelu_bwd(z.data_ptr(), dy.data_ptr(), dz.data_ptr(), n, c, h * w, mean.data_ptr(), var.data_ptr(),
                                            g.data_ptr(), b.data_ptr(), a.data_ptr(), BN_EPS, dgamma.data_ptr(), dbeta.data_ptr(),
-                                           dslope.data_ptr(), _stream(z)), "csnet_train_bn_prelu_bwd")
-        return dz, dgamma, dbeta, dslope
+                                           dslope.data_ptr(), int(ctx.frozen), _stream(z)), "csnet_train_bn_prelu_bwd")
+        return dz, dgamma, dbeta, dslope, None, None
 
 
 def bn_prelu_train(z, bn: torch.nn.BatchNorm2d, prelu: torch.nn.PReLU):
     """Apply + update running statistics the way nn.BatchNorm2d does in train mode (momentum 0.1, unbiased variance)."""
+    if not bn.training:                                  # frozen statistics (module left in eval mode)
+        y, _, _, gap = BnPreluFn.apply(z, bn.weight, bn.bias, prelu.weight, bn.running_mean, bn.running_var)
+        return y, gap
     y, mean, var, gap = BnPreluFn.apply(z, bn.weight, bn.bias, prelu.weight)
     if bn.track_running_stats:
         with torch.no_grad():
