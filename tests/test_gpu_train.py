@@ -41,19 +41,21 @@ def _oracle_fp64_grads(cfg, params, buffers, x, t, **kw):
 
 
 def _check_grads(m, ref_grads, g64):
-    worst, errs = ("", 0.0), []
+    worst, errs, noises = ("", 0.0), [], []
     for name, p in m.named_parameters():
         g, r, r64 = p.grad.detach().cpu().double(), ref_grads[name].double(), g64[name]
         scale = max(r64.abs().max().item(), 1e-6)
         noise = (r - r64).abs().max().item() / scale
         err = (g - r64).abs().max().item() / scale
         errs.append(err)
+        noises.append(noise)
         if err > worst[1]:
             worst = (name, err)
         # cancellation-dominated gradients (scale << the terms summed) amplify summation-order differences: allow 30x the
         # fp32 oracle's own deviation from float64 there, 1e-3 everywhere else
         assert err <= max(GRAD_TOL, 30.0 * noise), (name, err, noise, scale)
-    assert float(np.median(errs)) <= 2e-4, float(np.median(errs))       # and the bulk of the tensors agree tightly
+    # and the bulk of the tensors agree as tightly as the conditioning of this network allows
+    assert float(np.median(errs)) <= max(2e-4, 10.0 * float(np.median(noises))), (float(np.median(errs)), float(np.median(noises)))
     return worst
 
 
