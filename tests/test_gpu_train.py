@@ -41,21 +41,22 @@ def _oracle_fp64_grads(cfg, params, buffers, x, t, **kw):
 
 
 def _check_grads(m, ref_grads, g64):
-    worst, errs, noises = ("", 0.0), [], []
+    """Per tensor: max error <= 1e-3 of the tensor's scale wherever the gradient is well-conditioned (the fp32 oracle
+    itself is within 1e-4 of float64 there); cancellation-dominated tensors get 30x the fp32 oracle's own deviation.
+    Globally: relative L2 error of the whole gradient vector <= max(1e-3, 10x the fp32 oracle's)."""
+    num = den = nnum = 0.0
+    worst = ("", 0.0)
     for name, p in m.named_parameters():
         g, r, r64 = p.grad.detach().cpu().double(), ref_grads[name].double(), g64[name]
         scale = max(r64.abs().max().item(), 1e-6)
         noise = (r - r64).abs().max().item() / scale
         err = (g - r64).abs().max().item() / scale
-        errs.append(err)
-        noises.append(noise)
+        num += (g - r64).pow(2).sum().item(); nnum += (r - r64).pow(2).sum().item(); den += r64.pow(2).sum().item()
         if err > worst[1]:
             worst = (name, err)
-        # cancellation-dominated gradients (scale << the terms summed) amplify summation-order differences: allow 30x the
-        # fp32 oracle's own deviation from float64 there, 1e-3 everywhere else
-        assert err <= max(GRAD_TOL, 30.0 * noise), (name, err, noise, scale)
-    # and the bulk of the tensors agree as tightly as the conditioning of this network allows
-    assert float(np.median(errs)) <= max(2e-4, 10.0 * float(np.median(noises))), (float(np.median(errs)), float(np.median(noises)))
+        assert err <= (GRAD_TOL if noise <= 1e-4 else max(GRAD_TOL, 30.0 * noise)), (name, err, noise, scale)
+    rel, rel_noise = (num / den) ** 0.5, (nnum / den) ** 0.5
+    assert rel <= max(1e-3, 10.0 * rel_noise), (rel, rel_noise)
     return worst
 
 
