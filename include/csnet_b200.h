@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CSNET_ABI_VERSION 3
+#define CSNET_ABI_VERSION 4
 
 enum { CSNET_F32 = 0, CSNET_F16 = 1, CSNET_BF16 = 2 };
 
@@ -62,7 +62,8 @@ typedef struct {
  * ksize > 0 — convolution path, replaces the F.conv2d calls of gOctaveConv.forward
  *   (CSNet/model/csnet.py:702-717), Conv2dX100.forward (CSNet/model/conv2d.py:104) and
  *   MSBlock.forward (csnet.py:141-146), with the resampling the reference does around them folded
- *   into the read: pre_avg=1 applies avg_pool2d(2,2) first (csnet.py:679-680), pool=k applies
+ *   into the read: pre_avg=f (1 means 2) down-samples by f first — avg_pool2d(2,2) for f=2 (csnet.py:679-680) and
+ *   F.interpolate(bilinear) to 1/f size for f=2,4,8 (CSF+Res2Net/networks/gOctConv.py:101-102) —, pool=k applies
  *   max_pool2d(k,k) next (csnet.py:709-712); the convolution (cross-correlation, zero padding `pad`,
  *   dilation `dil`, stride `stride`) then runs on that pooled grid.
  *   A plain 1x1 conv path may carry up > 1: the source is bilinearly up-sampled FIRST (same linear map as the
@@ -85,6 +86,9 @@ typedef struct {
 enum {
   CSNET_OP_MIX = 1,       /* dst = prelu(sum_paths + bias)   — gOctaveCBR / MSBlock / cls_layer */
   CSNET_OP_DW = 2,        /* dst = prelu(dw3x3(src) + bias)  — SimplifiedGOctConvBR branch */
+  CSNET_OP_GN = 4,        /* dst = prelu(GroupNorm(src)): per-image statistics over (C/groups, H, W), eps 1e-5 — the CSF+Res2Net
+                             head (CSF+Res2Net/networks/gOctConv.py:133, csf_res2net.py:220).  paths[0].src = input,
+                             paths[0].up = groups, ext_off[0] / ext_off[1] = gamma / beta, slope_off = PReLU slope. */
   CSNET_OP_ILBLOCK = 3    /* whole ILBlock of the 1x1 kind in one kernel (ILBlock.forward, csnet.py:72-76):
                              paths[0].src / paths[1].src = high / low resolution inputs (cin = channels),
                              dst / dst2 = high / low resolution outputs (dst2 = -1 for a 2->1 block);

@@ -15,10 +15,12 @@
 #ifdef CSNET_HOST_EMU
 #include <math.h>
 #define CSNET_DEV inline
+#define CSNET_HD inline
 #else
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #define CSNET_DEV __device__ __forceinline__
+#define CSNET_HD __host__ __device__ __forceinline__
 #endif
 
 namespace csnet {
@@ -73,16 +75,23 @@ CSNET_DEV void st_elem(void* p, int dtype, int64_t i, float v) {
   reinterpret_cast<float*>(p)[i] = v;
 }
 
-// Value of the (avg-pooled, max-pooled) source plane at pooled-grid position (y, x); y, x in range.
+// pre_avg = f in {0, 1 (legacy: 2), 2, 4, 8}: down-sample by f first.  f = 2 is avg_pool2d(2,2) (csnet.py:679-680) and,
+// identically, F.interpolate(bilinear) to half size; f = 4 / 8 is F.interpolate(bilinear, align_corners=False) to a
+// quarter / eighth (CSF+Res2Net/networks/gOctConv.py:101-102): source index f*d + f/2 - 0.5, i.e. the mean of the
+// 2x2 pixels at offset f/2 - 1 of each f x f cell.
+CSNET_HD int pre_factor(int pre_avg) { return pre_avg == 0 ? 1 : (pre_avg == 1 ? 2 : pre_avg); }
+
+// Value of the (down-sampled, max-pooled) source plane at pooled-grid position (y, x); y, x in range.
 CSNET_DEV float fetch_pooled(const MixPath& P, int64_t plane, int y, int x) {
   if (!P.pre_avg && P.pool == 1) return ld_elem(P.src, P.dtype, plane + (int64_t)y * P.W + x);
+  const int f = pre_factor(P.pre_avg), fo = (f >> 1) - 1;
   float m = -INFINITY;
   for (int py = 0; py < P.pool; ++py) {
     for (int px = 0; px < P.pool; ++px) {
       const int yy = y * P.pool + py, xx = x * P.pool + px;
       float v;
       if (P.pre_avg) {
-        const int64_t b = plane + (int64_t)(2 * yy) * P.W + 2 * xx;
+        const int64_t b = plane + (int64_t)(f * yy + fo) * P.W + f * xx + fo;
         v = ((ld_elem(P.src, P.dtype, b) + ld_elem(P.src, P.dtype, b + 1)) + ld_elem(P.src, P.dtype, b + P.W)) +
             ld_elem(P.src, P.dtype, b + P.W + 1);
         v *= 0.25f;
@@ -160,7 +169,7 @@ CSNET_DEV void mix_thread(const MixArgs& A, const float* ws, int n, int oy, int 
     if (lo >= hi) continue;
     const int64_t plane_sz = (int64_t)P.H * P.W;
     if (P.ksize > 0) {
-      const int div = (P.pre_avg ? 2 : 1) * P.pool;
+      const int div = pre_factor(P.pre_avg) * P.pool;
       const int Hc = P.up > 1 ? P.H * P.up : P.H / div, Wc = P.up > 1 ? P.W * P.up : P.W / div;
       const int kk = P.ksize * P.ksize;
       for (int ci = 0; ci < P.cin; ++ci) {
@@ -204,6 +213,18 @@ CSNET_DEV void mix_thread(const MixArgs& A, const float* ws, int n, int oy, int 
     }
   }
 }
+
+// GroupNorm(groups) + PReLU (CSF+Res2Net/networks/gOctConv.py:133, csf_res2net.py:220-224): statistics per (image, group)
+// over (C/groups, H, W), eps 1e-5, biased variance; then y = prelu(gamma[c] * (x - mean) * rstd + beta[c]).
+struct GnArgs {
+  const void* src;
+  void* dst;
+  const float* gamma;
+  const float* beta;
+  const float* slope;        // nullptr: no PReLU
+  float* stats;              // [N][groups][2] = (mean, rstd), written by the stats pass
+  int32_t src_dtype, dst_dtype, C, HW, groups;
+};
 
 // Depthwise 3x3 (pad 1) + bias + PReLU: one column x, rows [oy0, oy0 + kDwRows) of plane (n, c).
 CSNET_DEV void dw_thread(const DwArgs& A, int n, int c, int oy0, int ox) {

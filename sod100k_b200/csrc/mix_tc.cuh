@@ -58,11 +58,12 @@ __device__ __forceinline__ float fetch_pooled16(const MixPath& P, const uint16_t
   const int W = P.W, pool = P.pool;
   float m = -INFINITY;
   if (P.pre_avg) {
+    const int f = pre_factor(P.pre_avg), fo = (f >> 1) - 1;   // fo is even (0, 0... ) only for f = 2; handled below
     for (int py = 0; py < pool; ++py) {
-      const uint16_t* r = plane + (size_t)(2 * (y * pool + py)) * W + 2 * (x * pool);
+      const uint16_t* r = plane + (size_t)(f * (y * pool + py) + fo) * W + f * (x * pool) + fo;
       for (int px = 0; px < pool; ++px) {
-        const float2 a = Pack<T>::to_f2(*reinterpret_cast<const uint32_t*>(r + 2 * px));
-        const float2 b = Pack<T>::to_f2(*reinterpret_cast<const uint32_t*>(r + W + 2 * px));
+        const float2 a = Pack<T>::to_f2(*reinterpret_cast<const uint32_t*>(r + f * px));
+        const float2 b = Pack<T>::to_f2(*reinterpret_cast<const uint32_t*>(r + W + f * px));
         const float v = (((a.x + a.y) + b.x) + b.y) * 0.25f;
         m = v > m ? v : m;
       }
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
   const int n = blockIdx.z;
   const int oy0 = (blockIdx.x / G.tiles_x) * kTcTH, ox0 = (blockIdx.x % G.tiles_x) * kTcTW;
   constexpr int M16 = MT * 16;
+  const int m_base = blockIdx.y * M16;                      // this CTA's slice of the output channels
 
   float acc[MT][4][4];
 #pragma unroll
@@ -113,12 +115,13 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
       ++p1;
     }
     const int cin = P0.cin, srcW = P0.W;
-    const int div = (P0.pre_avg ? 2 : 1) * P0.pool;
+    const int div = pre_factor(P0.pre_avg) * P0.pool;
     const int Hc = P0.up > 1 ? P0.H * P0.up : P0.H / div, Wc = P0.up > 1 ? P0.W * P0.up : P0.W / div;
     const int64_t plane_sz = (int64_t)P0.H * P0.W;
     const bool plain = !P0.pre_avg && P0.pool == 1 && P0.up == 1 && P0.dtype != DT_F32;   // raw 16-bit copy
     const bool vec = plain && (srcW & 3) == 0;
-    const bool pooled16 = P0.dtype != DT_F32 && P0.up == 1 && (P0.pre_avg || P0.pool > 1) && (srcW & 1) == 0;
+    // typed 32-bit pair loads need 4-byte alignment: true for f = 2 (offset 0); f = 4 / 8 start at odd pixels
+    const bool pooled16 = P0.dtype != DT_F32 && P0.up == 1 && (P0.pre_avg || P0.pool > 1) && (srcW & 1) == 0 && pre_factor(P0.pre_avg) <= 2;
     const int XH = kTcTH + 2 * pad, padL = tc_pad_left(pad), PS = tc_plane_halves(pad);
     const int XW = vec ? tc_xw_vec(pad) : tc_xw_exact(pad);
     const int64_t src_base = ((int64_t)n * P0.C + P0.c0) * plane_sz;
@@ -177,10 +180,11 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
         if (lane < kc8) {
           const bool k_ok = lane < kc_live;
           for (int tap = 0; tap < kk; ++tap) {
-            const float* wsrc = pw + ((int64_t)(c0 + lane) * kk + tap) * pcout - pcout0;
+            const float* wsrc = pw + ((int64_t)(c0 + lane) * kk + tap) * pcout - pcout0 + m_base;
 #pragma unroll
             for (int m = warp; m < M16; m += kTcWarps) {
-              const float w = (k_ok && m >= pcout0 && m < pcout0 + pcout) ? __ldg(wsrc + m) : 0.f;
+              const int mg = m_base + m;
+              const float w = (k_ok && mg >= pcout0 && mg < pcout0 + pcout) ? __ldg(wsrc + m) : 0.f;
               Ws[(tap * M16 + m) * WR + lane] = (uint16_t)(Pack<T>::from_f2(w, 0.f) & 0xffffu);
             }
           }
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int m = mt * 16 + g + 8 * h;
+      const int m = m_base + mt * 16 + g + 8 * h;
       if (m >= A.C) continue;
       const float bias = A.bias ? __ldg(A.bias + m) : 0.f;
       const bool has_slope = A.slope != nullptr;

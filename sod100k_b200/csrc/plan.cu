@@ -58,6 +58,54 @@ __global__ void __launch_bounds__(kThreads) dw_generic_kernel(const __grid_const
   csnet::dw_thread(A, blockIdx.z, blockIdx.y, (item / A.W) * csnet::kDwRows, item % A.W);
 }
 
+// GroupNorm statistics: one CTA per (group, image)
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const __grid_constant__ csnet::GnArgs A) {
+  const int g = blockIdx.x, n = blockIdx.y, cpg = A.C / A.groups;
+  const int64_t base = ((int64_t)n * A.C + (int64_t)g * cpg) * A.HW, cnt = (int64_t)cpg * A.HW;
+  __shared__ float sh[2][kThreads / 32];
+  __shared__ float mu_s;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < cnt; i += kThreads) s += csnet::ld_elem(A.src, A.src_dtype, base + i);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) t += sh[0][i];
+    mu_s = t / (float)cnt;
+  }
+  __syncthreads();
+  const float mu = mu_s;
+  float q = 0.f;
+  for (int64_t i = threadIdx.x; i < cnt; i += kThreads) {
+    const float d = csnet::ld_elem(A.src, A.src_dtype, base + i) - mu;
+    q += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) sh[1][threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) t += sh[1][i];
+    A.stats[((int64_t)n * A.groups + g) * 2] = mu;
+    A.stats[((int64_t)n * A.groups + g) * 2 + 1] = rsqrtf(t / (float)cnt + 1e-5f);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gn_apply_kernel(const __grid_constant__ csnet::GnArgs A) {
+  const int c = blockIdx.y, n = blockIdx.z, g = c / (A.C / A.groups);
+  const float mu = A.stats[((int64_t)n * A.groups + g) * 2], r = A.stats[((int64_t)n * A.groups + g) * 2 + 1];
+  const float ga = A.gamma[c] * r, be = A.beta[c] - mu * ga;
+  const bool has_slope = A.slope != nullptr;
+  const float sl = has_slope ? A.slope[c] : 1.f;
+  const int64_t base = ((int64_t)n * A.C + c) * A.HW;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < A.HW; i += gridDim.x * kThreads) {
+    float v = csnet::ld_elem(A.src, A.src_dtype, base + i) * ga + be;
+    if (has_slope) v = v > 0.f ? v : sl * v;
+    csnet::st_elem(A.dst, A.dst_dtype, base + i, v);
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -95,6 +143,8 @@ struct csnet_plan {
   void* h_out[2] = {nullptr, nullptr};
   size_t h_in_bytes = 0, h_out_bytes = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  float* gn_stats = nullptr;      // [max_batch][max groups][2] scratch of the GroupNorm ops
+  int gn_groups_max = 0;
 
   void* tensor_ptr(int t, int N, const void* const* ext) const {
     const csnet_tensor_desc& d = tensors[t];
@@ -125,8 +175,21 @@ int validate(const csnet_plan& P) {
       snprintf(buf, sizeof buf, "op %zu: %s", i, why);
       return fail(CSNET_E_INVALID, buf);
     };
-    if (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_DW && op.kind != CSNET_OP_ILBLOCK) return bad("unknown kind");
+    if (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_DW && op.kind != CSNET_OP_ILBLOCK && op.kind != CSNET_OP_GN)
+      return bad("unknown kind");
     if (op.dst < 0 || op.dst >= nt) return bad("dst out of range");
+    if (op.kind == CSNET_OP_GN) {
+      if (op.n_paths != 1) return bad("GN takes one input");
+      const int a = op.paths[0].src, groups = op.paths[0].up;
+      if (a < 0 || a >= nt || a == op.dst) return bad("GN input");
+      const csnet_tensor_desc &X = P.tensors[a], &Y = P.tensors[op.dst];
+      if (X.C != Y.C || X.H != Y.H || X.W != Y.W) return bad("GN shape");
+      if (groups < 1 || X.C % groups) return bad("GN groups must divide the channels");
+      if (op.ext_off[0] < 0 || op.ext_off[0] + X.C > P.blob_floats || op.ext_off[1] < 0 || op.ext_off[1] + X.C > P.blob_floats)
+        return bad("GN gamma/beta outside blob");
+      if (op.slope_off >= 0 && op.slope_off + X.C > P.blob_floats) return bad("slope outside blob");
+      continue;
+    }
     if (op.kind == CSNET_OP_ILBLOCK) {
       if (op.n_paths != 2) return bad("ILBLOCK takes two inputs");
       if (op.dst2 >= nt) return bad("dst2 out of range");
@@ -181,7 +244,8 @@ int validate(const csnet_plan& P) {
         if (q.up > 1 && (q.ksize != 1 || q.pool != 1 || q.pre_avg || q.stride != 1 || q.pad != 0))
           return bad("input-side up-sampling is only defined for plain 1x1 conv paths");
         if (q.pool < 1 || q.stride < 1 || q.dil < 1 || q.pad < 0) return bad("conv path params");
-        const int div = (q.pre_avg ? 2 : 1) * q.pool;
+        if (q.pre_avg != 0 && q.pre_avg != 1 && q.pre_avg != 2 && q.pre_avg != 4 && q.pre_avg != 8) return bad("pre_avg must be 0, 1, 2, 4 or 8");
+        const int div = csnet::pre_factor(q.pre_avg) * q.pool;
         if (S.H % div || S.W % div) return bad("pooling does not divide the source");
         const int Hc = q.up > 1 ? S.H * q.up : S.H / div, Wc = q.up > 1 ? S.W * q.up : S.W / div;
         const int Ho = (Hc + 2 * q.pad - q.dil * (q.ksize - 1) - 1) / q.stride + 1;
@@ -281,7 +345,7 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   static const bool use_tma = [] { const char* e = getenv("CSNET_TMA"); return e && e[0] == '1'; }();   // opt-in until the 16-byte start-alignment rule is met
   A.tma_h = use_tma && (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
   A.tma_l = use_tma && ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
-  static const int cand[][2] = {{32, 32}, {16, 32}, {8, 16}};        // the instantiated tile geometries
+  static const int cand[][2] = {{32, 32}, {16, 64}, {16, 32}, {8, 16}};   // the instantiated tile geometries
   double best = -1;
   for (auto& c : cand) {
     csnet::IlArgs T = A;
@@ -302,6 +366,7 @@ size_t il_smem_of(const csnet::IlArgs& A) {
 template <typename T>
 void launch_il_t(const csnet::IlArgs& A, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& h, const CUtensorMap& l) {
   if (A.TH == 32) csnet::il_block_kernel<T, 32, 32><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
+  else if (A.TH == 16 && A.TW == 64) csnet::il_block_kernel<T, 16, 64><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
   else if (A.TH == 16) csnet::il_block_kernel<T, 16, 32><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
   else csnet::il_block_kernel<T, 8, 16><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
 }
@@ -309,6 +374,7 @@ void launch_il_t(const csnet::IlArgs& A, dim3 grid, size_t smem, cudaStream_t st
 template <typename T>
 cudaError_t set_il_smem_t(int bytes) {
   cudaError_t e = cudaFuncSetAttribute(csnet::il_block_kernel<T, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_block_kernel<T, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_block_kernel<T, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_block_kernel<T, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   return e;
@@ -349,8 +415,8 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
     kk = q.ksize * q.ksize > kk ? q.ksize * q.ksize : kk;
     cin_max = q.cin > cin_max ? q.cin : cin_max;
   }
-  if (dt < 0 || nconv == 0 || D.C > 80 || pad > csnet::kTcMaxPad) return c;
-  c.mt = (D.C + 15) / 16;
+  if (dt < 0 || nconv == 0 || pad > csnet::kTcMaxPad) return c;
+  c.mt = D.C > 80 ? 5 : (D.C + 15) / 16;             // more than 80 output channels: 80-channel slices over grid.y
   c.dtype = dt;
   c.xs_halves = csnet::tc_plane_halves(pad);
   c.kk = kk;
@@ -435,6 +501,12 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   const size_t arena_bytes = (size_t)P->arena_per_image * (size_t)max_batch + 256;
   e = cudaMalloc(&P->arena, arena_bytes);
   if (e != cudaSuccess) return cleanup(CSNET_E_NOMEM, std::string("cudaMalloc(arena): ") + cudaGetErrorString(e));
+  for (const auto& op : P->ops)
+    if (op.kind == CSNET_OP_GN && op.paths[0].up > P->gn_groups_max) P->gn_groups_max = op.paths[0].up;
+  if (P->gn_groups_max > 0) {
+    e = cudaMalloc(&P->gn_stats, (size_t)max_batch * P->gn_groups_max * 2 * sizeof(float));
+    if (e != cudaSuccess) return cleanup(CSNET_E_NOMEM, std::string("cudaMalloc(gn stats): ") + cudaGetErrorString(e));
+  }
   // dynamic shared memory each MIX op needs (weights of one cout tile)
   P->op_smem.assign(P->ops.size(), 0);
   P->op_tc.assign(P->ops.size(), TcChoice());
@@ -502,12 +574,25 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     const TcChoice& tc = P->op_tc[i];
     csnet::TcGeom G{(D.W + csnet::kTcTW - 1) / csnet::kTcTW, tc.xs_halves, tc.kc};
-    dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), 1, N);
+    dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), (D.C + tc.mt * 16 - 1) / (tc.mt * 16), N);
     launch_mix_tc(tc, grid, P->op_smem[i], stream, A, G);
   } else if (op.kind == CSNET_OP_MIX) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     dim3 grid((D.H * D.W + kThreads - 1) / kThreads, (D.C + csnet::kMixCT - 1) / csnet::kMixCT, N);
     mix_generic_kernel<<<grid, kThreads, P->op_smem[i], stream>>>(A);
+  } else if (op.kind == CSNET_OP_GN) {
+    const csnet_tensor_desc& S = P->tensors[op.paths[0].src];
+    csnet::GnArgs A{};
+    A.src = P->tensor_ptr(op.paths[0].src, N, ext_ptrs);
+    A.dst = P->tensor_ptr(op.dst, N, ext_ptrs);
+    A.gamma = P->blob + op.ext_off[0];
+    A.beta = P->blob + op.ext_off[1];
+    A.slope = op.slope_off >= 0 ? P->blob + op.slope_off : nullptr;
+    A.stats = P->gn_stats;
+    A.src_dtype = S.dtype; A.dst_dtype = D.dtype; A.C = D.C; A.HW = D.H * D.W; A.groups = op.paths[0].up;
+    gn_stats_kernel<<<dim3(A.groups, N), kThreads, 0, stream>>>(A);
+    const int bx = (A.HW + kThreads * 4 - 1) / (kThreads * 4);
+    gn_apply_kernel<<<dim3(bx < 1 ? 1 : bx, D.C, N), kThreads, 0, stream>>>(A);
   } else if (op.kind == CSNET_OP_ILBLOCK) {
     csnet::IlArgs A;
     if (!make_il(*P, op, N, ext_ptrs, &A)) return fail(CSNET_E_UNSUPPORTED, "ILBLOCK op does not fit shared memory");
@@ -597,7 +682,12 @@ int csnet_plan_read_tensor(csnet_plan* P, int32_t tensor, int32_t N, void* dst, 
   return CSNET_OK;
 }
 
-int32_t csnet_plan_launches(const csnet_plan* P) { return P ? (int32_t)P->ops.size() : 0; }
+int32_t csnet_plan_launches(const csnet_plan* P) {
+  if (!P) return 0;
+  int32_t n = 0;
+  for (const auto& op : P->ops) n += op.kind == CSNET_OP_GN ? 2 : 1;
+  return n;
+}
 
 int64_t csnet_plan_arena_bytes(const csnet_plan* P) { return P ? P->arena_per_image * (int64_t)P->max_batch : 0; }
 
@@ -606,6 +696,7 @@ void csnet_plan_destroy(csnet_plan* P) {
   if (P->blob || P->arena) cudaSetDevice(P->device);
   if (P->blob) cudaFree(P->blob);
   if (P->arena) cudaFree(P->arena);
+  if (P->gn_stats) cudaFree(P->gn_stats);
   for (int b = 0; b < 2; ++b) {
     if (P->h_in[b]) cudaFree(P->h_in[b]);
     if (P->h_out[b]) cudaFree(P->h_out[b]);

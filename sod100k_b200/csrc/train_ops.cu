@@ -409,6 +409,7 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
 
 int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dsrc, void* stream) {
   const csnet::MixPath P = to_path(*path);
+  if (P.pre_avg > 2 || P.up > 1 && P.ksize > 0) { t_err = "csnet_train_mix_dgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
   tr_mix_dgrad_kernel<<<dim3((P.H * P.W + kT - 1) / kT, P.cin, N), kT, 0, (cudaStream_t)stream>>>(ddst, C, H, W, P, dsrc);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
@@ -417,6 +418,7 @@ int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
 int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dw, void* stream) {
   const csnet::MixPath P = to_path(*path);
   if (P.ksize == 0) { t_err = "csnet_train_mix_wgrad: resample paths have no weights"; return CSNET_E_INVALID; }
+  if (P.pre_avg > 2 || P.up > 1) { t_err = "csnet_train_mix_wgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
   const int kk = P.ksize * P.ksize;
   TR_CHECK(cudaMemsetAsync(dw, 0, (size_t)P.cin * kk * P.cout * sizeof(float), (cudaStream_t)stream));
   const int split = N < 32 ? N : 32;

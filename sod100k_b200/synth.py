@@ -84,3 +84,30 @@ def synth_state(shapes: dict, seed: int = 0) -> dict:
             x100 = (".convs." in key) or (".msconv." in key)   # depthwise / dilated Conv2dX100 weights
             out[key] = (w / 100.0).astype(np.float32) if x100 else w
     return out
+
+
+def synth_state_r(shapes: dict, seed: int = 0) -> dict:
+    """Seeded synthetic parameters for CSF+Res2Net (config 5): the reference ships no weights for it.  Conv weights
+    ~ N(0, 1/fan_in), norm gammas ~ U(0.5, 1.5) (the last BN of every residual branch ~ U(0.1, 0.3) so activations stay
+    O(1) through 16 residual blocks), betas / means ~ N(0, 0.1), variances ~ U(0.5, 1.5), PReLU slopes ~ U(0.1, 0.4)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for key in sorted(shapes):
+        shp = tuple(shapes[key])
+        if key.endswith("num_batches_tracked"):
+            out[key] = np.zeros(shp, np.int64)
+        elif key.endswith("running_var"):
+            out[key] = rng.uniform(0.5, 1.5, shp).astype(np.float32)
+        elif key.endswith("running_mean"):
+            out[key] = (0.1 * rng.standard_normal(shp)).astype(np.float32)
+        elif ".prelu" in key:
+            out[key] = rng.uniform(0.1, 0.4, shp).astype(np.float32)
+        elif len(shp) == 1 and key.endswith(".weight"):
+            lo, hi = (0.1, 0.3) if ".bn3." in key else (0.5, 1.5)
+            out[key] = rng.uniform(lo, hi, shp).astype(np.float32)
+        elif len(shp) == 1:
+            out[key] = (0.1 * rng.standard_normal(shp)).astype(np.float32)
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            out[key] = (rng.standard_normal(shp) / np.sqrt(fan_in)).astype(np.float32)
+    return out

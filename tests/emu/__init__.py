@@ -27,6 +27,23 @@ def lib():
     return _lib
 
 
+def run_ext(prog: ir.Program, ext_arrays, N: int, taps=()):
+    """Generic variant: `ext_arrays[i]` is bound to external i (float32 numpy arrays, outputs are written in place)."""
+    arena = np.zeros(prog.arena_bytes_per_image * N + 256, np.uint8)
+    ext = (C.c_void_p * len(ext_arrays))(*[a.ctypes.data for a in ext_arrays])
+    blob = np.ascontiguousarray(prog.blob, np.float32)
+    rc = lib().csnet_emu_run(prog.tensor_array(), len(prog.tensors), prog.op_array(), len(prog.ops),
+                             blob.ctypes.data_as(C.POINTER(C.c_float)), N, ext, arena.ctypes.data_as(C.c_char_p))
+    if rc != 0:
+        raise RuntimeError(f"emu failed rc={rc}")
+    got = {}
+    for name in taps:
+        t = prog.tensors[prog.taps[name]]
+        off = N * t.arena_offset
+        got[name] = arena[off:off + N * t.bytes_per_image].view(np.float32).reshape(N, t.C, t.H, t.W).copy()
+    return got
+
+
 def run(prog: ir.Program, x: np.ndarray, taps=()):
     """Execute an fp32 program on the host.  Returns (logits, {tap name: array}); compile the program with
     reuse_arena=False when taps are wanted."""

@@ -58,6 +58,27 @@ extern "C" int csnet_emu_run(const csnet_tensor_desc* tensors, int n_tensors, co
         for (int c = 0; c < D.C; ++c)
           for (int oy = 0; oy < D.H; oy += csnet::kDwRows)
             for (int ox = 0; ox < D.W; ++ox) csnet::dw_thread(A, n, c, oy, ox);
+    } else if (op.kind == CSNET_OP_GN) {
+      // GroupNorm + PReLU in plain C++ (the GPU kernels gn_stats_kernel / gn_apply_kernel are checked on the GPU)
+      const float* x = (const float*)ptr(op.paths[0].src);
+      float* y = (float*)ptr(op.dst);
+      const int groups = op.paths[0].up, cpg = D.C / groups, HW = D.H * D.W;
+      const float *ga = blob + op.ext_off[0], *be = blob + op.ext_off[1], *sl = op.slope_off >= 0 ? blob + op.slope_off : nullptr;
+      for (int n = 0; n < N; ++n)
+        for (int g = 0; g < groups; ++g) {
+          const int64_t base = ((int64_t)n * D.C + (int64_t)g * cpg) * HW, cnt = (int64_t)cpg * HW;
+          double s = 0, q = 0;
+          for (int64_t i = 0; i < cnt; ++i) s += x[base + i];
+          const double mu = s / cnt;
+          for (int64_t i = 0; i < cnt; ++i) { const double d = x[base + i] - mu; q += d * d; }
+          const float r = 1.0f / sqrtf((float)(q / cnt) + 1e-5f);
+          for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+            for (int i = 0; i < HW; ++i) {
+              float v = (x[((int64_t)n * D.C + c) * HW + i] - (float)mu) * r * ga[c] + be[c];
+              if (sl) v = v > 0.f ? v : sl[c] * v;
+              y[((int64_t)n * D.C + c) * HW + i] = v;
+            }
+        }
     } else {
       return -1;
     }

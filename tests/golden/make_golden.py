@@ -134,5 +134,39 @@ def main():
     print("wrote", sorted(os.listdir(HERE)))
 
 
+def main_r():
+    """CSF+Res2Net (config 5): reference `networks.csf_res2net.build_model()` with seeded synthetic weights."""
+    for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+        del sys.modules[k]
+    sys.path.insert(0, "/root/reference/CSF+Res2Net")
+    from networks.csf_res2net import build_model as build_r
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = build_r().eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = synth.synth_state_r(shapes, 21)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    out, feats = {}, {}
+    def grab(mod, inp, o):
+        feats["f"] = [t.detach().numpy() for t in o]        # (returns None: a hook's return value would replace the output)
+
+    hooks = [net.base.register_forward_hook(grab)]
+    for tag, hw, seed in (("a", (64, 96), 1301), ("b", (96, 96), 1302)):
+        feats.clear()
+        with torch.no_grad():
+            y = net(torch.from_numpy(synth.randn_images(1, hw[0], hw[1], seed))).numpy()
+        out[f"{tag}/logits"] = y
+        for i, f in enumerate(feats["f"]):
+            out[f"{tag}/feat{i}/stats"] = np.array([f.mean(), f.std(), np.abs(f).max()], np.float32)
+    for h in hooks:
+        h.remove()
+    meta = dict(seed=21, shapes={k: list(v) for k, v in shapes.items()}, params=int(sum(p.numel() for p in net.parameters())),
+                cases=dict(a=[64, 96, 1301], b=[96, 96, 1302]))
+    np.savez_compressed(os.path.join(HERE, "csf_res2net.npz"), __meta__=np.array(json.dumps(meta)), **out)
+    print("wrote csf_res2net.npz", {k: v.tolist() for k, v in out.items() if k.endswith("stats")})
+
+
 if __name__ == "__main__":
-    main()
+    if "--r-only" not in sys.argv:
+        main()
+    main_r()
