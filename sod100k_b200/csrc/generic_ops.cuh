@@ -122,82 +122,68 @@ CSNET_DEV float bilinear_up(const void* src, int dtype, int64_t plane, int Hs, i
   return hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
 }
 
-// Number of floats the weight stage of one (op, cout tile) needs.
-CSNET_DEV int mix_stage_floats(const MixArgs& A, int co_base) {
-  int n = 0;
-  for (int p = 0; p < A.n_paths; ++p) {
-    const MixPath& P = A.p[p];
-    if (P.ksize == 0) continue;
-    const int lo = co_base > P.cout0 ? co_base : P.cout0;
-    const int hi = (co_base + kMixCT) < (P.cout0 + P.cout) ? (co_base + kMixCT) : (P.cout0 + P.cout);
-    if (lo >= hi) continue;
-    n += P.cin * P.ksize * P.ksize * kMixCT;
-  }
-  return n;
+// The generic MIX kernel walks K in chunks: for every conv path that touches this cout tile, for every chunk of
+// input channels, the CTA stages that chunk's weights in shared memory ([ci][tap][kMixCT], zero where the output channel
+// is outside the path's slice, so the accumulate loop needs no predicates) and every thread accumulates its pixel.
+constexpr int kMixStageFloats = 8192;                       // 32 KB of staged weights per chunk
+
+CSNET_HD int mix_chunk_channels(int ksize) {
+  const int c = kMixStageFloats / (ksize * ksize * kMixCT);
+  return c < 1 ? 1 : c;
 }
 
-// Cooperative: copy this tile's weights into `ws` as [path][ci][tap][kMixCT], zero where the output
-// channel is outside the path's slice (so the accumulate loop needs no predicates).
-CSNET_DEV void mix_stage_weights(const MixArgs& A, int co_base, float* ws, int tid, int nthreads) {
-  int off = 0;
-  for (int p = 0; p < A.n_paths; ++p) {
-    const MixPath& P = A.p[p];
-    if (P.ksize == 0) continue;
-    const int lo = co_base > P.cout0 ? co_base : P.cout0;
-    const int hi = (co_base + kMixCT) < (P.cout0 + P.cout) ? (co_base + kMixCT) : (P.cout0 + P.cout);
-    if (lo >= hi) continue;
-    const int rows = P.cin * P.ksize * P.ksize;
-    for (int i = tid; i < rows * kMixCT; i += nthreads) {
-      const int r = i / kMixCT, t = i % kMixCT;
-      const int co = co_base + t;
-      ws[off + i] = (co >= lo && co < hi) ? P.w[(int64_t)r * P.cout + (co - P.cout0)] : 0.f;
-    }
-    off += rows * kMixCT;
+CSNET_DEV bool mix_path_live(const MixPath& P, int co_base) {
+  const int lo = co_base > P.cout0 ? co_base : P.cout0;
+  const int hi = (co_base + kMixCT) < (P.cout0 + P.cout) ? (co_base + kMixCT) : (P.cout0 + P.cout);
+  return lo < hi;
+}
+
+// Cooperative: weights of input channels [ci0, ci1) of path P for this cout tile -> ws[(ci-ci0)][tap][kMixCT].
+CSNET_DEV void mix_stage_chunk(const MixPath& P, int co_base, int ci0, int ci1, float* ws, int tid, int nthreads) {
+  const int kk = P.ksize * P.ksize, rows = (ci1 - ci0) * kk;
+  for (int i = tid; i < rows * kMixCT; i += nthreads) {
+    const int r = i / kMixCT, t = i % kMixCT;
+    const int co = co_base + t;
+    ws[i] = (co >= P.cout0 && co < P.cout0 + P.cout) ? P.w[((int64_t)ci0 * kk + r) * P.cout + (co - P.cout0)] : 0.f;
   }
 }
 
-// One output pixel (n, oy, ox), output channels [co_base, co_base + kMixCT).
-CSNET_DEV void mix_thread(const MixArgs& A, const float* ws, int n, int oy, int ox, int co_base) {
-  float acc[kMixCT];
+// One output pixel: accumulate input channels [ci0, ci1) of conv path P.
+CSNET_DEV void mix_acc_chunk(const MixPath& P, const float* ws, int ci0, int ci1, int n, int oy, int ox, float* acc) {
+  const int64_t plane_sz = (int64_t)P.H * P.W;
+  const int div = pre_factor(P.pre_avg) * P.pool;
+  const int Hc = P.up > 1 ? P.H * P.up : P.H / div, Wc = P.up > 1 ? P.W * P.up : P.W / div;
+  const int kk = P.ksize * P.ksize;
+  for (int ci = ci0; ci < ci1; ++ci) {
+    const int64_t plane = ((int64_t)n * P.C + P.c0 + ci) * plane_sz;
+    for (int ky = 0; ky < P.ksize; ++ky) {
+      const int y = oy * P.stride - P.pad + ky * P.dil;
+      for (int kx = 0; kx < P.ksize; ++kx) {
+        const int x = ox * P.stride - P.pad + kx * P.dil;
+        const float* wr = ws + ((ci - ci0) * kk + ky * P.ksize + kx) * kMixCT;
+        if (y < 0 || y >= Hc || x < 0 || x >= Wc) continue;   // zero padding
+        // up > 1 on a (1x1) conv path: the source is bilinearly up-sampled BEFORE the conv (same linear map as
+        // the reference's conv-then-interpolate, csnet.py:702-707)
+        const float v = P.up > 1 ? bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, y, x) : fetch_pooled(P, plane, y, x);
 #pragma unroll
-  for (int t = 0; t < kMixCT; ++t) acc[t] = 0.f;
-  int off = 0;
-  for (int p = 0; p < A.n_paths; ++p) {
-    const MixPath& P = A.p[p];
-    const int lo = co_base > P.cout0 ? co_base : P.cout0;
-    const int hi = (co_base + kMixCT) < (P.cout0 + P.cout) ? (co_base + kMixCT) : (P.cout0 + P.cout);
-    if (lo >= hi) continue;
-    const int64_t plane_sz = (int64_t)P.H * P.W;
-    if (P.ksize > 0) {
-      const int div = pre_factor(P.pre_avg) * P.pool;
-      const int Hc = P.up > 1 ? P.H * P.up : P.H / div, Wc = P.up > 1 ? P.W * P.up : P.W / div;
-      const int kk = P.ksize * P.ksize;
-      for (int ci = 0; ci < P.cin; ++ci) {
-        const int64_t plane = ((int64_t)n * P.C + P.c0 + ci) * plane_sz;
-        for (int ky = 0; ky < P.ksize; ++ky) {
-          const int y = oy * P.stride - P.pad + ky * P.dil;
-          for (int kx = 0; kx < P.ksize; ++kx) {
-            const int x = ox * P.stride - P.pad + kx * P.dil;
-            const float* wr = ws + off + (ci * kk + ky * P.ksize + kx) * kMixCT;
-            if (y < 0 || y >= Hc || x < 0 || x >= Wc) continue;   // zero padding
-            // up > 1 on a (1x1) conv path: the source is bilinearly up-sampled BEFORE the conv (same linear map as
-            // the reference's conv-then-interpolate, csnet.py:702-707)
-            const float v = P.up > 1 ? bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, y, x) : fetch_pooled(P, plane, y, x);
-#pragma unroll
-            for (int t = 0; t < kMixCT; ++t) acc[t] += v * wr[t];
-          }
-        }
+        for (int t = 0; t < kMixCT; ++t) acc[t] += v * wr[t];
       }
-      off += P.cin * kk * kMixCT;
-    } else {
-      const int Hs = P.H, Ws = P.W;
+    }
+  }
+}
+
+// One output pixel: resample-add paths, bias, PReLU, store.
+CSNET_DEV void mix_finish(const MixArgs& A, int n, int oy, int ox, int co_base, float* acc) {
+  for (int p = 0; p < A.n_paths; ++p) {
+    const MixPath& P = A.p[p];
+    if (P.ksize != 0 || !mix_path_live(P, co_base)) continue;
+    const int64_t plane_sz = (int64_t)P.H * P.W;
 #pragma unroll
-      for (int t = 0; t < kMixCT; ++t) {
-        const int co = co_base + t;
-        if (co >= lo && co < hi) {
-          const int64_t plane = ((int64_t)n * P.C + P.c0 + (co - P.cout0)) * plane_sz;
-          acc[t] += bilinear_up(P.src, P.dtype, plane, Hs, Ws, P.up, oy, ox);
-        }
+    for (int t = 0; t < kMixCT; ++t) {
+      const int co = co_base + t;
+      if (co >= P.cout0 && co < P.cout0 + P.cout) {
+        const int64_t plane = ((int64_t)n * P.C + P.c0 + (co - P.cout0)) * plane_sz;
+        acc[t] += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
       }
     }
   }

@@ -42,13 +42,27 @@ size_t dtype_size(int dt) { return dt == CSNET_F32 ? 4 : 2; }
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads, 2) mix_generic_kernel(const __grid_constant__ csnet::MixArgs A) {
-  extern __shared__ float ws[];
-  const int co_base = blockIdx.y * csnet::kMixCT;
-  csnet::mix_stage_weights(A, co_base, ws, threadIdx.x, kThreads);
-  __syncthreads();
+  __shared__ float ws[csnet::kMixStageFloats];
+  const int co_base = blockIdx.y * csnet::kMixCT, n = blockIdx.z;
   const int pix = blockIdx.x * kThreads + threadIdx.x;
-  if (pix >= A.H * A.W) return;
-  csnet::mix_thread(A, ws, blockIdx.z, pix / A.W, pix % A.W, co_base);
+  const bool live = pix < A.H * A.W;
+  const int oy = live ? pix / A.W : 0, ox = live ? pix % A.W : 0;
+  float acc[csnet::kMixCT];
+#pragma unroll
+  for (int t = 0; t < csnet::kMixCT; ++t) acc[t] = 0.f;
+  for (int p = 0; p < A.n_paths; ++p) {
+    const csnet::MixPath& P = A.p[p];
+    if (P.ksize == 0 || !csnet::mix_path_live(P, co_base)) continue;      // block-uniform
+    const int chunk = csnet::mix_chunk_channels(P.ksize);
+    for (int ci0 = 0; ci0 < P.cin; ci0 += chunk) {
+      const int ci1 = ci0 + chunk < P.cin ? ci0 + chunk : P.cin;
+      __syncthreads();
+      csnet::mix_stage_chunk(P, co_base, ci0, ci1, ws, threadIdx.x, kThreads);
+      __syncthreads();
+      if (live) csnet::mix_acc_chunk(P, ws, ci0, ci1, n, oy, ox, acc);
+    }
+  }
+  if (live) csnet::mix_finish(A, n, oy, ox, co_base, acc);
 }
 
 __global__ void __launch_bounds__(kThreads) dw_generic_kernel(const __grid_constant__ csnet::DwArgs A) {
@@ -133,7 +147,6 @@ struct csnet_plan {
   char* arena = nullptr;
   int64_t arena_per_image = 0;   // bytes
   int n_ext = 0;
-  size_t mix_smem_max = 0;
   size_t il_smem_max = 0;
   std::vector<size_t> op_smem;
   std::vector<TcChoice> op_tc;
@@ -380,23 +393,6 @@ cudaError_t set_il_smem_t(int bytes) {
   return e;
 }
 
-size_t mix_smem_bytes(const csnet::MixArgs& A) {
-  size_t mx = 0;
-  for (int co = 0; co < A.C; co += csnet::kMixCT) {
-    size_t f = 0;
-    for (int p = 0; p < A.n_paths; ++p) {
-      const csnet::MixPath& q = A.p[p];
-      if (q.ksize == 0) continue;
-      const int lo = co > q.cout0 ? co : q.cout0;
-      const int hi = (co + csnet::kMixCT) < (q.cout0 + q.cout) ? (co + csnet::kMixCT) : (q.cout0 + q.cout);
-      if (lo >= hi) continue;
-      f += (size_t)q.cin * q.ksize * q.ksize * csnet::kMixCT;
-    }
-    mx = f > mx ? f : mx;
-  }
-  return mx * sizeof(float);
-}
-
 // Can this MIX op run on the tensor-core kernel (mix_tc.cuh)?  Needs 16-bit operands somewhere, stride-1 conv
 // paths and at most 80 output channels; ext_off[23] == 1 is the compiler's veto (weights overflow 16 bits).
 TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
@@ -520,16 +516,13 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
       continue;
     }
     P->op_tc[i] = TcChoice();
-    csnet::MixArgs A = make_mix(*P, P->ops[i], 1, nullptr);
-    P->op_smem[i] = mix_smem_bytes(A);
-    P->mix_smem_max = P->op_smem[i] > P->mix_smem_max ? P->op_smem[i] : P->mix_smem_max;
+    P->op_smem[i] = 0;                                   // the generic kernel stages weights in static shared memory
   }
   if (tc_smem_max > 48 * 1024) {
     e = set_tc_smem_t<__half>((int)tc_smem_max);
     if (e == cudaSuccess) e = set_tc_smem_t<__nv_bfloat16>((int)tc_smem_max);
     if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(mix_tc): ") + cudaGetErrorString(e));
   }
-  if (P->mix_smem_max > 227 * 1024) return cleanup(CSNET_E_UNSUPPORTED, "MIX op weights exceed shared memory");
   for (size_t i = 0; i < P->ops.size(); ++i) {
     if (P->ops[i].kind != CSNET_OP_ILBLOCK) continue;
     csnet::IlArgs A;
@@ -541,10 +534,6 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     e = set_il_smem_t<__half>((int)P->il_smem_max);
     if (e == cudaSuccess) e = set_il_smem_t<__nv_bfloat16>((int)P->il_smem_max);
     if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(il_block): ") + cudaGetErrorString(e));
-  }
-  if (P->mix_smem_max > 48 * 1024) {
-    e = cudaFuncSetAttribute(mix_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->mix_smem_max);
-    if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   }
   *out = P;
   return CSNET_OK;
@@ -579,7 +568,7 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
   } else if (op.kind == CSNET_OP_MIX) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     dim3 grid((D.H * D.W + kThreads - 1) / kThreads, (D.C + csnet::kMixCT - 1) / csnet::kMixCT, N);
-    mix_generic_kernel<<<grid, kThreads, P->op_smem[i], stream>>>(A);
+    mix_generic_kernel<<<grid, kThreads, 0, stream>>>(A);
   } else if (op.kind == CSNET_OP_GN) {
     const csnet_tensor_desc& S = P->tensors[op.paths[0].src];
     csnet::GnArgs A{};

@@ -172,13 +172,27 @@ __global__ void __launch_bounds__(kT) dw_wgrad_kernel(const float* __restrict__ 
 
 // ---- MIX forward (raw: no bias / slope) -----------------------------------------------------------------------
 __global__ void __launch_bounds__(kT, 2) tr_mix_fwd_kernel(const __grid_constant__ csnet::MixArgs A) {
-  extern __shared__ float ws[];
-  const int co_base = blockIdx.y * csnet::kMixCT;
-  csnet::mix_stage_weights(A, co_base, ws, threadIdx.x, kT);
-  __syncthreads();
+  __shared__ float ws[csnet::kMixStageFloats];
+  const int co_base = blockIdx.y * csnet::kMixCT, n = blockIdx.z;
   const int pix = blockIdx.x * kT + threadIdx.x;
-  if (pix >= A.H * A.W) return;
-  csnet::mix_thread(A, ws, blockIdx.z, pix / A.W, pix % A.W, co_base);
+  const bool live = pix < A.H * A.W;
+  const int oy = live ? pix / A.W : 0, ox = live ? pix % A.W : 0;
+  float acc[csnet::kMixCT];
+#pragma unroll
+  for (int t = 0; t < csnet::kMixCT; ++t) acc[t] = 0.f;
+  for (int p = 0; p < A.n_paths; ++p) {
+    const csnet::MixPath& P = A.p[p];
+    if (P.ksize == 0 || !csnet::mix_path_live(P, co_base)) continue;      // block-uniform
+    const int chunk = csnet::mix_chunk_channels(P.ksize);
+    for (int ci0 = 0; ci0 < P.cin; ci0 += chunk) {
+      const int ci1 = ci0 + chunk < P.cin ? ci0 + chunk : P.cin;
+      __syncthreads();
+      csnet::mix_stage_chunk(P, co_base, ci0, ci1, ws, threadIdx.x, kT);
+      __syncthreads();
+      if (live) csnet::mix_acc_chunk(P, ws, ci0, ci1, n, oy, ox, acc);
+    }
+  }
+  if (live) csnet::mix_finish(A, n, oy, ox, co_base, acc);
 }
 
 // ---- MIX backward: data gradient of ONE path, gather over source elements -------------------------------------
@@ -386,23 +400,8 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
   if (n_paths < 1 || n_paths > CSNET_MAX_PATHS) { t_err = "csnet_train_mix_fwd: n_paths"; return CSNET_E_INVALID; }
   csnet::MixArgs A{};
   A.dst = dst; A.bias = nullptr; A.slope = nullptr; A.dtype = CSNET_F32; A.C = C; A.H = H; A.W = W; A.n_paths = n_paths;
-  size_t smem = 0;
   for (int p = 0; p < n_paths; ++p) A.p[p] = to_path(paths[p]);
-  for (int co = 0; co < C; co += csnet::kMixCT) {
-    size_t f = 0;
-    for (int p = 0; p < n_paths; ++p) {
-      const csnet::MixPath& q = A.p[p];
-      if (q.ksize == 0) continue;
-      const int lo = co > q.cout0 ? co : q.cout0;
-      const int hi = (co + csnet::kMixCT) < (q.cout0 + q.cout) ? (co + csnet::kMixCT) : (q.cout0 + q.cout);
-      if (lo < hi) f += (size_t)q.cin * q.ksize * q.ksize * csnet::kMixCT;
-    }
-    smem = f > smem ? f : smem;
-  }
-  smem *= sizeof(float);
-  if (smem > 200 * 1024) { t_err = "csnet_train_mix_fwd: weights exceed shared memory"; return CSNET_E_UNSUPPORTED; }
-  if (smem > 48 * 1024) TR_CHECK(cudaFuncSetAttribute(tr_mix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tr_mix_fwd_kernel<<<dim3((H * W + kT - 1) / kT, (C + csnet::kMixCT - 1) / csnet::kMixCT, N), kT, smem, (cudaStream_t)stream>>>(A);
+  tr_mix_fwd_kernel<<<dim3((H * W + kT - 1) / kT, (C + csnet::kMixCT - 1) / csnet::kMixCT, N), kT, 0, (cudaStream_t)stream>>>(A);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }

@@ -38,13 +38,28 @@ extern "C" int csnet_emu_run(const csnet_tensor_desc* tensors, int n_tensors, co
         m.pre_avg = q.pre_avg; m.pool = q.pool; m.ksize = q.ksize; m.dil = q.dil; m.stride = q.stride;
         m.pad = q.pad; m.up = q.up; m.cout0 = q.cout0; m.cout = q.cout;
       }
+      const int64_t npix = (int64_t)N * D.H * D.W;
       for (int co = 0; co < D.C; co += csnet::kMixCT) {
-        std::vector<float> ws(csnet::mix_stage_floats(A, co) + 1);
-        csnet::mix_stage_weights(A, co, ws.data(), 0, 1);
-#pragma omp parallel for collapse(2) schedule(static)
-        for (int n = 0; n < N; ++n)
-          for (int oy = 0; oy < D.H; ++oy)
-            for (int ox = 0; ox < D.W; ++ox) csnet::mix_thread(A, ws.data(), n, oy, ox, co);
+        std::vector<float> acc((size_t)npix * csnet::kMixCT, 0.f), ws(csnet::kMixStageFloats);
+        for (int p = 0; p < A.n_paths; ++p) {
+          const csnet::MixPath& P = A.p[p];
+          if (P.ksize == 0 || !csnet::mix_path_live(P, co)) continue;
+          const int chunk = csnet::mix_chunk_channels(P.ksize);
+          for (int ci0 = 0; ci0 < P.cin; ci0 += chunk) {
+            const int ci1 = ci0 + chunk < P.cin ? ci0 + chunk : P.cin;
+            csnet::mix_stage_chunk(P, co, ci0, ci1, ws.data(), 0, 1);
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < npix; ++i) {
+              const int n = (int)(i / (D.H * D.W)), r = (int)(i % (D.H * D.W));
+              csnet::mix_acc_chunk(P, ws.data(), ci0, ci1, n, r / D.W, r % D.W, &acc[(size_t)i * csnet::kMixCT]);
+            }
+          }
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < npix; ++i) {
+          const int n = (int)(i / (D.H * D.W)), r = (int)(i % (D.H * D.W));
+          csnet::mix_finish(A, n, r / D.W, r % D.W, co, &acc[(size_t)i * csnet::kMixCT]);
+        }
       }
     } else if (op.kind == CSNET_OP_DW) {
       const csnet_path_desc& q = op.paths[0];

@@ -172,13 +172,6 @@ def test_large_batch_full_size_properties():
     assert torch.isfinite(y).all()
 
 
-def test_train_mode_is_loud_until_built():
-    m, _, _ = _model("csnet-L-x1")
-    m.train()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 3, 32, 32).cuda())
-
-
 @pytest.mark.parametrize("tag,hw,dtype", [("csnet-L-x2", (224, 224), "fp16"), ("csnet-L-x2", (96, 160), "fp16"),
                                           ("csnet-L-x1", (128, 64), "fp16"), ("csnet-L-x2", (64, 96), "bf16"),
                                           ("init-x2", (96, 96), "fp16")])
