@@ -52,6 +52,7 @@ struct IlArgs {
   int32_t TH, TW, tiles_x;     // tile (one of the instantiated geometries) and tiles per image row
   int32_t K8, MH16, ML16;
   int32_t rowsAh, rowsAl;
+  int32_t t2h;                 // channels of the hi T2 buffer: Cho (whole layer resident) or 8 (channel-chunked dw tail)
   int32_t tma_h, tma_l;        // 1: that input is loaded with TMA
 };
 
@@ -262,7 +263,7 @@ __device__ __forceinline__ void dw_pass(const uint16_t* inH, uint16_t* outH, con
 }
 
 inline size_t il_smem_bytes(const IlArgs& A, int NPH, int NPL) {
-  size_t halves = (size_t)A.rowsAh * NPH + (size_t)A.Cho * NPH + (size_t)A.rowsAl * NPL + (size_t)A.Clo * NPL +
+  size_t halves = (size_t)A.rowsAh * NPH + (size_t)A.t2h * NPH + (size_t)A.rowsAl * NPL + (size_t)A.Clo * NPL +
                   (size_t)A.MH16 * A.K8 + (size_t)A.ML16 * A.K8;
   return halves * 2 + 128 /*base alignment*/ + 128 /*mbarrier + front guard*/ + 128 /*bufAh size round-up*/ + 128 /*tail guard*/;
 }
@@ -288,7 +289,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   off = (off + 127) & ~(size_t)127;
   uint16_t* bufAl = bufAh + off / 2;                                // [x_l | pool(x_h)] -> T1L (in place)
   uint16_t* bufBh = bufAl + (size_t)A.rowsAl * NPL;                 // T2H
-  uint16_t* bufBl = bufBh + (size_t)Cho * NPH;                      // T2L
+  uint16_t* bufBl = bufBh + (size_t)A.t2h * NPH;                    // T2L
   uint16_t* wsH = bufBl + (size_t)Clo * NPL;
   uint16_t* wsL = wsH + A.MH16 * A.K8;
   uint16_t* tail = wsL + A.ML16 * A.K8;
@@ -463,16 +464,33 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   }
   __syncthreads();
 
-  // ---- phase 3: dw1 (T1 -> T2, smem) ------------------------------------------------------------------
+  // ---- phase 3/4: the two depthwise layers ---------------------------------------------------------------
   constexpr int rh = TH + 8, rl = TH / 2 + 4;         // region rows that matter (without the padding row)
-  dw_pass<T, false, 6, DwGeom<RWh, NPH, 3, rh - 3, 0, RWh / 4>, DwGeom<RWl, NPL, 1, rl - 1, 0, RWl / 4>>(
-      bufAh, bufBh, A.dw1h, Cho, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l, Clo, ly0 - 2, lx0 - 4, tid);
-  __syncthreads();
-
-  // ---- phase 4: dw2 (T2 -> global) --------------------------------------------------------------------
-  dw_pass<T, true, 4, DwGeom<RWh, NPH, 4, rh - 4, 1, RWh / 4 - 1>, DwGeom<RWl, NPL, 2, rl - 2, 1, RWl / 4 - 1>>(
-      bufBh, reinterpret_cast<uint16_t*>(A.yh) + (size_t)n * Cho * H * W, A.dw2h, Cho, hy0 - 4, hx0 - 4, H, W, bufBl,
-      Clo > 0 ? reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * Clo * Hl * Wl : nullptr, A.dw2l, Clo, ly0 - 2, lx0 - 4, tid);
+  using GH1 = DwGeom<RWh, NPH, 3, rh - 3, 0, RWh / 4>;
+  using GL1 = DwGeom<RWl, NPL, 1, rl - 1, 0, RWl / 4>;
+  using GH2 = DwGeom<RWh, NPH, 4, rh - 4, 1, RWh / 4 - 1>;
+  using GL2 = DwGeom<RWl, NPL, 2, rl - 2, 1, RWl / 4 - 1>;
+  uint16_t* outH = reinterpret_cast<uint16_t*>(A.yh) + (size_t)n * Cho * H * W;
+  uint16_t* outL = Clo > 0 ? reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * Clo * Hl * Wl : nullptr;
+  if (A.t2h >= Cho) {
+    // whole layers resident: dw1 (T1 -> T2, smem) then dw2 (T2 -> global)
+    dw_pass<T, false, 6, GH1, GL1>(bufAh, bufBh, A.dw1h, Cho, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l, Clo, ly0 - 2, lx0 - 4, tid);
+    __syncthreads();
+    dw_pass<T, true, 4, GH2, GL2>(bufBh, outH, A.dw2h, Cho, hy0 - 4, hx0 - 4, H, W, bufBl, outL, A.dw2l, Clo, ly0 - 2, lx0 - 4, tid);
+  } else {
+    // wide blocks: the hi branch goes through the two layers 8 channels at a time (T2 buffer of 8 planes), the lo
+    // branch rides along with the first chunk
+    for (int c0 = 0; c0 < Cho; c0 += A.t2h) {
+      const int cc = (Cho - c0) < A.t2h ? (Cho - c0) : A.t2h;
+      const DwParams p1{A.dw1h.w + c0 * 9, A.dw1h.b + c0, A.dw1h.s + c0}, p2{A.dw2h.w + c0 * 9, A.dw2h.b + c0, A.dw2h.s + c0};
+      if (c0 > 0) __syncthreads();                      // the previous chunk's dw2 finished reading the T2 buffer
+      dw_pass<T, false, 3, GH1, GL1>(bufAh + (size_t)c0 * NPH, bufBh, p1, cc, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l,
+                                     c0 == 0 ? Clo : 0, ly0 - 2, lx0 - 4, tid);
+      __syncthreads();
+      dw_pass<T, true, 2, GH2, GL2>(bufBh, outH + (size_t)c0 * H * W, p2, cc, hy0 - 4, hx0 - 4, H, W, bufBl, outL, A.dw2l,
+                                    c0 == 0 ? Clo : 0, ly0 - 2, lx0 - 4, tid);
+    }
+  }
 }
 
 }  // namespace csnet

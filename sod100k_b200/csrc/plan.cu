@@ -360,14 +360,18 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   A.tma_l = use_tma && ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
   static const int cand[][2] = {{32, 32}, {16, 64}, {16, 32}, {8, 16}};   // the instantiated tile geometries
   double best = -1;
-  for (auto& c : cand) {
-    csnet::IlArgs T = A;
-    T.TH = c[0]; T.TW = c[1];
-    const int NPH = ((T.TH + 8) | 1) * (T.TW + 8), NPL = ((T.TH / 2 + 4) | 1) * (T.TW / 2 + 8);
-    if (csnet::il_smem_bytes(T, NPH, NPL) > 227 * 1024) continue;
-    const int ty = (A.H + T.TH - 1) / T.TH, tx = (A.W + T.TW - 1) / T.TW;
-    const double cost = (double)ty * tx * NPH;
-    if (best < 0 || cost < best) { best = cost; T.tiles_x = tx; *out = T; }
+  for (int chunked = 0; chunked < 2; ++chunked) {
+    for (auto& c : cand) {
+      csnet::IlArgs T = A;
+      T.TH = c[0]; T.TW = c[1];
+      T.t2h = chunked ? 8 : A.Cho;                       // chunked: the depthwise tail runs 8 hi channels at a time
+      if (chunked && A.Cho <= 8) continue;
+      const int NPH = ((T.TH + 8) | 1) * (T.TW + 8), NPL = ((T.TH / 2 + 4) | 1) * (T.TW / 2 + 8);
+      if (csnet::il_smem_bytes(T, NPH, NPL) > 227 * 1024) continue;
+      const int ty = (A.H + T.TH - 1) / T.TH, tx = (A.W + T.TW - 1) / T.TW;
+      const double cost = (double)ty * tx * NPH * (chunked ? 1.15 : 1.0);   // halo work, small penalty for the extra barriers
+      if (best < 0 || cost < best) { best = cost; T.tiles_x = tx; *out = T; }
+    }
   }
   return best >= 0;
 }
