@@ -112,3 +112,20 @@ def test_layer_config_pickle_roundtrip(tmp_path):
     back = csnet.load_layer_config(str(tmp_path / "layer_config_latest.bin"))
     m = csnet.build_model(predefine=str(tmp_path / "layer_config_3.bin"))
     assert back[-1] == cfg[-1] and len(m.state_dict()) > 700
+
+
+def test_simplesum_reproduces_the_reference_counters():
+    """the reference's own counter gives 0.0936 M / 0.4354 G (x1) and 0.1409 M / 0.7167 G (x2)."""
+    import contextlib
+    import io
+
+    from sod100k_b200 import checkpoints
+    from sod100k_b200.model.utils.simplesum_octconv import simplesum
+
+    for tag, params, gflops in (("csnet-L-x1", 93647, 0.4354), ("csnet-L-x2", 140894, 0.7167)):
+        m, _, _ = checkpoints.build_from_npz(tag)
+        with contextlib.redirect_stdout(io.StringIO()) as out:
+            p, f = simplesum(m, inputsize=(3, 224, 224), device=-1)
+        assert p == params and abs(f / 1e9 - gflops) < 5e-5
+        assert "Number of params" in out.getvalue() and "Number of FLOPs" in out.getvalue()
+        assert not any(x._forward_hooks for x in m.modules())
