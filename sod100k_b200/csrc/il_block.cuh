@@ -133,6 +133,9 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid
   const int sz = valid ? 8 : 0;       // src-size 0: the 8 destination bytes are zero-filled
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // D[M16 x NP] = Ws[M16 x K8] . X[K8 x NP], result handed to epi() pair-wise; X may be overwritten by epi() for the

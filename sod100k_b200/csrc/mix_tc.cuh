@@ -28,6 +28,10 @@ struct TcGeom {
   int32_t tiles_x;
   int32_t xs_halves;      // allocated halves per staged channel plane (max over groups)
   int32_t kc;             // input channels per staged chunk (8, 16 or 32)
+  int32_t m16_total;      // output channels rounded up to the CTA slice (MT*16) multiple
+  // 16-bit weights of every conv path, packed at csnet_plan_set_blob time as [chunk][tap][m16_total][kc + 8]
+  // (zero outside the path's cout slice / beyond cin): a CTA's slice of one (chunk, tap) is contiguous.
+  const uint16_t* w16[kMaxPaths];
 };
 
 // Staged window of a conv group with halo `pad`: rows [oy0-pad, oy0+8+pad); columns start at ox0-padL with the left
@@ -49,6 +53,35 @@ constexpr int kTcMaxPad = 16;                                          // 3x3 wi
 __device__ __forceinline__ float tc_fetch(const MixPath& P, int64_t plane, int cy, int cx) {
   if (P.up > 1) return bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, cy, cx);
   return fetch_pooled(P, plane, cy, cx);
+}
+
+// F.interpolate(bilinear, align_corners=False) by an integer factor from a 16-bit plane: same arithmetic as bilinear_up()
+// without the per-load dtype dispatch.
+template <typename T>
+__device__ __forceinline__ float bilinear_up16(const uint16_t* plane, int Hs, int Ws, int up, int oy, int ox) {
+  const float inv = 1.0f / (float)up;
+  float sy = ((float)oy + 0.5f) * inv - 0.5f, sx = ((float)ox + 0.5f) * inv - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const uint16_t *r0 = plane + (size_t)y0 * Ws, *r1 = plane + (size_t)y1 * Ws;
+  return hy * (hx * Pack<T>::to_f(r0[x0]) + lx * Pack<T>::to_f(r0[x1])) + ly * (hx * Pack<T>::to_f(r1[x0]) + lx * Pack<T>::to_f(r1[x1]));
+}
+
+// x2 up-sample of an fp32 plane for the output pixel pair (ox even, ox+1): fixed taps (1/4, 3/4), clamped indices —
+// the same values bilinear_up() produces for up == 2.
+__device__ __forceinline__ void bilinear_up2_pair_f32(const float* plane, int Hs, int Ws, int oy, int ox, float& v0, float& v1) {
+  const int i = oy >> 1, j = ox >> 1;
+  const int ya = (oy & 1) ? i : (i > 0 ? i - 1 : 0), yb = (oy & 1) ? (i + 1 < Hs ? i + 1 : Hs - 1) : i;
+  const float wa = (oy & 1) ? 0.75f : 0.25f, wb = 1.f - wa;
+  const int jm = j > 0 ? j - 1 : 0, jp = j + 1 < Ws ? j + 1 : Ws - 1;
+  const float *ra = plane + (size_t)ya * Ws, *rb = plane + (size_t)yb * Ws;
+  const float am = ra[jm], a0 = ra[j], ap = ra[jp], bm = rb[jm], b0 = rb[j], bp = rb[jp];
+  // even column 2j: (1/4) src[j-1] + (3/4) src[j];  odd column 2j+1: (3/4) src[j] + (1/4) src[j+1]
+  v0 += wa * (0.25f * am + 0.75f * a0) + wb * (0.25f * bm + 0.75f * b0);
+  v1 += wa * (0.75f * a0 + 0.25f * ap) + wb * (0.75f * b0 + 0.25f * bp);
 }
 
 // Same as fetch_pooled() for a 16-bit source of type T with an even row length: pixel pairs come in as one
@@ -122,6 +155,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
     const bool vec = plain && (srcW & 3) == 0;
     // typed 32-bit pair loads need 4-byte alignment: true for f = 2 (offset 0); f = 4 / 8 start at odd pixels
     const bool pooled16 = P0.dtype != DT_F32 && P0.up == 1 && (P0.pre_avg || P0.pool > 1) && (srcW & 1) == 0 && pre_factor(P0.pre_avg) <= 2;
+    const bool up16 = P0.dtype != DT_F32 && P0.up > 1;
     const int XH = kTcTH + 2 * pad, padL = tc_pad_left(pad), PS = tc_plane_halves(pad);
     const int XW = vec ? tc_xw_vec(pad) : tc_xw_exact(pad);
     const int64_t src_base = ((int64_t)n * P0.C + P0.c0) * plane_sz;
@@ -162,7 +196,8 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
                 v[q] = 0.f;
                 if (col_ok && y0 + q < XH && cy >= 0 && cy < Hc)
                   v[q] = pooled16 ? fetch_pooled16<T>(P0, reinterpret_cast<const uint16_t*>(P0.src) + plane, cy, cx)
-                                  : tc_fetch(P0, plane, cy, cx);
+                         : up16 ? bilinear_up16<T>(reinterpret_cast<const uint16_t*>(P0.src) + plane, P0.H, P0.W, P0.up, cy, cx)
+                                : tc_fetch(P0, plane, cy, cx);
               }
 #pragma unroll
               for (int q = 0; q < 4; ++q)
@@ -173,21 +208,17 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
       }
       for (int p = p0; p < p1; ++p) {
         const MixPath& P = A.p[p];
-        const int ksz = P.ksize, kk = ksz * ksz, dil = P.dil, pcout0 = P.cout0, pcout = P.cout;
-        const float* pw = P.w;
+        const int ksz = P.ksize, kk = ksz * ksz, dil = P.dil;
         if (p > p0) __syncthreads();                       // Ws of the previous path is no longer read
-        // ---- stage this path's weights for the chunk: Ws[tap][m][k]; thread = (k = lane, m = warp, warp+8, ...) ----
-        if (lane < kc8) {
-          const bool k_ok = lane < kc_live;
-          for (int tap = 0; tap < kk; ++tap) {
-            const float* wsrc = pw + ((int64_t)(c0 + lane) * kk + tap) * pcout - pcout0 + m_base;
-#pragma unroll
-            for (int m = warp; m < M16; m += kTcWarps) {
-              const int mg = m_base + m;
-              const float w = (k_ok && mg >= pcout0 && mg < pcout0 + pcout) ? __ldg(wsrc + m) : 0.f;
-              Ws[(tap * M16 + m) * WR + lane] = (uint16_t)(Pack<T>::from_f2(w, 0.f) & 0xffffu);
-            }
+        // ---- stage this path's weights for the chunk: 16-byte cp.async copies of the pre-packed [tap][m][kc+8] slices ----
+        {
+          const int vec_row = WR >> 3, per_tap = M16 * vec_row;          // 16-byte vectors per weight row / per tap
+          const uint16_t* wsrc = G.w16[p] + ((size_t)(c0 / KC) * kk * G.m16_total + m_base) * WR;
+          for (int i = tid; i < kk * per_tap; i += kTcThreads) {
+            const int tap = i / per_tap, r = i - tap * per_tap;
+            cp_async16(Ws + (size_t)tap * M16 * WR + r * 8, wsrc + (size_t)tap * G.m16_total * WR + r * 8);
           }
+          cp_async_wait_all();
         }
         __syncthreads();
         // ---- tensor-core accumulate --------------------------------------------------------------------
@@ -245,8 +276,12 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
           const MixPath& P = A.p[__ffs(mk) - 1];
           if (m < P.cout0 || m >= P.cout0 + P.cout) continue;
           const int64_t plane = ((int64_t)n * P.C + P.c0 + (m - P.cout0)) * (int64_t)P.H * P.W;
-          v0 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
-          if (ox + 1 < A.W) v1 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox + 1);
+          if (P.up == 2 && P.dtype == DT_F32 && ox + 1 < A.W) {
+            bilinear_up2_pair_f32(reinterpret_cast<const float*>(P.src) + plane, P.H, P.W, oy, ox, v0, v1);
+          } else {
+            v0 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
+            if (ox + 1 < A.W) v1 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox + 1);
+          }
         }
         if (has_slope) { v0 = prelu(v0, slope); v1 = prelu(v1, slope); }
         if (pair_store) {

@@ -150,6 +150,7 @@ struct csnet_plan {
   size_t il_smem_max = 0;
   std::vector<size_t> op_smem;
   std::vector<TcChoice> op_tc;
+  std::vector<std::vector<uint16_t*>> op_w16;     // per tensor-core MIX op, per path: packed 16-bit weights (device)
   // host-buffer pipeline (csnet_plan_run_host): copy streams, ping-pong staging, ordering events
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   void* h_in[2] = {nullptr, nullptr};
@@ -522,6 +523,21 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     P->op_tc[i] = TcChoice();
     P->op_smem[i] = 0;                                   // the generic kernel stages weights in static shared memory
   }
+  P->op_w16.assign(P->ops.size(), std::vector<uint16_t*>());
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    const TcChoice& tc = P->op_tc[i];
+    if (tc.mt <= 0) continue;
+    const csnet_op_desc& op = P->ops[i];
+    const int C = P->tensors[op.dst].C, slice = tc.mt * 16, m16t = (C + slice - 1) / slice * slice, WR = tc.kc + 8;
+    P->op_w16[i].assign(op.n_paths, nullptr);
+    for (int p = 0; p < op.n_paths; ++p) {
+      const csnet_path_desc& q = op.paths[p];
+      if (q.ksize == 0) continue;
+      const size_t halves = (size_t)((q.cin + tc.kc - 1) / tc.kc) * q.ksize * q.ksize * m16t * WR;
+      e = cudaMalloc(&P->op_w16[i][p], halves * 2);
+      if (e != cudaSuccess) return cleanup(CSNET_E_NOMEM, std::string("cudaMalloc(packed weights): ") + cudaGetErrorString(e));
+    }
+  }
   if (tc_smem_max > 48 * 1024) {
     e = set_tc_smem_t<__half>((int)tc_smem_max);
     if (e == cudaSuccess) e = set_tc_smem_t<__nv_bfloat16>((int)tc_smem_max);
@@ -547,6 +563,33 @@ int csnet_plan_set_blob(csnet_plan* P, const float* host_blob, int64_t n, void* 
   if (!P || !host_blob || n != P->blob_floats) return fail(CSNET_E_INVALID, "csnet_plan_set_blob: size mismatch");
   CU_CHECK(cudaSetDevice(P->device));
   CU_CHECK(cudaMemcpyAsync(P->blob, host_blob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  // tensor-core MIX ops read their weights as 16-bit [chunk][tap][m16_total][kc + 8] blocks: pack them here, once per
+  // weight update, so the kernels stage them with plain 16-byte copies
+  std::vector<std::vector<uint16_t>> keep;
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    const TcChoice& tc = P->op_tc[i];
+    if (tc.mt <= 0) continue;
+    const csnet_op_desc& op = P->ops[i];
+    const int C = P->tensors[op.dst].C, slice = tc.mt * 16, m16t = (C + slice - 1) / slice * slice, WR = tc.kc + 8;
+    for (int p = 0; p < op.n_paths; ++p) {
+      const csnet_path_desc& q = op.paths[p];
+      if (q.ksize == 0) continue;
+      const int kk = q.ksize * q.ksize, nchunks = (q.cin + tc.kc - 1) / tc.kc;
+      std::vector<uint16_t> h((size_t)nchunks * kk * m16t * WR, 0);
+      const float* w = host_blob + q.w_off;                         // [cin][kk][cout]
+      for (int ci = 0; ci < q.cin; ++ci)
+        for (int tap = 0; tap < kk; ++tap)
+          for (int co = 0; co < q.cout; ++co) {
+            const float v = w[((size_t)ci * kk + tap) * q.cout + co];
+            uint16_t bits;
+            if (tc.dtype == CSNET_F16) { __half hv = __float2half_rn(v); memcpy(&bits, &hv, 2); }
+            else { __nv_bfloat16 hv = __float2bfloat16_rn(v); memcpy(&bits, &hv, 2); }
+            h[(((size_t)(ci / tc.kc) * kk + tap) * m16t + q.cout0 + co) * WR + ci % tc.kc] = bits;
+          }
+      CU_CHECK(cudaMemcpyAsync(P->op_w16[i][p], h.data(), h.size() * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+      keep.push_back(std::move(h));
+    }
+  }
   CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   return CSNET_OK;
 }
@@ -566,7 +609,10 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
   if (op.kind == CSNET_OP_MIX && P->op_tc[i].mt > 0) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     const TcChoice& tc = P->op_tc[i];
-    csnet::TcGeom G{(D.W + csnet::kTcTW - 1) / csnet::kTcTW, tc.xs_halves, tc.kc};
+    csnet::TcGeom G{};
+    G.tiles_x = (D.W + csnet::kTcTW - 1) / csnet::kTcTW; G.xs_halves = tc.xs_halves; G.kc = tc.kc;
+    G.m16_total = (D.C + tc.mt * 16 - 1) / (tc.mt * 16) * (tc.mt * 16);
+    for (int p = 0; p < op.n_paths; ++p) G.w16[p] = P->op_w16[i][p];
     dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), (D.C + tc.mt * 16 - 1) / (tc.mt * 16), N);
     launch_mix_tc(tc, grid, P->op_smem[i], stream, A, G);
   } else if (op.kind == CSNET_OP_MIX) {
@@ -690,6 +736,9 @@ void csnet_plan_destroy(csnet_plan* P) {
   if (P->blob) cudaFree(P->blob);
   if (P->arena) cudaFree(P->arena);
   if (P->gn_stats) cudaFree(P->gn_stats);
+  for (auto& v : P->op_w16)
+    for (uint16_t* q : v)
+      if (q) cudaFree(q);
   for (int b = 0; b < 2; ++b) {
     if (P->h_in[b]) cudaFree(P->h_in[b]);
     if (P->h_out[b]) cudaFree(P->h_out[b]);

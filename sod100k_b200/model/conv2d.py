@@ -45,6 +45,8 @@ class Conv2dX100(nn.Module):
                 f"padding={self.padding}, dilation={self.dilation}, groups={self.groups}, x100")
 
     def forward(self, x):
-        from ..modular import conv2d_x100_forward
-
+        try:
+            from ..modular import conv2d_x100_forward
+        except ImportError:
+            from sod100k_b200.modular import conv2d_x100_forward
         return conv2d_x100_forward(self, x)

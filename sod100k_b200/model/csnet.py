@@ -21,7 +21,12 @@ import torch
 import torch.nn as nn
 from torch.nn import init
 
-from .. import splits
+try:
+    from .. import modular, splits
+    from ..engine import ModelEngine
+except ImportError:      # imported as the top-level package `model` (dropped under the reference's scripts)
+    from sod100k_b200 import modular, splits
+    from sod100k_b200.engine import ModelEngine
 from .conv2d import Conv2dX100
 
 __all__ = ["CSNet", "ILBlock", "gOctaveConv", "gOctaveCBR", "SimplifiedGOctConvBR", "CSFHead", "PallMSBlock",
@@ -56,9 +61,7 @@ class gOctaveConv(nn.Module):
         init.kaiming_uniform_(self.weight, a=math.sqrt(5))
 
     def forward(self, xset):
-        from ..modular import goct_conv_forward
-
-        return goct_conv_forward(self, xset)
+        return modular.goct_conv_forward(self, xset)
 
 
 class gOctaveCBR(nn.Module):
@@ -83,9 +86,7 @@ class gOctaveCBR(nn.Module):
         self.all_flops, self.baseflop, self.expandflop = 0, None, None
 
     def forward(self, xset):
-        from ..modular import goct_cbr_forward
-
-        return goct_cbr_forward(self, xset)
+        return modular.goct_cbr_forward(self, xset)
 
 
 class SimplifiedGOctConvBR(nn.Module):
@@ -110,9 +111,7 @@ class SimplifiedGOctConvBR(nn.Module):
         self.all_flops, self.baseflop, self.expandflop = 0, None, None
 
     def forward(self, xset):
-        from ..modular import dw_cbr_forward
-
-        return dw_cbr_forward(self, xset)
+        return modular.dw_cbr_forward(self, xset)
 
 
 class ILBlock(nn.Module):
@@ -150,9 +149,7 @@ class MSBlock(nn.Module):
         self.prelu = nn.PReLU(out_channels)
 
     def forward(self, x):
-        from ..modular import ms_block_forward
-
-        return ms_block_forward(self, x)
+        return modular.ms_block_forward(self, x)
 
 
 class PallMSBlock(nn.Module):
@@ -218,8 +215,6 @@ class CSNet(nn.Module):
 
     # ---- engine -------------------------------------------------------------------------------------
     def engine(self):
-        from ..engine import ModelEngine
-
         if self._engine is None:
             object.__setattr__(self, "_engine", ModelEngine(self))
         return self._engine

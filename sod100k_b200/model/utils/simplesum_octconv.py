@@ -59,8 +59,6 @@ def _norm_act(bn, prelu, shape):
 
 
 def print_model_parm_flops(model, inputsize, device=-1):
-    from ..csnet import ILBlock  # noqa: F401  (module tree walked below)
-
     c, h, w = inputsize
     total = 0.0
 
