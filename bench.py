@@ -34,8 +34,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
-                    help="infer (default, BASELINE configs[1]) or train: fwd+bwd+Adam step, fp32 module-granular kernels")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "csf"],
+                    help="infer (default, BASELINE configs[1]); train: fwd+bwd+Adam step (configs 3-4 shape, fp32 kernels); "
+                         "csf: CSF+Res2Net-50 inference (config 5: bs 64, 352x352, fp16; backbone on torch/cuDNN, head on the engine)")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--dtype", default="fp16", choices=["fp32", "fp16", "bf16"])
@@ -365,11 +366,61 @@ def run_train(a):
         dist.destroy_process_group()
 
 
+def run_csf(a):
+    """Config 5: CSF+Res2Net-50, bs 64, 352x352, fp16, seeded synthetic weights (the reference ships none).  The line splits
+    the step into the cuDNN backbone (library) and the CSF head (our kernels): only the head is the product."""
+    import torch
+
+    from sod100k_b200 import synth
+    from sod100k_b200.networks import csf_res2net
+
+    torch.cuda.set_device(0)
+    m = csf_res2net.build_model()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_r(shapes, 21).items()})
+    m.cuda().eval().set_precision(a.dtype)
+    B, S = (64 if a.batch == 256 else a.batch), (352 if a.size == 224 else a.size)
+    x = torch.from_numpy(synth.randn_images(min(B, 8), S, S, 1234)).repeat((B + 7) // 8, 1, 1, 1)[:B].cuda()
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    with torch.no_grad():
+        for _ in range(a.warmup):
+            m(x)
+        clocks = ClockSampler(0)
+        ms = timed(lambda: m(x), a.steps)
+        clk = clocks.stop()
+        ms_backbone = timed(lambda: m.backbone(x), a.steps)
+    ips = B * a.steps / (ms * 1e-3)
+    head_ms = (ms - ms_backbone) / a.steps
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tf = float(json.load(open(peaks))["bf16_tflops"]) if os.path.exists(peaks) else 1590.0
+    head_flops = 2 * 8.11e9 * (S / 352.0) ** 2 * B               # SURVEY: 8.11 GMAC per 352x352 image in the head
+    print(json.dumps({
+        "metric": "images/sec CSF+Res2Net50 fwd 352x352", "value": ips, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": f"CSF+Res2Net-50 inference, {B} x {S}x{S}, {a.dtype}; backbone = torch/cuDNN (library), CSF head = engine",
+                   "backbone_ms": ms_backbone / a.steps, "head_ms": head_ms, "weights": "seeded synthetic (no checkpoint ships)"},
+        "clocks": clk, "gpu_launches": None,
+        "roofline": {"bound": "tensor", "achieved": head_flops / (head_ms * 1e-3) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                     "frac": head_flops / (head_ms * 1e-3) / 1e12 / tf, "traffic": None, "kernel": "CSF head (all engine kernels)"}}))
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     if a.impl == "reference":
         run_reference(a, rank)
+    elif a.mode == "csf":
+        run_csf(a)
     elif a.mode == "train":
         if a.batch == 256:
             a.batch = 32

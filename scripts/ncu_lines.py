@@ -11,8 +11,9 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "sod100k_b200", "libcsnet_b200.so")], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "--print-line-info", cubin], cwd=tmp, capture_output=True, text=True).stdout.splitlines()
+sass = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    sass += subprocess.run(["nvdisasm", "--print-line-info", cubin], cwd=tmp, capture_output=True, text=True).stdout.splitlines()
 lines, cur, inside = [], None, False
 for l in sass:
     if l.startswith("\t.section\t.text."):
