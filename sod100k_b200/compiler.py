@@ -59,6 +59,17 @@ def il_block_fits(Chi, Cli, Cho, Clo) -> bool:
     return halves * 2 + 512 <= 227 * 1024
 
 
+def upsample_input_side(cin: int, cout: int, up: int) -> bool:
+    """A 1x1 up path can up-sample its INPUT (conv at the high resolution over cin channels, cin bilinear evaluations per
+    output pixel at staging) or its OUTPUT (the reference's order: conv at the low resolution, cout bilinear evaluations per
+    output pixel in the epilogue).  Cost model in issued-instruction equivalents per output pixel: a MAC on the tensor-core
+    path ~0.16, a staged bilinear evaluation ~30, an epilogue one ~20.  Narrow layers (CSNet: 24 -> 79) win on the input
+    side; wide ones (CSF+Res2Net: 256 -> 1408) must keep the conv at the low resolution."""
+    cost_in = 0.16 * cin * cout + 30.0 * cin
+    cost_out = 0.16 * cin * cout / (up * up) + 20.0 * cout
+    return cost_in < cost_out
+
+
 def _np(v) -> np.ndarray:
     if hasattr(v, "detach"):
         v = v.detach().cpu().numpy()
@@ -154,7 +165,7 @@ class _Lowering:
                 cin = ci[i + 1] - ci[i]
                 w = W4[co[j]:co[j + 1], ci[i]:ci[i + 1]] * s[:, None, None, None]
                 common = dict(pre_avg=int(stride == 2), ksize=ksize, pad=pad, w_off=self.conv_w(w))
-                if i > j and ksize == 1 and stride == 1 and self.upsample_inputs and cin <= cj:
+                if i > j and ksize == 1 and stride == 1 and self.upsample_inputs and upsample_input_side(cin, cj, 2 ** (i - j)):
                     # 16-bit programs, 1x1, fewer input than output channels: up-sample the conv INPUT instead of its
                     # output (identical linear map, cin instead of cout bilinear evaluations, no scratch tensor)
                     paths.append(ir.Path(x, cin, cj, ksize=1, up=2 ** (i - j), w_off=self.conv_w(w)))

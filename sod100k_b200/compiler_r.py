@@ -18,7 +18,7 @@ from typing import Mapping, Sequence, Tuple
 import numpy as np
 
 from . import ir, splits
-from .compiler import _np
+from .compiler import _np, upsample_input_side
 
 FUSE_IN_SPLIT = [1 / 15, 2 / 15, 4 / 15, 8 / 15]       # csf_res2net.py:240
 FUSE_OUT_SPLIT = [1 / 11, 2 / 11, 4 / 11, 4 / 11]      # :242
@@ -82,11 +82,19 @@ def compile_csf_head(params: Mapping[str, object], feat_dims: Sequence[Tuple[int
         b.op(ir.OP_MIX, raw, paths, name=f"ms.convs.{br}")
         zs.append(gn(raw, f"ms.convs.{br}.bn", f"ms.convs.{br}.prelu", f"ms/{br}"))
         b.prog.taps[f"ms/{br}"] = zs[-1]
-    # ---- fuse1x1: 4 -> 1; up paths (cin < cout) up-sample the conv input ------------------------------------------------
+    # ---- fuse1x1: 4 -> 1 (up paths: input- or output-side resampling by the cost model in compiler.upsample_input_side) ----
     W1 = p("fuse1x1.conv.weights")
     c1 = splits.cuts(W1.shape[1], FUSE_OUT_SPLIT)
     cout = W1.shape[0]
-    paths = [ir.Path(zs[i], c1[i + 1] - c1[i], cout, ksize=1, up=2 ** i, w_off=conv_w(W1[:, c1[i]:c1[i + 1]])) for i in range(4)]
+    paths = []
+    for i in range(4):
+        cin_i, w_i = c1[i + 1] - c1[i], W1[:, c1[i]:c1[i + 1]]
+        if i == 0 or (dt != ir.F32 and upsample_input_side(cin_i, cout, 2 ** i)):
+            paths.append(ir.Path(zs[i], cin_i, cout, ksize=1, up=2 ** i, w_off=conv_w(w_i)))
+        else:                                             # wide layers: conv at the low resolution, resample the output
+            low = b.tensor(cout, feat_dims[i][1], feat_dims[i][2], ir.F32, name=f"fuse1x1/low{i}")
+            b.op(ir.OP_MIX, low, [ir.Path(zs[i], cin_i, cout, ksize=1, w_off=conv_w(w_i))], name=f"fuse1x1.low{i}")
+            paths.append(ir.Path(low, cout, cout, ksize=0, up=2 ** i))
     raw = b.tensor(cout, feat_dims[0][1], feat_dims[0][2], dt, name="fuse1x1/raw")
     b.op(ir.OP_MIX, raw, paths, name="fuse1x1.0")
     f0 = gn(raw, "fuse1x1.bns.0", "fuse1x1.prelus.0", "fuse1x1/0")
