@@ -52,7 +52,6 @@ struct IlArgs {
   int32_t TH, TW, tiles_x;     // tile (one of the instantiated geometries) and tiles per image row
   int32_t K8, MH16, ML16;
   int32_t rowsAh, rowsAl;
-  int32_t dw_mma;              // percent of the depthwise channels computed in the banded-Toeplitz mma form (0: FMA only)
   int32_t t2h;                 // channels of the hi T2 buffer: Cho (whole layer resident) or 8 (channel-chunked dw tail)
   int32_t tma_h, tma_l;        // 1: that input is loaded with TMA
 };
@@ -248,145 +247,6 @@ __device__ __forceinline__ void dw_task(int task, const uint16_t* in, uint16_t* 
         if (!in_img) v = make_uint2(0u, 0u);
         *reinterpret_cast<uint2*>(out + c * NP + r * RW + x) = v;
       }
-    }
-  }
-}
-
-// ---- depthwise 3x3 on the tensor cores --------------------------------------------------------------------------
-// A depthwise conv along a row is a banded (Toeplitz) matrix product: out[r][x0+n] = sum_dy sum_k in[r+dy-1][x0+o+k] *
-// B_dy,o[k][n] with B_dy,o[k][n] = w[dy][k - n + 1 + o] (zero outside the 3 taps).  One warp produces a 16-row x 8-column
-// block of one channel with 9 mma.sync m16n8k8 (3 row shifts x the 8-column windows at o = -8, 0, +8 — all 16-byte
-// aligned, so the A operand comes straight from the smem plane with ldmatrix), fp32 accumulation, bias as the
-// accumulator's initial value; products of two 16-bit values are exact in fp32, so this matches the FMA path up to the
-// 16-bit rounding of the 9 weights.  ~0.3 issued warp-instructions per output instead of ~0.85 on the FMA path.
-template <typename T, bool kToGlobal, typename GEO>
-__device__ __forceinline__ void dw_block_mma(int task, const uint16_t* in, uint16_t* out, const DwParams& P, int oy0, int ox0,
-                                             int imgH, int imgW, int RH, int lane) {
-  constexpr int RW = GEO::RW, NP = GEO::NP, R0 = GEO::R0, R1 = GEO::R1, C0 = 4 * GEO::G0, C1 = 4 * GEO::G1;
-  constexpr int NCB = RW / 8, NRB = (R1 - R0 + 15) / 16;
-  const int rb = task % NRB, c = task / NRB;
-  const int g = lane >> 2, t = lane & 3;
-  const int rbase = R0 + rb * 16;
-  const float bias = __ldg(P.b + c), slope = __ldg(P.s + c);
-  // B fragments of the 3 row shifts x 3 windows, built once per (channel, row block): B[k][n = g] = w[dy][k - g + 1 + o].
-  // Middle window: a band; left window: only B[7][0] = w[dy][0] (lane 3, high half); right: only B[0][7] = w[dy][2]
-  // (lane 28, low half).  Selection runs on the already converted 16-bit values with integer masks (branch-free).
-  uint32_t bf[3][3];
-  {
-    const int i0 = 2 * t - g + 1;
-    const uint32_t a0 = i0 == 0 ? 0xffffu : 0u, a1 = i0 == 1 ? 0xffffu : 0u, a2 = i0 == 2 ? 0xffffu : 0u;
-    const uint32_t b0 = i0 == -1 ? 0xffffu : 0u;                       // high half: index i0 + 1 -> b1 = a0, b2 = a1
-    const uint32_t l3 = lane == 3 ? 0xffff0000u : 0u, l28 = lane == 28 ? 0xffffu : 0u;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const uint32_t h01 = Pack<T>::from_f2(__ldg(P.w + c * 9 + dy * 3), __ldg(P.w + c * 9 + dy * 3 + 1));
-      const uint32_t h2 = Pack<T>::from_f2(__ldg(P.w + c * 9 + dy * 3 + 2), 0.f) & 0xffffu;
-      const uint32_t h0 = h01 & 0xffffu, h1 = h01 >> 16;
-      const uint32_t lo = (h0 & a0) | (h1 & a1) | (h2 & a2), hi = (h0 & b0) | (h1 & a0) | (h2 & a1);
-      bf[dy][0] = (h0 << 16) & l3;
-      bf[dy][1] = lo | (hi << 16);
-      bf[dy][2] = h2 & l28;
-    }
-  }
-  // row this lane addresses for ldmatrix.x2: lanes 0-7 -> rows 0-7, lanes 8-15 -> rows 8-15 of the 16-row block
-  const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1);
-  const uint16_t* rowp[3];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    int r = rbase + lrow + dy - 1;
-    r = r < 0 ? 0 : (r > RH - 1 ? RH - 1 : r);                 // clamped rows only feed outputs that are discarded
-    rowp[dy] = in + c * NP + r * RW;
-  }
-  const int r0 = rbase + g, r1 = r0 + 8;
-  const int gy0 = oy0 + r0, gy1 = oy0 + r1;
-  const bool img0 = (unsigned)gy0 < (unsigned)imgH, img1 = (unsigned)gy1 < (unsigned)imgH;
-  const bool st0 = r0 < R1 && (!kToGlobal || img0), st1 = r1 < R1 && (!kToGlobal || img1);
-  const int gxb = ox0 + 2 * t;
-  // row pointers of this lane's two output rows (the per-column-block offset is a compile-time constant)
-  uint16_t* o0 = kToGlobal ? out + ((size_t)c * imgH + (img0 ? gy0 : 0)) * imgW + gxb : out + c * NP + r0 * RW + 2 * t;
-  uint16_t* o1 = kToGlobal ? out + ((size_t)c * imgH + (img1 ? gy1 : 0)) * imgW + gxb : out + c * NP + r1 * RW + 2 * t;
-  // sliding window of A fragments: win[dy][0..2] = the 8-column windows at x0-8, x0, x0+8 of row shift dy; each window is
-  // loaded once and used by three consecutive column blocks (the loop is fully unrolled, the shifts are renames)
-  uint32_t win[3][3][2];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    win[dy][0][0] = win[dy][0][1] = 0u;
-    ldmatrix_x2(win[dy][1], rowp[dy]);
-    if (NCB > 1) ldmatrix_x2(win[dy][2], rowp[dy] + 8);
-  }
-#pragma unroll
-  for (int cb = 0; cb < NCB; ++cb) {
-    const int x0 = cb * 8;
-    // one accumulator per row shift: three independent mma chains of depth <= 3 instead of one of depth 9
-    float acc3[3][4];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc3[dy][j] = dy == 0 ? bias : 0.f;
-#pragma unroll
-    for (int oi = 0; oi < 3; ++oi) {
-      // the windows left of the first / right of the last column block lie outside the row: they only feed the unused
-      // halo columns 0 and RW-1, and must not be read (0 x NaN from unwritten smem would poison the whole row)
-      if ((oi == 0 && cb == 0) || (oi == 2 && cb == NCB - 1)) continue;
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) Pack<T>::mma(acc3[dy], win[dy][oi], bf[dy][oi]);
-    }
-    float acc[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = (acc3[0][j] + acc3[1][j]) + acc3[2][j];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      win[dy][0][0] = win[dy][1][0]; win[dy][0][1] = win[dy][1][1];
-      win[dy][1][0] = win[dy][2][0]; win[dy][1][1] = win[dy][2][1];
-      if (cb + 2 < NCB) ldmatrix_x2(win[dy][2], rowp[dy] + x0 + 16);
-    }
-    const int x = x0 + 2 * t;
-    const bool col_rng = x >= C0 && x < C1;                    // C0, C1, imgW, gx even: pairs are all in or all out
-    const bool col_img = (unsigned)(gxb + x0) < (unsigned)imgW;
-    uint32_t v0 = Pack<T>::from_f2(prelu(acc[0], slope), prelu(acc[1], slope));
-    uint32_t v1 = Pack<T>::from_f2(prelu(acc[2], slope), prelu(acc[3], slope));
-    if (kToGlobal) {
-      if (col_rng && col_img && st0) *reinterpret_cast<uint32_t*>(o0 + x0) = v0;
-      if (col_rng && col_img && st1) *reinterpret_cast<uint32_t*>(o1 + x0) = v1;
-    } else {
-      v0 = (col_img && img0) ? v0 : 0u;
-      v1 = (col_img && img1) ? v1 : 0u;
-      if (col_rng && st0) *reinterpret_cast<uint32_t*>(o0 + x0) = v0;
-      if (col_rng && st1) *reinterpret_cast<uint32_t*>(o1 + x0) = v1;
-    }
-  }
-}
-
-// Hybrid pass: legacy mma.sync on sm_100 runs the banded form at about the FP32-FMA rate (the tensor pipe is the limiter:
-// only 3 of every 24 k-columns of B are non-zero), but the tensor and FMA pipes are independent.  Two of the four warps
-// of every scheduler take the first `pct` percent of the channels in the mma form, the other two take the rest in the
-// FMA form, so both pipes are busy at once.
-template <typename T, bool kToGlobal, int RUN, typename GH, typename GL>
-__device__ __forceinline__ void dw_pass_hybrid(const uint16_t* inH, uint16_t* outH, const DwParams& PH, int Ch, int hy, int hx, int H,
-                                               int W, int RHh, const uint16_t* inL, uint16_t* outL, const DwParams& PL, int Cl, int ly,
-                                               int lx, int RHl, int tid, int pct) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int ChM = (Ch * pct + 50) / 100, ClM = (Cl * pct + 50) / 100;
-  const int sub = (warp & 3) + 4 * (warp >> 3);                  // 0..7 within the mma / FMA warp set
-  if (((warp >> 2) & 1) == 0) {
-    constexpr int perH = (GH::R1 - GH::R0 + 15) / 16, perL = (GL::R1 - GL::R0 + 15) / 16;
-    const int nA = ChM * perH, nB = ClM * perL;
-    for (int task = sub; task < nA + nB; task += 8) {
-      if (task < nA) dw_block_mma<T, kToGlobal, GH>(task, inH, outH, PH, hy, hx, H, W, RHh, lane);
-      else dw_block_mma<T, kToGlobal, GL>(task - nA, inL, outL, PL, ly, lx, H >> 1, W >> 1, RHl, lane);
-    }
-  } else {
-    constexpr int perH = ((GH::R1 - GH::R0 + RUN - 1) / RUN) * (GH::G1 - GH::G0);
-    constexpr int perL = ((GL::R1 - GL::R0 + RUN - 1) / RUN) * (GL::G1 - GL::G0);
-    const int nA = (Ch - ChM) * perH, nB = (Cl - ClM) * perL;
-    const DwParams QH{PH.w + ChM * 9, PH.b + ChM, PH.s + ChM}, QL{PL.w + ClM * 9, PL.b + ClM, PL.s + ClM};
-    const uint16_t* iH = inH + (size_t)ChM * GH::NP;
-    const uint16_t* iL = inL + (size_t)ClM * GL::NP;
-    uint16_t* oH = outH + (kToGlobal ? (size_t)ChM * H * W : (size_t)ChM * GH::NP);
-    uint16_t* oL = outL + (kToGlobal ? (size_t)ClM * (H >> 1) * (W >> 1) : (size_t)ClM * GL::NP);
-    for (int task = sub * 32 + lane; task < nA + nB; task += 256) {
-      if (task < nA) dw_task<T, kToGlobal, RUN, GH>(task, iH, oH, QH, hy, hx, H, W);
-      else dw_task<T, kToGlobal, RUN, GL>(task - nA, iL, oL, QL, ly, lx, H >> 1, W >> 1);
     }
   }
 }
@@ -615,26 +475,11 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   using GL2 = DwGeom<RWl, NPL, 2, rl - 2, 1, RWl / 4 - 1>;
   uint16_t* outH = reinterpret_cast<uint16_t*>(A.yh) + (size_t)n * Cho * H * W;
   uint16_t* outL = Clo > 0 ? reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * Clo * Hl * Wl : nullptr;
-  if (A.t2h >= Cho && A.dw_mma) {
-    dw_pass_hybrid<T, false, 6, GH1, GL1>(bufAh, bufBh, A.dw1h, Cho, hy0 - 4, hx0 - 4, H, W, RHh, bufAl, bufBl, A.dw1l, Clo, ly0 - 2, lx0 - 4, RHl, tid, A.dw_mma);
-    __syncthreads();
-    dw_pass_hybrid<T, true, 4, GH2, GL2>(bufBh, outH, A.dw2h, Cho, hy0 - 4, hx0 - 4, H, W, RHh, bufBl, outL, A.dw2l, Clo, ly0 - 2, lx0 - 4, RHl, tid, A.dw_mma);
-  } else if (A.t2h >= Cho) {
+  if (A.t2h >= Cho) {
     // whole layers resident: dw1 (T1 -> T2, smem) then dw2 (T2 -> global)
     dw_pass<T, false, 6, GH1, GL1>(bufAh, bufBh, A.dw1h, Cho, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l, Clo, ly0 - 2, lx0 - 4, tid);
     __syncthreads();
     dw_pass<T, true, 4, GH2, GL2>(bufBh, outH, A.dw2h, Cho, hy0 - 4, hx0 - 4, H, W, bufBl, outL, A.dw2l, Clo, ly0 - 2, lx0 - 4, tid);
-  } else if (A.dw_mma) {
-    for (int c0 = 0; c0 < Cho; c0 += A.t2h) {
-      const int cc = (Cho - c0) < A.t2h ? (Cho - c0) : A.t2h;
-      const DwParams p1{A.dw1h.w + c0 * 9, A.dw1h.b + c0, A.dw1h.s + c0}, p2{A.dw2h.w + c0 * 9, A.dw2h.b + c0, A.dw2h.s + c0};
-      if (c0 > 0) __syncthreads();
-      dw_pass_hybrid<T, false, 6, GH1, GL1>(bufAh + (size_t)c0 * NPH, bufBh, p1, cc, hy0 - 4, hx0 - 4, H, W, RHh, bufAl, bufBl, A.dw1l,
-                                            c0 == 0 ? Clo : 0, ly0 - 2, lx0 - 4, RHl, tid, A.dw_mma);
-      __syncthreads();
-      dw_pass_hybrid<T, true, 4, GH2, GL2>(bufBh, outH + (size_t)c0 * H * W, p2, cc, hy0 - 4, hx0 - 4, H, W, RHh, bufBl, outL, A.dw2l,
-                                           c0 == 0 ? Clo : 0, ly0 - 2, lx0 - 4, RHl, tid, A.dw_mma);
-    }
   } else {
     // wide blocks: the hi branch goes through the two layers 8 channels at a time (T2 buffer of 8 planes), the lo
     // branch rides along with the first chunk

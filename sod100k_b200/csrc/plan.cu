@@ -356,8 +356,6 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   A.ML16 = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
   A.rowsAh = A.K8 > A.Cho ? A.K8 : A.Cho;
   A.rowsAl = A.Clo > 0 ? (A.K8 > A.Clo ? A.K8 : A.Clo) : A.Cli;
-  static const int dw_mma_pct = [] { const char* e = getenv("CSNET_DW_MMA"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
-  A.dw_mma = dw_mma_pct;
   static const bool use_tma = [] { const char* e = getenv("CSNET_TMA"); return e && e[0] == '1'; }();   // opt-in until the 16-byte start-alignment rule is met
   A.tma_h = use_tma && (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
   A.tma_l = use_tma && ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
@@ -372,10 +370,7 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
       const int NPH = ((T.TH + 8) | 1) * (T.TW + 8), NPL = ((T.TH / 2 + 4) | 1) * (T.TW / 2 + 8);
       if (csnet::il_smem_bytes(T, NPH, NPL) > 227 * 1024) continue;
       const int ty = (A.H + T.TH - 1) / T.TH, tx = (A.W + T.TW - 1) / T.TW;
-      // halo work (+ the 16-row mma blocks of the two depthwise layers, which round TH+2 and TH rows up), small penalty
-      // for the extra barriers of the chunked tail.  28-row tiles make both layers fit whole blocks (30 -> 32, 28 -> 32).
-      const double mma_rows = A.dw_mma ? 0.5 * 16.0 * ((T.TH + 2 + 15) / 16 + (T.TH + 15) / 16) * (T.TW + 8) : 0.0;
-      const double cost = (double)ty * tx * (NPH + mma_rows) * (chunked ? 1.15 : 1.0);
+      const double cost = (double)ty * tx * NPH * (chunked ? 1.15 : 1.0);   // halo work, small penalty for the extra barriers
       if (best < 0 || cost < best) { best = cost; T.tiles_x = tx; *out = T; }
     }
   }
