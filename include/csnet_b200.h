@@ -98,7 +98,11 @@ enum {
                                1 WL  packed 16-bit [ru16(Clo)][K8]: columns [W_ll | W_hl] (x_l, then max-pooled x_h)
                                2,3   conv bias / PReLU slope of the hi branch      4,5  of the lo branch
                                6-8   conv3x3_1 hi: weights [C][9], bias, slope     9-11 conv3x3_1 lo
-                               12-14 conv3x3_2 hi                                  15-17 conv3x3_2 lo */
+                               12-14 conv3x3_2 hi                                  15-17 conv3x3_2 lo
+                             Stem form (the first block, `first=True`, csnet.py:60-71): paths[0] and paths[1] both name
+                             the fp32 input image (cin <= 3) with ksize = 3, pad = 1, paths[1].pool = 2; both branches are
+                             3x3 convs of it (lo: of its 2x2 max-pool).  WH / WL are then [ru16(C)][32] with column
+                             k = ci*9 + ky*3 + kx; the kernel builds the im2col planes in shared memory. */
 };
 
 /*

@@ -245,12 +245,50 @@ class _Lowering:
         op.dst2, op.ext_off = yl, ext
         return [yh] + ([yl] if Clo else [])
 
+    def il_block_stem_fused(self, prefix, xs, a_in, a_out):
+        """The first ILBlock (one fp32 image in, 3x3 gOctaveCBR, csnet.py:60-76) as one CSNET_OP_ILBLOCK in its stem
+        form: the kernel builds im2col planes of the image / its 2x2 max-pool and reuses the 1x1 machinery."""
+        if len(a_in) != 1 or len(a_out) not in (1, 2) or xs[0] is None:
+            return None
+        W4 = self.p(prefix + ".conv1x1.conv.weight")
+        co = splits.cuts(W4.shape[0], a_out)
+        Cho, Clo = co[1] - co[0], (co[2] - co[1]) if len(a_out) == 2 else 0
+        Ci, H_, W_ = self.dims(xs[0])
+        if self.b.prog.tensors[xs[0]].dtype != ir.F32 or Ci * 9 > 32 or W4.shape[1] != Ci or Cho <= 0 or (len(a_out) == 2 and Clo <= 0):
+            return None
+        if W_ % 8 or H_ % 2 or not il_block_fits(Ci * 9, 0, Cho, Clo):
+            return None
+        K8 = 32
+        s_h, t_h = self.bn_fold(prefix + ".conv1x1.bns.0")
+        WH = np.zeros((_ru(Cho, 16), K8))
+        WH[:Cho, :Ci * 9] = (W4[co[0]:co[1]] * s_h[:, None, None, None]).reshape(Cho, -1)
+        WL = np.zeros((max(_ru(Clo, 16), 16), K8))
+        ext = [0, 0, self.b.param(t_h), self.b.param(self.p(prefix + ".conv1x1.prelus.0.weight")), -1, -1]
+        if Clo > 0:
+            s_l, t_l = self.bn_fold(prefix + ".conv1x1.bns.1")
+            WL[:Clo, :Ci * 9] = (W4[co[1]:co[2]] * s_l[:, None, None, None]).reshape(Clo, -1)
+            ext[4], ext[5] = self.b.param(t_l), self.b.param(self.p(prefix + ".conv1x1.prelus.1.weight"))
+        lim = 6.0e4 if self.dt == ir.F16 else 3.0e38
+        if not (np.isfinite(WH).all() and np.isfinite(WL).all() and max(np.abs(WH).max(), np.abs(WL).max()) < lim):
+            return None
+        ext[0] = self.b.param_bits16(to_bits16(WH, self.dt))
+        ext[1] = self.b.param_bits16(to_bits16(WL, self.dt))
+        none3 = [-1, -1, -1]
+        ext += self.dw_params(prefix + ".conv3x3_1", 0) + (self.dw_params(prefix + ".conv3x3_1", 1) if Clo else none3)
+        ext += self.dw_params(prefix + ".conv3x3_2", 0) + (self.dw_params(prefix + ".conv3x3_2", 1) if Clo else none3)
+        yh = self.b.tensor(Cho, H_, W_, self.dt, name=f"{prefix}/0")
+        yl = self.b.tensor(Clo, H_ // 2, W_ // 2, self.dt, name=f"{prefix}/1") if Clo else -1
+        op = self.b.op(ir.OP_ILBLOCK, yh, [ir.Path(xs[0], Ci, Cho, ksize=3, pad=1),
+                                           ir.Path(xs[0], Ci, max(Clo, 1), ksize=3, pad=1, pool=2)], name=prefix)
+        op.dst2, op.ext_off = yl, ext
+        return [yh] + ([yl] if Clo else [])
+
     def il_block(self, prefix, xs, in_split, out_split, stride, first):
         """ILBlock.forward (csnet.py:72-76)."""
         a_in, a_out = splits.alphas(in_split), splits.alphas(out_split)
         k = 3 if (first or stride == 2) else 1
-        if k == 1 and (self.fuse is True or (self.fuse and prefix in self.fuse)):
-            y = self.il_block_fused(prefix, xs, a_in, a_out)
+        if (k == 1 or (first and stride == 1)) and (self.fuse is True or (self.fuse and prefix in self.fuse)):
+            y = self.il_block_fused(prefix, xs, a_in, a_out) if k == 1 else self.il_block_stem_fused(prefix, xs, a_in, a_out)
             if y is not None:
                 for b_, t in enumerate(y):
                     self.b.prog.taps[f"{prefix}/{b_}"] = t

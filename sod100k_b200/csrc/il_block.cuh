@@ -52,6 +52,8 @@ struct IlArgs {
   int32_t TH, TW, tiles_x;     // tile (one of the instantiated geometries) and tiles per image row
   int32_t K8, MH16, ML16;
   int32_t rowsAh, rowsAl;
+  int32_t first;               // 1: stem form — xh is the fp32 image [N][Chi/9][H][W], both branches are 3x3 convs of it
+                               //    (lo: of its 2x2 max-pool), lowered to the same GEMMs through im2col planes built in smem
   int32_t t2h;                 // channels of the hi T2 buffer: Cho (whole layer resident) or 8 (channel-chunked dw tail)
   int32_t tma_h, tma_l;        // 1: that input is loaded with TMA
 };
@@ -325,7 +327,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     for (int i = y0 + tid; i < y1; i += kIlThreads) reinterpret_cast<uint32_t*>(bufAl)[i] = 0u;
   }
   // cp.async fallback loaders (8-byte chunks, zero fill outside the image)
-  if (!A.tma_h) {
+  if (!A.tma_h && !A.first) {
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(A.xh) + (size_t)n * Chi * H * W;
     constexpr int quads_row = RWh >> 2, quads_plane = NPH >> 2;
     for (int i = tid; i < Chi * quads_plane; i += kIlThreads) {
@@ -336,7 +338,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
       cp_async8(bufAh + (size_t)c * NPH + pq * 4, ok ? xh + ((size_t)c * H + gy) * W + gx : xh, ok);
     }
   }
-  if (!A.tma_l) {
+  if (!A.tma_l && !A.first) {
     const uint16_t* xl = reinterpret_cast<const uint16_t*>(A.xl) + (size_t)n * Cli * Hl * Wl;
     constexpr int quads_row = RWl >> 2, quads_plane = NPL >> 2;
     for (int i = tid; i < Cli * quads_plane; i += kIlThreads) {
@@ -356,6 +358,49 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   }
   __syncthreads();
 
+  if (A.first) {
+    // ---- stem form: fp32 image tile -> smem scratch (the T2 buffers, free until dw1), then the im2col planes ----
+    // scratch tile: image rows [hy0-6, hy0+TH+6), cols [hx0-12, hx0+TW+12), zero outside the image; covers the hi
+    // region +-1 pixel and the pooled lo region +-1 lo pixel
+    constexpr int IH = TH + 12, IW = TW + 24;
+    const int Ci = Chi / 9;
+    float* img = reinterpret_cast<float*>(bufBh);
+    const float* x = reinterpret_cast<const float*>(A.xh) + (size_t)n * Ci * H * W;
+    for (int i = tid; i < Ci * IH * (IW / 4); i += kIlThreads) {
+      const int c = i / (IH * (IW / 4)), r = i - c * (IH * (IW / 4));
+      const int iy = r / (IW / 4), ix = (r - iy * (IW / 4)) * 4;
+      const int gy = hy0 - 6 + iy, gx = hx0 - 12 + ix;          // gx % 4 == 0 and W % 4 == 0: a quad is all in or all out
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)c * H + gy) * W + gx));
+      *reinterpret_cast<float4*>(img + (c * IH + iy) * IW + ix) = v;
+    }
+    __syncthreads();
+    // hi planes: row k = (ci, ky, kx) holds the image shifted by (ky-1, kx-1); region (ry, rx) = image (hy0-4+ry, hx0-4+rx)
+    for (int i = tid; i < Chi * (NPH / 2); i += kIlThreads) {
+      const int k = i / (NPH / 2), pp = i - k * (NPH / 2);
+      const int ci = k / 9, t9 = k - ci * 9, ky = t9 / 3, kx = t9 - ky * 3;
+      const int ry = (2 * pp) / RWh, rx = 2 * pp - ry * RWh;
+      const float* src = img + (ci * IH + ry + 1 + ky) * IW + rx + 7 + kx;
+      reinterpret_cast<uint32_t*>(bufAh + (size_t)k * NPH)[pp] = Pack<T>::from_f2(src[0], src[1]);
+    }
+    // lo planes: 2x2 max-pool of the image, shifted by (ky-1, kx-1) lo pixels, zero outside the lo image (conv padding)
+    if (Clo > 0) {
+      constexpr int rl_ = TH / 2 + 4;
+      for (int i = tid; i < Chi * NPL; i += kIlThreads) {
+        const int k = i / NPL, p = i - k * NPL;
+        const int ci = k / 9, t9 = k - ci * 9, ky = t9 / 3, kx = t9 - ky * 3;
+        const int ry = p / RWl, rx = p - ry * RWl;
+        const int gy = ly0 - 3 + ry + ky, gx = lx0 - 5 + rx + kx;
+        float v = 0.f;
+        if (ry < rl_ && gy >= 0 && gy < Hl && gx >= 0 && gx < Wl) {
+          const float* src = img + (ci * IH + 2 * (ry + ky)) * IW + 2 * (rx + kx) + 2;
+          v = fmaxf(fmaxf(src[0], src[1]), fmaxf(src[IW], src[IW + 1]));
+        }
+        uint16_t h = (uint16_t)(Pack<T>::from_f2(v, 0.f) & 0xffffu);
+        bufAl[(size_t)k * NPL + p] = h;
+      }
+    }
+  } else {
   // ---- phase 1: resample both ways --------------------------------------------------------------------
   // (a) max_pool2d 2x2 of x_h -> AL rows [Cli, Cli+Chi): two lo pixels per task from 2 hi rows x 4 hi pixels
   if (Clo > 0) {
@@ -420,6 +465,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
       const int c = i / tailh, k = i - c * tailh;
       reinterpret_cast<uint32_t*>(bufAh + (size_t)(Chi + c) * NPH + covered)[k] = 0u;
     }
+  }
   }
   __syncthreads();
 

@@ -212,14 +212,22 @@ int validate(const csnet_plan& P) {
       if (a < 0 || a >= nt || b < 0 || b >= nt) return bad("ILBLOCK input out of range");
       const csnet_tensor_desc &Xh = P.tensors[a], &Xl = P.tensors[b];
       if (a == op.dst || b == op.dst || a == op.dst2 || b == op.dst2) return bad("in-place op");
-      if (Yh.dtype == CSNET_F32 || Xh.dtype != Yh.dtype || Xl.dtype != Yh.dtype) return bad("ILBLOCK needs one 16-bit dtype");
-      if (Xh.H != Yh.H || Xh.W != Yh.W || Xl.H * 2 != Xh.H || Xl.W * 2 != Xh.W) return bad("ILBLOCK input/output resolutions");
+      const bool stem = op.paths[0].ksize == 3;          // stem form: both branches are 3x3 convs of one fp32 image
+      if (Yh.dtype == CSNET_F32) return bad("ILBLOCK needs a 16-bit destination");
       if (Yh.W % 8 || Yh.H % 2) return bad("ILBLOCK needs W % 8 == 0 and H % 2 == 0");
+      if (stem) {
+        if (a != b || Xh.dtype != CSNET_F32 || Xh.C * 9 > 32) return bad("ILBLOCK stem form takes one fp32 image of at most 3 channels");
+        if (Xh.H != Yh.H || Xh.W != Yh.W) return bad("ILBLOCK input/output resolutions");
+        if (op.paths[1].ksize != 3 || op.paths[1].pool != 2) return bad("ILBLOCK stem form: lo path is a 3x3 conv of the 2x2 max-pool");
+      } else {
+        if (Xh.dtype != Yh.dtype || Xl.dtype != Yh.dtype) return bad("ILBLOCK needs one 16-bit dtype");
+        if (Xh.H != Yh.H || Xh.W != Yh.W || Xl.H * 2 != Xh.H || Xl.W * 2 != Xh.W) return bad("ILBLOCK input/output resolutions");
+      }
       if (op.paths[0].cin != Xh.C || op.paths[1].cin != Xl.C) return bad("ILBLOCK consumes whole input tensors");
       int Clo = 0;
       if (op.dst2 >= 0) {
         const csnet_tensor_desc& Yl = P.tensors[op.dst2];
-        if (Yl.dtype != Yh.dtype || Yl.H != Xl.H || Yl.W != Xl.W) return bad("ILBLOCK lo output shape");
+        if (Yl.dtype != Yh.dtype || Yl.H * 2 != Yh.H || Yl.W * 2 != Yh.W) return bad("ILBLOCK lo output shape");
         Clo = Yl.C;
       }
       const int nreq = Clo > 0 ? 18 : 15;
@@ -344,6 +352,8 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   A.yl = op.dst2 >= 0 ? P.tensor_ptr(op.dst2, N, ext) : nullptr;
   A.H = Yh.H; A.W = Yh.W;
   A.Chi = Xh.C; A.Cli = Xl.C; A.Cho = Yh.C; A.Clo = op.dst2 >= 0 ? P.tensors[op.dst2].C : 0;
+  A.first = op.paths[0].ksize == 3;
+  if (A.first) { A.Chi = Xh.C * 9; A.Cli = 0; A.xl = nullptr; }   // im2col rows of the image; no lo input tensor
   auto f = [&](int e) { return op.ext_off[e] >= 0 ? P.blob + op.ext_off[e] : nullptr; };
   A.wh = reinterpret_cast<const uint32_t*>(f(0));
   A.wl = reinterpret_cast<const uint32_t*>(f(1));
@@ -357,8 +367,8 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   A.rowsAh = A.K8 > A.Cho ? A.K8 : A.Cho;
   A.rowsAl = A.Clo > 0 ? (A.K8 > A.Clo ? A.K8 : A.Clo) : A.Cli;
   static const bool use_tma = [] { const char* e = getenv("CSNET_TMA"); return e && e[0] == '1'; }();   // opt-in until the 16-byte start-alignment rule is met
-  A.tma_h = use_tma && (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
-  A.tma_l = use_tma && ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
+  A.tma_h = use_tma && !A.first && (A.W % 8 == 0) && encode_tiled_fn() != nullptr;
+  A.tma_l = use_tma && !A.first && ((A.W / 2) % 8 == 0) && encode_tiled_fn() != nullptr;
   static const int cand[][2] = {{32, 32}, {28, 32}, {16, 64}, {16, 32}, {8, 16}};   // the instantiated tile geometries
   double best = -1;
   for (int chunked = 0; chunked < 2; ++chunked) {
@@ -369,6 +379,8 @@ bool make_il(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
       if (chunked && A.Cho <= 8) continue;
       const int NPH = ((T.TH + 8) | 1) * (T.TW + 8), NPL = ((T.TH / 2 + 4) | 1) * (T.TW / 2 + 8);
       if (csnet::il_smem_bytes(T, NPH, NPL) > 227 * 1024) continue;
+      // stem form: the fp32 image tile is staged in the T2 buffers before they are needed
+      if (A.first && (size_t)Xh.C * (T.TH + 12) * (T.TW + 24) * 4 > ((size_t)T.t2h * NPH + (size_t)A.Clo * NPL) * 2) continue;
       const int ty = (A.H + T.TH - 1) / T.TH, tx = (A.W + T.TW - 1) / T.TW;
       const double cost = (double)ty * tx * NPH * (chunked ? 1.15 : 1.0);   // halo work, small penalty for the extra barriers
       if (best < 0 || cost < best) { best = cost; T.tiles_x = tx; *out = T; }
