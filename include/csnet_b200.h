@@ -89,7 +89,7 @@ enum {
   CSNET_OP_GN = 4,        /* dst = prelu(GroupNorm(src)): per-image statistics over (C/groups, H, W), eps 1e-5 — the CSF+Res2Net
                              head (CSF+Res2Net/networks/gOctConv.py:133, csf_res2net.py:220).  paths[0].src = input,
                              paths[0].up = groups, ext_off[0] / ext_off[1] = gamma / beta, slope_off = PReLU slope. */
-  CSNET_OP_ILBLOCK = 3    /* whole ILBlock of the 1x1 kind in one kernel (ILBlock.forward, csnet.py:72-76):
+  CSNET_OP_ILBLOCK = 3,   /* whole ILBlock of the 1x1 kind in one kernel (ILBlock.forward, csnet.py:72-76):
                              paths[0].src / paths[1].src = high / low resolution inputs (cin = channels),
                              dst / dst2 = high / low resolution outputs (dst2 = -1 for a 2->1 block);
                              16-bit activations only.  ext_off[] (blob offsets, floats):
@@ -103,6 +103,11 @@ enum {
                              the fp32 input image (cin <= 3) with ksize = 3, pad = 1, paths[1].pool = 2; both branches are
                              3x3 convs of it (lo: of its 2x2 max-pool).  WH / WL are then [ru16(C)][32] with column
                              k = ci*9 + ky*3 + kx; the kernel builds the im2col planes in shared memory. */
+  CSNET_OP_MIXPROJ = 5     /* a MIX op whose Cmid-channel result is never stored: a 1x1 projection to the single dst channel
+                             runs in the epilogue, dst = proj_b + sum_c proj_w[c] * prelu(mix[c] + bias[c])  (CSNet.forward,
+                             csnet.py:383-384: fuse1x1 -> cls_layer).  paths / bias_off / slope_off describe the Cmid-channel
+                             MIX; ext_off[0] = proj_w offset (Cmid floats), ext_off[1] = proj_b offset or -1,
+                             ext_off[2] = Cmid (<= 80).  Tensor-core kernel only: 16-bit sources, stride-1 conv paths. */
 };
 
 /*

@@ -335,6 +335,30 @@ class _Lowering:
                     self.b.prog.taps[f"{prefix}{name}/{b_}"] = t
         return out
 
+    def project_cls(self, feat: int, low: int, cls_w: np.ndarray) -> bool:
+        """cls_layer (a 1x1 conv to one channel, csnet.py:383) folded into the epilogue of the op that produces its
+        input: that op becomes a CSNET_OP_MIXPROJ and the feature tensor is never written.  16-bit tensor-core
+        programs only; `fuse` / `tensor_core` name sets gate it like the other fused kernels ("cls_layer")."""
+        ops = self.b.prog.ops
+        prod = next((o for o in reversed(ops) if o.dst == feat), None)
+        C_ = self.dims(feat)[0]
+        want = self.fuse is True or (self.fuse and "cls_layer" in self.fuse)
+        if not want or self.dt == ir.F32 or prod is None or prod.kind != ir.OP_MIX or cls_w.shape[0] != 1 or C_ > 80:
+            return False
+        if not (self.tensor_core is True or (self.tensor_core and any(prod.name.startswith(x) for x in self.tensor_core))):
+            return False
+        if any(feat in (q.src for q in o.paths) for o in ops):
+            return False                                   # somebody else reads the feature tensor
+        lim = 6.0e4 if self.dt == ir.F16 else 3.0e38
+        conv = [q for q in prod.paths if q.ksize > 0]
+        if not conv or any(q.stride != 1 or self._wmax.get(q.w_off, 0.0) >= lim for q in conv):
+            return False
+        prod.kind, prod.dst, prod.name = ir.OP_MIXPROJ, low, prod.name + "+cls_layer"
+        prod.ext_off = [self.b.param(cls_w.reshape(-1)), self.b.param(self.p("cls_layer.bias")), C_]
+        for key in [k for k, t in self.b.prog.taps.items() if t == feat]:
+            del self.b.prog.taps[key]                      # the tapped tensor no longer exists
+        return True
+
     def run(self, reuse: bool) -> ir.Program:
         """CSNet.forward (csnet.py:365-387)."""
         b = self.b
@@ -352,8 +376,9 @@ class _Lowering:
         C_, Hf, Wf = self.dims(fuse[0])
         cls_w = self.p("cls_layer.weight")
         low = b.tensor(cls_w.shape[0], Hf, Wf, ir.F32, name="cls/low")
-        b.op(ir.OP_MIX, low, [ir.Path(fuse[0], C_, cls_w.shape[0], ksize=1, w_off=self.conv_w(cls_w))],
-             bias=self.p("cls_layer.bias"), name="cls_layer")
+        if not self.project_cls(fuse[0], low, cls_w):
+            b.op(ir.OP_MIX, low, [ir.Path(fuse[0], C_, cls_w.shape[0], ksize=1, w_off=self.conv_w(cls_w))],
+                 bias=self.p("cls_layer.bias"), name="cls_layer")
         if self.H % Hf or self.W % Wf or self.H // Hf != self.W // Wf:
             raise ValueError("final resample factor is not an integer")
         out = b.tensor(cls_w.shape[0], self.H, self.W, ir.F32, external=1, name="logits")

@@ -64,4 +64,21 @@ __global__ void __launch_bounds__(kDwfThreads) dw_fast_kernel(const __grid_const
   }
 }
 
+// A MIX op that is a single resample path (F.interpolate(bilinear, align_corners=False), the final x2 of CSNet.forward,
+// csnet.py:385-386, or the x4 of CSF+Res2Net): one thread per output pixel of one plane, the same bilinear_up() arithmetic
+// as the generic kernel without its path / channel-tile loops.
+__global__ void __launch_bounds__(256) resample_fast_kernel(const __grid_constant__ MixArgs A) {
+  const int64_t hw = (int64_t)A.H * A.W;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= hw) return;
+  const MixPath& P = A.p[0];
+  const int co = blockIdx.y, n = blockIdx.z;
+  const int oy = (int)(i / A.W), ox = (int)(i - (int64_t)oy * A.W);
+  const int64_t plane = ((int64_t)n * P.C + P.c0 + co) * (int64_t)P.H * P.W;
+  float y = bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
+  if (A.bias) y += __ldg(A.bias + co);
+  if (A.slope) y = prelu(y, __ldg(A.slope + co));
+  st_elem(A.dst, A.dtype, ((int64_t)n * A.C + co) * hw + i, y);
+}
+
 }  // namespace csnet

@@ -47,6 +47,8 @@ struct MixArgs {
   const float* slope;         // nullptr: none
   int32_t dtype, C, H, W;
   int32_t n_paths;
+  const float* proj_w;        // CSNET_OP_MIXPROJ: [C] projection weights (the C-channel result is not stored); else nullptr
+  const float* proj_b;        // projection bias (one float) or nullptr
   MixPath p[kMaxPaths];
 };
 

@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
     if (A.p[p].ksize == 0) rmask |= 1u << p;
   const int64_t out_plane = (int64_t)A.H * A.W;
   const bool pair_store = A.dtype != DT_F32 && (A.W & 1) == 0;
+  const bool proj = A.proj_w != nullptr;                    // CSNET_OP_MIXPROJ: dot the channels with proj_w instead of storing
+  float ps[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -266,6 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
       const float bias = A.bias ? __ldg(A.bias + m) : 0.f;
       const bool has_slope = A.slope != nullptr;
       const float slope = has_slope ? __ldg(A.slope + m) : 1.f;
+      const float pw = proj ? __ldg(A.proj_w + m) : 0.f;
       const int64_t orow = ((int64_t)n * A.C + m) * out_plane + (int64_t)oy * A.W;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -284,12 +287,32 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
           }
         }
         if (has_slope) { v0 = prelu(v0, slope); v1 = prelu(v1, slope); }
-        if (pair_store) {
+        if (proj) {
+          ps[j][0] = fmaf(pw, v0, ps[j][0]);
+          ps[j][1] = fmaf(pw, v1, ps[j][1]);
+        } else if (pair_store) {
           *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(A.dst) + orow + ox) = Pack<T>::from_f2(v0, v1);
         } else {
           st_elem(A.dst, A.dtype, orow + ox, v0);
           if (ox + 1 < A.W) st_elem(A.dst, A.dtype, orow + ox + 1, v1);
         }
+      }
+    }
+  }
+  if (proj) {
+    // the channel rows of a pixel live in the 8 lanes that share t (lane = 4 g + t): butterfly over g, lane g == 0 stores
+    const float pb = A.proj_b ? __ldg(A.proj_b) : 0.f;
+    const int64_t orow = (int64_t)n * out_plane + (int64_t)oy * A.W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float v = ps[j][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        const int ox = ox0 + j * 8 + 2 * t + e;
+        if (g == 0 && ox < A.W) st_elem(A.dst, A.dtype, orow + ox, v + pb);
       }
     }
   }

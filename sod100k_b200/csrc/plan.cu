@@ -169,6 +169,11 @@ struct csnet_plan {
 
 namespace {
 
+// Channels of a MIX-kind op's result: the destination's, or ext_off[2] when a projection consumes it in the epilogue.
+static inline int mix_channels(const csnet_plan& P, const csnet_op_desc& op) {
+  return op.kind == CSNET_OP_MIXPROJ ? (int)op.ext_off[2] : P.tensors[op.dst].C;
+}
+
 int validate(const csnet_plan& P) {
   const int nt = (int)P.tensors.size();
   char buf[256];
@@ -189,7 +194,8 @@ int validate(const csnet_plan& P) {
       snprintf(buf, sizeof buf, "op %zu: %s", i, why);
       return fail(CSNET_E_INVALID, buf);
     };
-    if (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_DW && op.kind != CSNET_OP_ILBLOCK && op.kind != CSNET_OP_GN)
+    if (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_DW && op.kind != CSNET_OP_ILBLOCK && op.kind != CSNET_OP_GN &&
+        op.kind != CSNET_OP_MIXPROJ)
       return bad("unknown kind");
     if (op.dst < 0 || op.dst >= nt) return bad("dst out of range");
     if (op.kind == CSNET_OP_GN) {
@@ -239,8 +245,14 @@ int validate(const csnet_plan& P) {
     }
     if (op.n_paths < 1 || op.n_paths > CSNET_MAX_PATHS) return bad("n_paths out of range");
     const csnet_tensor_desc& D = P.tensors[op.dst];
-    if (op.bias_off >= 0 && op.bias_off + D.C > P.blob_floats) return bad("bias outside blob");
-    if (op.slope_off >= 0 && op.slope_off + D.C > P.blob_floats) return bad("slope outside blob");
+    const int Cm = mix_channels(P, op);               // channels of the MIX result (== D.C unless projected away)
+    if (op.kind == CSNET_OP_MIXPROJ) {
+      if (D.C != 1 || Cm < 1 || Cm > 80) return bad("MIXPROJ projects 1..80 channels onto one");
+      if (op.ext_off[0] < 0 || op.ext_off[0] + Cm > P.blob_floats) return bad("projection weights outside blob");
+      if (op.ext_off[1] >= P.blob_floats) return bad("projection bias outside blob");
+    }
+    if (op.bias_off >= 0 && op.bias_off + Cm > P.blob_floats) return bad("bias outside blob");
+    if (op.slope_off >= 0 && op.slope_off + Cm > P.blob_floats) return bad("slope outside blob");
     if (op.kind == CSNET_OP_DW && op.n_paths != 1) return bad("DW takes one path");
     for (int p = 0; p < op.n_paths; ++p) {
       const csnet_path_desc& q = op.paths[p];
@@ -248,7 +260,7 @@ int validate(const csnet_plan& P) {
       if (q.src == op.dst) return bad("in-place op");
       const csnet_tensor_desc& S = P.tensors[q.src];
       if (q.c0 < 0 || q.cin <= 0 || q.c0 + q.cin > S.C) return bad("path input channel slice");
-      if (q.cout0 < 0 || q.cout <= 0 || q.cout0 + q.cout > D.C) return bad("path output channel slice");
+      if (q.cout0 < 0 || q.cout <= 0 || q.cout0 + q.cout > Cm) return bad("path output channel slice");
       if (op.kind == CSNET_OP_DW) {
         if (q.ksize != 3 || q.dil != 1 || q.pad != 1 || q.stride != 1 || q.pre_avg || q.pool != 1 || q.up != 1)
           return bad("DW must be 3x3 pad 1");
@@ -287,8 +299,12 @@ csnet::MixArgs make_mix(const csnet_plan& P, const csnet_op_desc& op, int N, con
   A.dst = P.tensor_ptr(op.dst, N, ext);
   A.bias = op.bias_off >= 0 ? P.blob + op.bias_off : nullptr;
   A.slope = op.slope_off >= 0 ? P.blob + op.slope_off : nullptr;
-  A.dtype = D.dtype; A.C = D.C; A.H = D.H; A.W = D.W;
+  A.dtype = D.dtype; A.C = mix_channels(P, op); A.H = D.H; A.W = D.W;
   A.n_paths = op.n_paths;
+  if (op.kind == CSNET_OP_MIXPROJ) {
+    A.proj_w = P.blob + op.ext_off[0];
+    A.proj_b = op.ext_off[1] >= 0 ? P.blob + op.ext_off[1] : nullptr;
+  }
   for (int p = 0; p < op.n_paths; ++p) {
     const csnet_path_desc& q = op.paths[p];
     const csnet_tensor_desc& S = P.tensors[q.src];
@@ -417,8 +433,10 @@ cudaError_t set_il_smem_t(int bytes) {
 TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
   TcChoice c;
   static const bool enabled = [] { const char* e = getenv("CSNET_TC"); return !(e && e[0] == '0'); }();
-  if (!enabled || op.kind != CSNET_OP_MIX || op.ext_off[23] == 1) return c;
+  if (op.kind == CSNET_OP_MIXPROJ) { /* no other kernel implements it */ }
+  else if (!enabled || op.kind != CSNET_OP_MIX || op.ext_off[23] == 1) return c;
   const csnet_tensor_desc& D = P.tensors[op.dst];
+  const int Cm = mix_channels(P, op);
   int dt = D.dtype != CSNET_F32 ? D.dtype : -1, pad = 0, nconv = 0, kk = 1, cin_max = 0;
   for (int p = 0; p < op.n_paths; ++p) {
     const csnet_path_desc& q = op.paths[p];
@@ -431,7 +449,7 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
     cin_max = q.cin > cin_max ? q.cin : cin_max;
   }
   if (dt < 0 || nconv == 0 || pad > csnet::kTcMaxPad) return c;
-  c.mt = D.C > 80 ? 5 : (D.C + 15) / 16;             // more than 80 output channels: 80-channel slices over grid.y
+  c.mt = Cm > 80 ? 5 : (Cm + 15) / 16;               // more than 80 output channels: 80-channel slices over grid.y
   c.dtype = dt;
   c.xs_halves = csnet::tc_plane_halves(pad);
   c.kk = kk;
@@ -527,13 +545,15 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   P->op_tc.assign(P->ops.size(), TcChoice());
   size_t tc_smem_max = 0;
   for (size_t i = 0; i < P->ops.size(); ++i) {
-    if (P->ops[i].kind != CSNET_OP_MIX) continue;
+    if (P->ops[i].kind != CSNET_OP_MIX && P->ops[i].kind != CSNET_OP_MIXPROJ) continue;
     P->op_tc[i] = choose_tc(*P, P->ops[i]);
     if (P->op_tc[i].mt > 0 && tc_smem_bytes(P->op_tc[i]) <= 200 * 1024) {
       P->op_smem[i] = tc_smem_bytes(P->op_tc[i]);
       tc_smem_max = P->op_smem[i] > tc_smem_max ? P->op_smem[i] : tc_smem_max;
       continue;
     }
+    if (P->ops[i].kind == CSNET_OP_MIXPROJ)
+      return cleanup(CSNET_E_UNSUPPORTED, "MIXPROJ op does not qualify for the tensor-core kernel (16-bit sources, stride 1, pad <= limit)");
     P->op_tc[i] = TcChoice();
     P->op_smem[i] = 0;                                   // the generic kernel stages weights in static shared memory
   }
@@ -542,7 +562,7 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     const TcChoice& tc = P->op_tc[i];
     if (tc.mt <= 0) continue;
     const csnet_op_desc& op = P->ops[i];
-    const int C = P->tensors[op.dst].C, slice = tc.mt * 16, m16t = (C + slice - 1) / slice * slice, WR = tc.kc + 8;
+    const int C = mix_channels(*P, op), slice = tc.mt * 16, m16t = (C + slice - 1) / slice * slice, WR = tc.kc + 8;
     P->op_w16[i].assign(op.n_paths, nullptr);
     for (int p = 0; p < op.n_paths; ++p) {
       const csnet_path_desc& q = op.paths[p];
@@ -584,7 +604,7 @@ int csnet_plan_set_blob(csnet_plan* P, const float* host_blob, int64_t n, void* 
     const TcChoice& tc = P->op_tc[i];
     if (tc.mt <= 0) continue;
     const csnet_op_desc& op = P->ops[i];
-    const int C = P->tensors[op.dst].C, slice = tc.mt * 16, m16t = (C + slice - 1) / slice * slice, WR = tc.kc + 8;
+    const int C = mix_channels(*P, op), slice = tc.mt * 16, m16t = (C + slice - 1) / slice * slice, WR = tc.kc + 8;
     for (int p = 0; p < op.n_paths; ++p) {
       const csnet_path_desc& q = op.paths[p];
       if (q.ksize == 0) continue;
@@ -620,15 +640,20 @@ static int check_run_args(csnet_plan* P, int32_t N, const void* const* ext_ptrs,
 static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_ptrs, cudaStream_t stream) {
   const csnet_op_desc& op = P->ops[i];
   const csnet_tensor_desc& D = P->tensors[op.dst];
-  if (op.kind == CSNET_OP_MIX && P->op_tc[i].mt > 0) {
+  if ((op.kind == CSNET_OP_MIX || op.kind == CSNET_OP_MIXPROJ) && P->op_tc[i].mt > 0) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     const TcChoice& tc = P->op_tc[i];
+    const int Cm = A.C;
     csnet::TcGeom G{};
     G.tiles_x = (D.W + csnet::kTcTW - 1) / csnet::kTcTW; G.xs_halves = tc.xs_halves; G.kc = tc.kc;
-    G.m16_total = (D.C + tc.mt * 16 - 1) / (tc.mt * 16) * (tc.mt * 16);
+    G.m16_total = (Cm + tc.mt * 16 - 1) / (tc.mt * 16) * (tc.mt * 16);
     for (int p = 0; p < op.n_paths; ++p) G.w16[p] = P->op_w16[i][p];
-    dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), (D.C + tc.mt * 16 - 1) / (tc.mt * 16), N);
+    dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), (Cm + tc.mt * 16 - 1) / (tc.mt * 16), N);
     launch_mix_tc(tc, grid, P->op_smem[i], stream, A, G);
+  } else if (op.kind == CSNET_OP_MIX && op.n_paths == 1 && op.paths[0].ksize == 0 && op.paths[0].cout0 == 0 &&
+             op.paths[0].cout == D.C) {
+    csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);         // a pure resample
+    csnet::resample_fast_kernel<<<dim3((D.H * D.W + 255) / 256, D.C, N), 256, 0, stream>>>(A);
   } else if (op.kind == CSNET_OP_MIX) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     dim3 grid((D.H * D.W + kThreads - 1) / kThreads, (D.C + csnet::kMixCT - 1) / csnet::kMixCT, N);

@@ -244,6 +244,11 @@ def test_tensor_core_mix_kernel_matches_generic_ops(tag, hw, dtype):
     prog = compiler.compile_csnet(cfg, sd, h, w, dtype, fuse=False, tensor_core={"cls_layer", "upsample"})
     y1 = runtime.Plan(prog, max_batch=2).forward(x)
     assert (y1 - y0).abs().max().item() <= rel * max(1.0, y0.abs().max().item())
+    # cls_layer folded into the fuse1x1 epilogue (CSNET_OP_MIXPROJ): only that op on the tensor-core kernel, logits compared
+    prog = compiler.compile_csnet(cfg, sd, h, w, dtype, fuse={"cls_layer"}, tensor_core={"oct_fuse.fuse1x1"})
+    assert sum(o.kind == 5 for o in prog.ops) == 1 and not any(o.name == "cls_layer" for o in prog.ops)
+    y2 = runtime.Plan(prog, max_batch=2).forward(x)
+    assert (y2 - y0).abs().max().item() <= rel * max(1.0, y0.abs().max().item())
     # everything on: fused ILBlocks + tensor-core MIX, against the oracle
     y = torch.sigmoid(runtime.Plan(compiler.compile_csnet(cfg, sd, h, w, dtype), max_batch=2).forward(x)).cpu()
     ref = torch.sigmoid(_oracle(cfg, sd, x.cpu().numpy()))
