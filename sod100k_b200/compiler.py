@@ -144,6 +144,20 @@ class _Lowering:
             self.b.op(ir.OP_MIX, dst, [path], bias=t, slope=self.p(prefix + ".prelus.0.weight"), name=prefix)
             return [dst]
         ci, co = splits.cuts(cin_t, a_in), splits.cuts(cout_t, a_out)
+        if stride == 2 and self.dt != ir.F32 and (self.fuse is True or (self.fuse and prefix in self.fuse)):
+            # gOctaveConv's stride 2 is avg_pool2d(2, 2) of every input branch followed by a stride-1 conv (:679-680).
+            # 16-bit programs materialise the pooled branches once (one bandwidth-bound pass) instead of averaging in the
+            # staging loop of each of the 2-3 conv ops that read them; the stored value is the one they would stage.
+            pooled: List[Optional[int]] = []
+            for i, x in enumerate(xs):
+                if x is None or ci[i] == ci[i + 1]:
+                    pooled.append(x)
+                    continue
+                C_, H_, W_ = self.dims(x)
+                t = self.b.tensor(C_, H_ // 2, W_ // 2, self.dt, name=f"{prefix}/pool{i}")
+                self.b.op(ir.OP_MIX, t, [ir.Path(x, C_, C_, ksize=0, pre_avg=1)], name=f"{prefix}.pool{i}")
+                pooled.append(t)
+            xs, stride = pooled, 1
         base = None                                                   # resolution of branch 0 after the stride-2 pool
         for i, x in enumerate(xs):
             if x is not None:

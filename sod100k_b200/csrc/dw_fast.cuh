@@ -75,10 +75,35 @@ __global__ void __launch_bounds__(256) resample_fast_kernel(const __grid_constan
   const int co = blockIdx.y, n = blockIdx.z;
   const int oy = (int)(i / A.W), ox = (int)(i - (int64_t)oy * A.W);
   const int64_t plane = ((int64_t)n * P.C + P.c0 + co) * (int64_t)P.H * P.W;
-  float y = bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
+  float y = (P.pre_avg || P.pool > 1) ? fetch_pooled(P, plane, oy, ox) : bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
   if (A.bias) y += __ldg(A.bias + co);
   if (A.slope) y = prelu(y, __ldg(A.slope + co));
   st_elem(A.dst, A.dtype, ((int64_t)n * A.C + co) * hw + i, y);
+}
+
+// avg_pool2d(2, 2) of a 16-bit tensor (the stride-2 entry of gOctaveConv, csnet.py:679-680, materialised once for all the
+// conv paths that consume it): 4 output pixels per thread from two 16-byte loads; the same (((a + b) + c) + d) / 4 order
+// as fetch_pooled(), so the stored value equals what the MIX kernels would stage.  A.W % 4 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool2_fast_kernel(const __grid_constant__ MixArgs A) {
+  const int G = A.W >> 2;
+  const int task = blockIdx.x * 256 + threadIdx.x;
+  if (task >= G * A.H) return;
+  const int oy = task / G, x = 4 * (task - oy * G), c = blockIdx.y, n = blockIdx.z;
+  const MixPath& P = A.p[0];
+  const uint16_t* src = reinterpret_cast<const uint16_t*>(P.src) + ((size_t)n * P.C + c) * (size_t)P.H * P.W + (size_t)(2 * oy) * P.W + 2 * x;
+  const uint4 r0 = *reinterpret_cast<const uint4*>(src), r1 = *reinterpret_cast<const uint4*>(src + P.W);
+  const uint32_t a[4] = {r0.x, r0.y, r0.z, r0.w}, b[4] = {r1.x, r1.y, r1.z, r1.w};
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 u = Pack<T>::to_f2(a[k]), v = Pack<T>::to_f2(b[k]);
+    o[k] = (((u.x + u.y) + v.x) + v.y) * 0.25f;
+  }
+  uint2 out;
+  out.x = Pack<T>::from_f2(o[0], o[1]);
+  out.y = Pack<T>::from_f2(o[2], o[3]);
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(A.dst) + ((size_t)n * A.C + c) * (size_t)A.H * A.W + (size_t)oy * A.W + x) = out;
 }
 
 }  // namespace csnet

@@ -185,7 +185,8 @@ CSNET_DEV void mix_finish(const MixArgs& A, int n, int oy, int ox, int co_base, 
       const int co = co_base + t;
       if (co >= P.cout0 && co < P.cout0 + P.cout) {
         const int64_t plane = ((int64_t)n * P.C + P.c0 + (co - P.cout0)) * plane_sz;
-        acc[t] += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
+        // a resample path adds the source up-sampled (up > 1), or down-sampled by pre_avg / pool (up == 1), or as it is
+        acc[t] += (P.pre_avg || P.pool > 1) ? fetch_pooled(P, plane, oy, ox) : bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
       }
     }
   }

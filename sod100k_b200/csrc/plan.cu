@@ -270,8 +270,12 @@ int validate(const csnet_plan& P) {
         continue;
       }
       if (q.ksize == 0) {
-        if (q.up < 1 || q.cin != q.cout) return bad("resample path");
-        if (S.H * q.up != D.H || S.W * q.up != D.W) return bad("resample path size");
+        if (q.up < 1 || q.cin != q.cout || q.pool < 1) return bad("resample path");
+        if (q.pre_avg != 0 && q.pre_avg != 1 && q.pre_avg != 2 && q.pre_avg != 4 && q.pre_avg != 8) return bad("pre_avg must be 0, 1, 2, 4 or 8");
+        const int div = csnet::pre_factor(q.pre_avg) * q.pool;
+        if (div > 1 && q.up != 1) return bad("a resample path either up-samples or down-samples");
+        if (S.H % div || S.W % div) return bad("pooling does not divide the source");
+        if (S.H / div * q.up != D.H || S.W / div * q.up != D.W) return bad("resample path size");
       } else {
         if (q.ksize != 1 && q.ksize != 3) return bad("ksize must be 1 or 3");
         if (q.up < 1) return bad("conv path up < 1");
@@ -440,6 +444,7 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
   int dt = D.dtype != CSNET_F32 ? D.dtype : -1, pad = 0, nconv = 0, kk = 1, cin_max = 0;
   for (int p = 0; p < op.n_paths; ++p) {
     const csnet_path_desc& q = op.paths[p];
+    if (q.ksize == 0 && (q.pre_avg || q.pool > 1)) return c;     // down-sampling resample paths: generic kernels only
     if (q.ksize == 0) continue;
     ++nconv;
     if (q.stride != 1) return c;
@@ -653,7 +658,16 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
   } else if (op.kind == CSNET_OP_MIX && op.n_paths == 1 && op.paths[0].ksize == 0 && op.paths[0].cout0 == 0 &&
              op.paths[0].cout == D.C) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);         // a pure resample
-    csnet::resample_fast_kernel<<<dim3((D.H * D.W + 255) / 256, D.C, N), 256, 0, stream>>>(A);
+    const csnet_path_desc& q = op.paths[0];
+    const csnet_tensor_desc& S = P->tensors[q.src];
+    if (q.pre_avg == 1 && q.pool == 1 && q.up == 1 && q.c0 == 0 && S.dtype == D.dtype && D.dtype != CSNET_F32 && D.W % 4 == 0 &&
+        op.bias_off < 0 && op.slope_off < 0) {
+      const dim3 grid((D.H * (D.W / 4) + 255) / 256, D.C, N);    // avg_pool2d(2, 2) of a 16-bit tensor
+      if (D.dtype == CSNET_F16) csnet::avgpool2_fast_kernel<__half><<<grid, 256, 0, stream>>>(A);
+      else csnet::avgpool2_fast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(A);
+    } else {
+      csnet::resample_fast_kernel<<<dim3((D.H * D.W + 255) / 256, D.C, N), 256, 0, stream>>>(A);
+    }
   } else if (op.kind == CSNET_OP_MIX) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     dim3 grid((D.H * D.W + kThreads - 1) / kThreads, (D.C + csnet::kMixCT - 1) / csnet::kMixCT, N);

@@ -253,3 +253,30 @@ def test_tensor_core_mix_kernel_matches_generic_ops(tag, hw, dtype):
     y = torch.sigmoid(runtime.Plan(compiler.compile_csnet(cfg, sd, h, w, dtype), max_batch=2).forward(x)).cpu()
     ref = torch.sigmoid(_oracle(cfg, sd, x.cpu().numpy()))
     assert (y - ref).abs().max().item() <= (SIG_TOL_FP16 if dtype == "fp16" else SIG_TOL_BF16)
+
+
+@pytest.mark.parametrize("tag,hw,dtype", [("csnet-L-x2", (224, 224), "fp16"), ("csnet-L-x1", (96, 160), "bf16")])
+def test_materialised_avgpool_of_stride2_entry_blocks(tag, hw, dtype):
+    """16-bit programs store avg_pool2d(2,2) of the inputs of a stride-2 gOctaveCBR once (avgpool2_fast_kernel) instead
+    of averaging inside every consumer's staging loop.  One entry block at a time against the on-the-fly form, generic
+    conv kernels on both sides: the only difference is the 16-bit rounding of the stored averages."""
+    cfg, sd = fixtures.checkpoint(tag)
+    h, w = hw
+    x = torch.from_numpy(synth.randn_images(2, h, w, 53)).cuda()
+    base = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse=False, tensor_core=False)
+    p0 = runtime.Plan(base, max_batch=2)
+    p0.forward(x)
+    rel = 4e-3 if dtype == "fp16" else 3e-2
+    for blk in ("stage2.0", "stage3.0", "stage4.0"):
+        prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse={blk + ".conv1x1"}, tensor_core=False)
+        assert sum(".pool" in o.name for o in prog.ops) >= 1
+        p1 = runtime.Plan(prog, max_batch=2)
+        p1.forward(x)
+        for b in (0, 1):
+            key = f"{blk}/{b}"
+            if key not in prog.taps:
+                continue
+            ref, got = p0.read_tensor(base.taps[key], 2), p1.read_tensor(prog.taps[key], 2)
+            err = (got - ref).abs().max().item()
+            assert err <= rel * max(1.0, ref.abs().max().item()), (key, err, ref.abs().max().item())
+        p1.close()
