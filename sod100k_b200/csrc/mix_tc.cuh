@@ -179,8 +179,35 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
           }
         }
         cp_async_wait_all();
+      } else if (up16 && XH * XW <= kTcThreads) {
+        // ---- (b) input-side bilinear up-sampling of a 16-bit source (1x1 paths, pad 0): one staged pixel per thread, its
+        //      four source offsets and weights computed once, then a channel loop of 4 loads + the bilinear_up16() blend ----
+        const int y = tid / XW, x = tid - y * XW;
+        const int cy = oy0 - pad + y, cx = ox0 - padL + x;
+        const bool ok = tid < XH * XW && cy >= 0 && cy < Hc && cx >= 0 && cx < Wc;
+        const float inv = 1.0f / (float)P0.up;
+        float sy = ((float)cy + 0.5f) * inv - 0.5f, sx = ((float)cx + 0.5f) * inv - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int sy0 = ok ? (int)sy : 0, sx0 = ok ? (int)sx : 0;
+        const int sy1 = sy0 + (sy0 < P0.H - 1 ? 1 : 0), sx1 = sx0 + (sx0 < P0.W - 1 ? 1 : 0);
+        const float ly = sy - (float)sy0, lx = sx - (float)sx0, hy = 1.f - ly, hx = 1.f - lx;
+        const int o00 = sy0 * srcW + sx0, o01 = sy0 * srcW + sx1, o10 = sy1 * srcW + sx0, o11 = sy1 * srcW + sx1;
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(P0.src) + src_base + (int64_t)c0 * plane_sz;
+        uint16_t* dp = Xs + y * XW + x;
+        if (tid < XH * XW) {
+#pragma unroll 4
+          for (int ch = 0; ch < kc8; ++ch) {
+            float v = 0.f;
+            if (ok && ch < kc_live) {
+              const uint16_t* pl = sp + (int64_t)ch * plane_sz;
+              v = hy * (hx * Pack<T>::to_f(pl[o00]) + lx * Pack<T>::to_f(pl[o01])) + ly * (hx * Pack<T>::to_f(pl[o10]) + lx * Pack<T>::to_f(pl[o11]));
+            }
+            dp[ch * PS] = (uint16_t)(Pack<T>::from_f2(v, 0.f) & 0xffffu);
+          }
+        }
       } else {
-        // ---- (b)/(c) scalar copy or computed (pool / avg / up-sample / fp32 source): 4 rows in flight per step ----
+        // ---- (c) scalar copy or computed (pool / avg / up-sample / fp32 source): 4 rows in flight per step ----
         for (int ch = warp; ch < kc8; ch += kTcWarps) {
           const bool ch_ok = ch < kc_live;
           const int64_t plane = src_base + (int64_t)(c0 + ch) * plane_sz;
@@ -223,24 +250,34 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
         __syncthreads();
         // ---- tensor-core accumulate --------------------------------------------------------------------
         const int off = pad - P.pad, offx = padL - P.pad;   // this path's window sits inside the staged one
+        // One tap of one k-step: A fragments of every m tile, then per n tile a B register assembled from the two channel
+        // planes of this lane's k pair (one PRMT) and MT mma.  All addresses advance by increments (no multiplies in the loop).
+        auto tap = [&](const uint16_t* ra, const uint16_t* rb, const uint16_t* wt) {
+          uint32_t af[MT][2];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            af[mt][0] = *reinterpret_cast<const uint32_t*>(wt + mt * 16 * WR);
+            af[mt][1] = *reinterpret_cast<const uint32_t*>(wt + (mt * 16 + 8) * WR);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t b = __byte_perm((uint32_t)ra[j * 8], (uint32_t)rb[j * 8], 0x5410);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) Pack<T>::mma(acc[mt][j], af[mt], b);
+          }
+        };
+        const int rstep = dil * XW, wstep = M16 * WR;
         for (int ks = 0; ks < kc8; ks += 8) {
-          const uint16_t* x0 = Xs + (ks + 2 * t) * PS + (warp + off) * XW + g + offx;
-          for (int ky = 0; ky < ksz; ++ky) {
-            for (int kx = 0; kx < ksz; ++kx) {
-              const uint16_t* wt = Ws + ((ky * ksz + kx) * M16 + g) * WR + ks + 2 * t;
-              uint32_t af[MT][2];
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                af[mt][0] = *reinterpret_cast<const uint32_t*>(wt + mt * 16 * WR);
-                af[mt][1] = *reinterpret_cast<const uint32_t*>(wt + (mt * 16 + 8) * WR);
-              }
-              const uint16_t* xt = x0 + (ky * dil) * XW + kx * dil;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t b = (uint32_t)xt[j * 8] | ((uint32_t)xt[PS + j * 8] << 16);
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) Pack<T>::mma(acc[mt][j], af[mt], b);
-              }
+          const uint16_t* xa = Xs + (ks + 2 * t) * PS + (warp + off) * XW + g + offx;   // channel ks + 2t; + PS: ks + 2t + 1
+          const uint16_t* wt = Ws + g * WR + ks + 2 * t;
+          if (ksz == 1) {
+            tap(xa, xa + PS, wt);
+          } else {
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ++ky, xa += rstep) {
+              const uint16_t* ra = xa;
+#pragma unroll(MT <= 1 ? 3 : 1)
+              for (int kx = 0; kx < 3; ++kx, ra += dil, wt += wstep) tap(ra, ra + PS, wt);
             }
           }
         }
