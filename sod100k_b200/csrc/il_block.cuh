@@ -254,14 +254,14 @@ __device__ __forceinline__ void dw_task(int task, const uint16_t* in, uint16_t* 
 }
 
 // hi and lo plane sets share one task index space so the 512 threads stay evenly loaded
-template <typename T, bool kToGlobal, int RUN, typename GH, typename GL>
+template <typename T, bool kToGlobal, int RUN, typename GH, typename GL, int NT>
 __device__ __forceinline__ void dw_pass(const uint16_t* inH, uint16_t* outH, const DwParams& PH, int Ch, int hy, int hx, int H,
                                         int W, const uint16_t* inL, uint16_t* outL, const DwParams& PL, int Cl, int ly, int lx,
                                         int tid) {
   constexpr int perH = ((GH::R1 - GH::R0 + RUN - 1) / RUN) * (GH::G1 - GH::G0);
   constexpr int perL = ((GL::R1 - GL::R0 + RUN - 1) / RUN) * (GL::G1 - GL::G0);
   const int nA = Ch * perH, nB = Cl * perL;
-  for (int task = tid; task < nA + nB; task += kIlThreads) {
+  for (int task = tid; task < nA + nB; task += NT) {
     if (task < nA) dw_task<T, kToGlobal, RUN, GH>(task, inH, outH, PH, hy, hx, H, W);
     else dw_task<T, kToGlobal, RUN, GL>(task - nA, inL, outL, PL, ly, lx, H >> 1, W >> 1);
   }
@@ -273,12 +273,13 @@ inline size_t il_smem_bytes(const IlArgs& A, int NPH, int NPL) {
   return halves * 2 + 128 /*base alignment*/ + 128 /*mbarrier + front guard*/ + 128 /*bufAh size round-up*/ + 128 /*tail guard*/;
 }
 
-template <typename T, int TH, int TW>
-__global__ void __launch_bounds__(kIlThreads, 1)
+// NT threads per CTA (512, one CTA per SM; 256 x 2 CTAs, 768 and 1024 were measured and are no faster, profiles/r01_f).
+template <typename T, int TH, int TW, int NT = kIlThreads>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1)
 il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL) {
   using GEO = IlGeom<TH, TW>;
   extern __shared__ uint8_t smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kIlThreads >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
   const int n = blockIdx.z;
   const int tile_y = blockIdx.x / A.tiles_x, tile_x = blockIdx.x % A.tiles_x;
   const int hy0 = tile_y * TH, hx0 = tile_x * TW, ly0 = hy0 >> 1, lx0 = hx0 >> 1;
@@ -316,21 +317,21 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     if (A.tma_l) tma_load_4d(bufAl, &tmL, mbar, lx0 - 4, ly0 - 2, 0, n);
   }
   // weights (tiny, L2-resident) and the zero K-padding rows, while the bulk copies fly
-  for (int i = tid; i < (A.MH16 * A.K8) >> 1; i += kIlThreads) reinterpret_cast<uint32_t*>(wsH)[i] = __ldg(A.wh + i);
+  for (int i = tid; i < (A.MH16 * A.K8) >> 1; i += NT) reinterpret_cast<uint32_t*>(wsH)[i] = __ldg(A.wh + i);
   if (Clo > 0)
-    for (int i = tid; i < (A.ML16 * A.K8) >> 1; i += kIlThreads) reinterpret_cast<uint32_t*>(wsL)[i] = __ldg(A.wl + i);
+    for (int i = tid; i < (A.ML16 * A.K8) >> 1; i += NT) reinterpret_cast<uint32_t*>(wsL)[i] = __ldg(A.wl + i);
   {
     const int z0 = (Chi + Cli) * (NPH >> 1), z1 = A.rowsAh * (NPH >> 1);
-    for (int i = z0 + tid; i < z1; i += kIlThreads) reinterpret_cast<uint32_t*>(bufAh)[i] = 0u;
+    for (int i = z0 + tid; i < z1; i += NT) reinterpret_cast<uint32_t*>(bufAh)[i] = 0u;
     const int kl = Clo > 0 ? (Chi + Cli) : Cli;
     const int y0 = kl * (NPL >> 1), y1 = A.rowsAl * (NPL >> 1);
-    for (int i = y0 + tid; i < y1; i += kIlThreads) reinterpret_cast<uint32_t*>(bufAl)[i] = 0u;
+    for (int i = y0 + tid; i < y1; i += NT) reinterpret_cast<uint32_t*>(bufAl)[i] = 0u;
   }
   // cp.async fallback loaders (8-byte chunks, zero fill outside the image)
   if (!A.tma_h && !A.first) {
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(A.xh) + (size_t)n * Chi * H * W;
     constexpr int quads_row = RWh >> 2, quads_plane = NPH >> 2;
-    for (int i = tid; i < Chi * quads_plane; i += kIlThreads) {
+    for (int i = tid; i < Chi * quads_plane; i += NT) {
       const int c = i / quads_plane, pq = i - c * quads_plane;
       const int ry = pq / quads_row, rx = (pq - ry * quads_row) * 4;
       const int gy = hy0 - 4 + ry, gx = hx0 - 4 + rx;
@@ -341,7 +342,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   if (!A.tma_l && !A.first) {
     const uint16_t* xl = reinterpret_cast<const uint16_t*>(A.xl) + (size_t)n * Cli * Hl * Wl;
     constexpr int quads_row = RWl >> 2, quads_plane = NPL >> 2;
-    for (int i = tid; i < Cli * quads_plane; i += kIlThreads) {
+    for (int i = tid; i < Cli * quads_plane; i += NT) {
       const int c = i / quads_plane, pq = i - c * quads_plane;
       const int ry = pq / quads_row, rx = (pq - ry * quads_row) * 4;
       const int gy = ly0 - 2 + ry, gx = lx0 - 4 + rx;
@@ -366,7 +367,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     const int Ci = Chi / 9;
     float* img = reinterpret_cast<float*>(bufBh);
     const float* x = reinterpret_cast<const float*>(A.xh) + (size_t)n * Ci * H * W;
-    for (int i = tid; i < Ci * IH * (IW / 4); i += kIlThreads) {
+    for (int i = tid; i < Ci * IH * (IW / 4); i += NT) {
       const int c = i / (IH * (IW / 4)), r = i - c * (IH * (IW / 4));
       const int iy = r / (IW / 4), ix = (r - iy * (IW / 4)) * 4;
       const int gy = hy0 - 6 + iy, gx = hx0 - 12 + ix;          // gx % 4 == 0 and W % 4 == 0: a quad is all in or all out
@@ -376,7 +377,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     }
     __syncthreads();
     // hi planes: row k = (ci, ky, kx) holds the image shifted by (ky-1, kx-1); region (ry, rx) = image (hy0-4+ry, hx0-4+rx)
-    for (int i = tid; i < Chi * (NPH / 2); i += kIlThreads) {
+    for (int i = tid; i < Chi * (NPH / 2); i += NT) {
       const int k = i / (NPH / 2), pp = i - k * (NPH / 2);
       const int ci = k / 9, t9 = k - ci * 9, ky = t9 / 3, kx = t9 - ky * 3;
       const int ry = (2 * pp) / RWh, rx = 2 * pp - ry * RWh;
@@ -386,7 +387,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     // lo planes: 2x2 max-pool of the image, shifted by (ky-1, kx-1) lo pixels, zero outside the lo image (conv padding)
     if (Clo > 0) {
       constexpr int rl_ = TH / 2 + 4;
-      for (int i = tid; i < Chi * NPL; i += kIlThreads) {
+      for (int i = tid; i < Chi * NPL; i += NT) {
         const int k = i / NPL, p = i - k * NPL;
         const int ci = k / 9, t9 = k - ci * 9, ky = t9 / 3, kx = t9 - ky * 3;
         const int ry = p / RWl, rx = p - ry * RWl;
@@ -406,7 +407,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   if (Clo > 0) {
     constexpr int pairs_row = RWl >> 1, pairs_plane = NPL >> 1;
     constexpr int umax = RWh >> 2;
-    for (int i = tid; i < Chi * pairs_plane; i += kIlThreads) {
+    for (int i = tid; i < Chi * pairs_plane; i += NT) {
       const int c = i / pairs_plane, pp = i - c * pairs_plane;
       const int ry = pp / pairs_row, u = pp - ry * pairs_row;
       uint32_t v = 0u;
@@ -427,7 +428,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     constexpr int quads_row = RWh >> 2;
     constexpr int row_pairs = RHh >> 1;               // hi rows (2a, 2a+1), a < RHh/2 (an odd last row stays zero-filled)
     constexpr int per_plane = row_pairs * quads_row;
-    for (int i = tid; i < Cli * per_plane; i += kIlThreads) {
+    for (int i = tid; i < Cli * per_plane; i += NT) {
       const int c = i / per_plane, rem = i - c * per_plane;
       const int a = rem / quads_row, q = rem - a * quads_row;
       // hi rows (2a, 2a+1) <-> image rows gy = hy0-4+2a (even) and gy+1; lo image row of gy/2: li = ly0-2+a
@@ -461,7 +462,7 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     // rows of the hi planes not covered above (odd last row, padded tail): zero
     constexpr int covered = (RHh >> 1) * 2 * RWh;
     constexpr int tailh = (NPH - covered) >> 1;
-    for (int i = tid; i < Cli * tailh; i += kIlThreads) {
+    for (int i = tid; i < Cli * tailh; i += NT) {
       const int c = i / tailh, k = i - c * tailh;
       reinterpret_cast<uint32_t*>(bufAh + (size_t)(Chi + c) * NPH + covered)[k] = 0u;
     }
@@ -523,9 +524,9 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   uint16_t* outL = Clo > 0 ? reinterpret_cast<uint16_t*>(A.yl) + (size_t)n * Clo * Hl * Wl : nullptr;
   if (A.t2h >= Cho) {
     // whole layers resident: dw1 (T1 -> T2, smem) then dw2 (T2 -> global)
-    dw_pass<T, false, 6, GH1, GL1>(bufAh, bufBh, A.dw1h, Cho, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l, Clo, ly0 - 2, lx0 - 4, tid);
+    dw_pass<T, false, 6, GH1, GL1, NT>(bufAh, bufBh, A.dw1h, Cho, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l, Clo, ly0 - 2, lx0 - 4, tid);
     __syncthreads();
-    dw_pass<T, true, 4, GH2, GL2>(bufBh, outH, A.dw2h, Cho, hy0 - 4, hx0 - 4, H, W, bufBl, outL, A.dw2l, Clo, ly0 - 2, lx0 - 4, tid);
+    dw_pass<T, true, 4, GH2, GL2, NT>(bufBh, outH, A.dw2h, Cho, hy0 - 4, hx0 - 4, H, W, bufBl, outL, A.dw2l, Clo, ly0 - 2, lx0 - 4, tid);
   } else {
     // wide blocks: the hi branch goes through the two layers 8 channels at a time (T2 buffer of 8 planes), the lo
     // branch rides along with the first chunk
@@ -533,10 +534,10 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
       const int cc = (Cho - c0) < A.t2h ? (Cho - c0) : A.t2h;
       const DwParams p1{A.dw1h.w + c0 * 9, A.dw1h.b + c0, A.dw1h.s + c0}, p2{A.dw2h.w + c0 * 9, A.dw2h.b + c0, A.dw2h.s + c0};
       if (c0 > 0) __syncthreads();                      // the previous chunk's dw2 finished reading the T2 buffer
-      dw_pass<T, false, 3, GH1, GL1>(bufAh + (size_t)c0 * NPH, bufBh, p1, cc, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l,
+      dw_pass<T, false, 3, GH1, GL1, NT>(bufAh + (size_t)c0 * NPH, bufBh, p1, cc, hy0 - 4, hx0 - 4, H, W, bufAl, bufBl, A.dw1l,
                                      c0 == 0 ? Clo : 0, ly0 - 2, lx0 - 4, tid);
       __syncthreads();
-      dw_pass<T, true, 2, GH2, GL2>(bufBh, outH + (size_t)c0 * H * W, p2, cc, hy0 - 4, hx0 - 4, H, W, bufBl, outL, A.dw2l,
+      dw_pass<T, true, 2, GH2, GL2, NT>(bufBh, outH + (size_t)c0 * H * W, p2, cc, hy0 - 4, hx0 - 4, H, W, bufBl, outL, A.dw2l,
                                     c0 == 0 ? Clo : 0, ly0 - 2, lx0 - 4, tid);
     }
   }
