@@ -144,7 +144,8 @@ class _Lowering:
             self.b.op(ir.OP_MIX, dst, [path], bias=t, slope=self.p(prefix + ".prelus.0.weight"), name=prefix)
             return [dst]
         ci, co = splits.cuts(cin_t, a_in), splits.cuts(cout_t, a_out)
-        if stride == 2 and self.dt != ir.F32 and (self.fuse is True or (self.fuse and prefix in self.fuse)):
+        pool_once = self.dt != ir.F32 and (self.fuse is True or bool(self.fuse and prefix in self.fuse))
+        if stride == 2 and pool_once:
             # gOctaveConv's stride 2 is avg_pool2d(2, 2) of every input branch followed by a stride-1 conv (:679-680).
             # 16-bit programs materialise the pooled branches once (one bandwidth-bound pass) instead of averaging in the
             # staging loop of each of the 2-3 conv ops that read them; the stored value is the one they would stage.
@@ -188,7 +189,9 @@ class _Lowering:
                     low = self.b.tensor(cj, Hi // stride, Wi // stride, ir.F32, name=f"{prefix}/low{i}to{j}")
                     self.b.op(ir.OP_MIX, low, [ir.Path(x, cin, cj, **common)], name=f"{prefix}.low{i}to{j}")
                     paths.append(ir.Path(low, cj, cj, ksize=0, up=2 ** (i - j)))
-                else:                                                # same res, or max-pool first (:708-717)
+                elif j > i and pool_once and not common["pre_avg"]:   # max-pool first (:708-717), materialised once per source
+                    paths.append(ir.Path(self.maxpooled(x, 2 ** (j - i), prefix), cin, cj, **common))
+                else:                                                # same res, or max-pool in the consumer's staging loop
                     paths.append(ir.Path(x, cin, cj, pool=2 ** (j - i), **common))
             if not paths:
                 outs.append(None)
@@ -197,6 +200,22 @@ class _Lowering:
             self.b.op(ir.OP_MIX, dst, paths, bias=t, slope=self.p(f"{prefix}.prelus.{j}.weight"), name=f"{prefix}.{j}")
             outs.append(dst)
         return outs
+
+    def maxpooled(self, x: int, f: int, prefix: str) -> int:
+        """max_pool2d(f, f) of a whole 16-bit tensor as its own bandwidth-bound op(s) (a chain of 2x2 steps, exact for a
+        maximum), cached per source: several conv paths (oct_fuse.fuse.1 / .2) read the same pooled branch."""
+        if not hasattr(self, "_pooled"):
+            self._pooled: Dict[tuple, int] = {}
+        if f == 1:
+            return x
+        key = (x, f)
+        if key not in self._pooled:
+            src = self.maxpooled(x, f // 2, prefix)
+            C_, H_, W_ = self.dims(src)
+            t = self.b.tensor(C_, H_ // 2, W_ // 2, self.dt, name=f"{prefix}/maxpool{f}of{x}")
+            self.b.op(ir.OP_MIX, t, [ir.Path(src, C_, C_, ksize=0, pool=2)], name=f"{prefix}.maxpool{f}of{x}")
+            self._pooled[key] = t
+        return self._pooled[key]
 
     def dw_cbr(self, prefix: str, xs: List[Optional[int]]):
         """SimplifiedGOctConvBR.forward (csnet.py:838-851)."""

@@ -81,11 +81,12 @@ __global__ void __launch_bounds__(256) resample_fast_kernel(const __grid_constan
   st_elem(A.dst, A.dtype, ((int64_t)n * A.C + co) * hw + i, y);
 }
 
-// avg_pool2d(2, 2) of a 16-bit tensor (the stride-2 entry of gOctaveConv, csnet.py:679-680, materialised once for all the
-// conv paths that consume it): 4 output pixels per thread from two 16-byte loads; the same (((a + b) + c) + d) / 4 order
-// as fetch_pooled(), so the stored value equals what the MIX kernels would stage.  A.W % 4 == 0.
+// avg_pool2d(2, 2) (the stride-2 entry of gOctaveConv, csnet.py:679-680) or max_pool2d(2, 2) (its high-to-low paths,
+// :708-717) of a 16-bit tensor, materialised once for all the conv paths that consume it: 4 output pixels per thread from
+// two 16-byte loads; the average uses the same (((a + b) + c) + d) / 4 order as fetch_pooled(), so the stored value equals
+// what the MIX kernels would stage (a maximum is exact anyway).  A.W % 4 == 0.
 template <typename T>
-__global__ void __launch_bounds__(256) avgpool2_fast_kernel(const __grid_constant__ MixArgs A) {
+__global__ void __launch_bounds__(256) pool2_fast_kernel(const __grid_constant__ MixArgs A, const bool is_max) {
   const int G = A.W >> 2;
   const int task = blockIdx.x * 256 + threadIdx.x;
   if (task >= G * A.H) return;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) avgpool2_fast_kernel(const __grid_constan
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float2 u = Pack<T>::to_f2(a[k]), v = Pack<T>::to_f2(b[k]);
-    o[k] = (((u.x + u.y) + v.x) + v.y) * 0.25f;
+    o[k] = is_max ? fmaxf(fmaxf(u.x, u.y), fmaxf(v.x, v.y)) : (((u.x + u.y) + v.x) + v.y) * 0.25f;
   }
   uint2 out;
   out.x = Pack<T>::from_f2(o[0], o[1]);

@@ -660,11 +660,12 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);         // a pure resample
     const csnet_path_desc& q = op.paths[0];
     const csnet_tensor_desc& S = P->tensors[q.src];
-    if (q.pre_avg == 1 && q.pool == 1 && q.up == 1 && q.c0 == 0 && S.dtype == D.dtype && D.dtype != CSNET_F32 && D.W % 4 == 0 &&
+    const bool avg2 = q.pre_avg == 1 && q.pool == 1, max2 = q.pre_avg == 0 && q.pool == 2;
+    if ((avg2 || max2) && q.up == 1 && q.c0 == 0 && S.dtype == D.dtype && D.dtype != CSNET_F32 && D.W % 4 == 0 &&
         op.bias_off < 0 && op.slope_off < 0) {
-      const dim3 grid((D.H * (D.W / 4) + 255) / 256, D.C, N);    // avg_pool2d(2, 2) of a 16-bit tensor
-      if (D.dtype == CSNET_F16) csnet::avgpool2_fast_kernel<__half><<<grid, 256, 0, stream>>>(A);
-      else csnet::avgpool2_fast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(A);
+      const dim3 grid((D.H * (D.W / 4) + 255) / 256, D.C, N);    // avg_pool2d(2, 2) / max_pool2d(2, 2) of a 16-bit tensor
+      if (D.dtype == CSNET_F16) csnet::pool2_fast_kernel<__half><<<grid, 256, 0, stream>>>(A, max2);
+      else csnet::pool2_fast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(A, max2);
     } else {
       csnet::resample_fast_kernel<<<dim3((D.H * D.W + 255) / 256, D.C, N), 256, 0, stream>>>(A);
     }

@@ -257,9 +257,10 @@ def test_tensor_core_mix_kernel_matches_generic_ops(tag, hw, dtype):
 
 @pytest.mark.parametrize("tag,hw,dtype", [("csnet-L-x2", (224, 224), "fp16"), ("csnet-L-x1", (96, 160), "bf16")])
 def test_materialised_avgpool_of_stride2_entry_blocks(tag, hw, dtype):
-    """16-bit programs store avg_pool2d(2,2) of the inputs of a stride-2 gOctaveCBR once (avgpool2_fast_kernel) instead
-    of averaging inside every consumer's staging loop.  One entry block at a time against the on-the-fly form, generic
-    conv kernels on both sides: the only difference is the 16-bit rounding of the stored averages."""
+    """16-bit programs store avg_pool2d(2,2) of the inputs of a stride-2 gOctaveCBR, and max_pool2d of the high-to-low
+    paths of any gOctaveCBR, once (pool2_fast_kernel) instead of pooling inside every consumer's staging loop.  One
+    module at a time against the on-the-fly form, generic conv kernels on both sides: the only difference is the 16-bit
+    rounding of the stored averages (stored maxima are exact)."""
     cfg, sd = fixtures.checkpoint(tag)
     h, w = hw
     x = torch.from_numpy(synth.randn_images(2, h, w, 53)).cuda()
@@ -267,9 +268,10 @@ def test_materialised_avgpool_of_stride2_entry_blocks(tag, hw, dtype):
     p0 = runtime.Plan(base, max_batch=2)
     p0.forward(x)
     rel = 4e-3 if dtype == "fp16" else 3e-2
-    for blk in ("stage2.0", "stage3.0", "stage4.0"):
-        prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse={blk + ".conv1x1"}, tensor_core=False)
-        assert sum(".pool" in o.name for o in prog.ops) >= 1
+    for name, blk in (("stage2.0.conv1x1", "stage2.0"), ("stage3.0.conv1x1", "stage3.0"), ("stage4.0.conv1x1", "stage4.0"),
+                      ("stage4.1.conv1x1", "stage4.1"), ("oct_fuse.fuse", "oct_fuse.fuse")):
+        prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse={name}, tensor_core=False)
+        assert sum("pool" in o.name for o in prog.ops) >= 1
         p1 = runtime.Plan(prog, max_batch=2)
         p1.forward(x)
         for b in (0, 1):
