@@ -183,7 +183,10 @@ class _Lowering:
                 if i > j and ksize == 1 and stride == 1 and self.upsample_inputs and upsample_input_side(cin, cj, 2 ** (i - j)):
                     # 16-bit programs, 1x1, fewer input than output channels: up-sample the conv INPUT instead of its
                     # output (identical linear map, cin instead of cout bilinear evaluations, no scratch tensor)
-                    paths.append(ir.Path(x, cin, cj, ksize=1, up=2 ** (i - j), w_off=self.conv_w(w)))
+                    if pool_once:                                    # ... and do it once, in a bandwidth-bound op of its own
+                        paths.append(ir.Path(self.upsampled(x, 2 ** (i - j), prefix), cin, cj, ksize=1, w_off=self.conv_w(w)))
+                    else:
+                        paths.append(ir.Path(x, cin, cj, ksize=1, up=2 ** (i - j), w_off=self.conv_w(w)))
                 elif i > j:                                          # conv at low res, then bilinear (:702-707)
                     _, Hi, Wi = self.dims(x)
                     low = self.b.tensor(cj, Hi // stride, Wi // stride, ir.F32, name=f"{prefix}/low{i}to{j}")
@@ -216,6 +219,14 @@ class _Lowering:
             self.b.op(ir.OP_MIX, t, [ir.Path(src, C_, C_, ksize=0, pool=2)], name=f"{prefix}.maxpool{f}of{x}")
             self._pooled[key] = t
         return self._pooled[key]
+
+    def upsampled(self, x: int, f: int, prefix: str) -> int:
+        """F.interpolate(scale_factor=f, bilinear) of a whole 16-bit tensor as its own op: the stored 16-bit value is the one
+        the tensor-core kernel would stage for an input-side up-sampled 1x1 path, computed once instead of once per tile."""
+        C_, H_, W_ = self.dims(x)
+        t = self.b.tensor(C_, H_ * f, W_ * f, self.dt, name=f"{prefix}/up{f}of{x}")
+        self.b.op(ir.OP_MIX, t, [ir.Path(x, C_, C_, ksize=0, up=f)], name=f"{prefix}.up{f}of{x}")
+        return t
 
     def dw_cbr(self, prefix: str, xs: List[Optional[int]]):
         """SimplifiedGOctConvBR.forward (csnet.py:838-851)."""

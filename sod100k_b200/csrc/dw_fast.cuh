@@ -107,4 +107,37 @@ __global__ void __launch_bounds__(256) pool2_fast_kernel(const __grid_constant__
   *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(A.dst) + ((size_t)n * A.C + c) * (size_t)A.H * A.W + (size_t)oy * A.W + x) = out;
 }
 
+// F.interpolate(scale_factor=up, bilinear, align_corners=False) of a 16-bit tensor into a 16-bit tensor (the materialised
+// input of an up-sampling 1x1 path): 4 output pixels of one row per thread, the row pair and its weights computed once, the
+// same blend expression as bilinear_up(), one 8-byte store.  A.W % 4 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_fast_kernel(const __grid_constant__ MixArgs A) {
+  const int G = A.W >> 2;
+  const int task = blockIdx.x * 256 + threadIdx.x;
+  if (task >= G * A.H) return;
+  const int oy = task / G, x = 4 * (task - oy * G), c = blockIdx.y, n = blockIdx.z;
+  const MixPath& P = A.p[0];
+  const int Hs = P.H, Ws = P.W;
+  const float inv = 1.0f / (float)P.up;
+  float sy = ((float)oy + 0.5f) * inv - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  const int y0 = (int)sy, y1 = y0 + (y0 < Hs - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, hy = 1.f - ly;
+  const uint16_t* plane = reinterpret_cast<const uint16_t*>(P.src) + ((size_t)n * P.C + P.c0 + c) * (size_t)Hs * Ws;
+  const uint16_t *r0 = plane + (size_t)y0 * Ws, *r1 = plane + (size_t)y1 * Ws;
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float sx = ((float)(x + k) + 0.5f) * inv - 0.5f;
+    sx = sx < 0.f ? 0.f : sx;
+    const int x0 = (int)sx, x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+    const float lx = sx - (float)x0, hx = 1.f - lx;
+    o[k] = hy * (hx * Pack<T>::to_f(r0[x0]) + lx * Pack<T>::to_f(r0[x1])) + ly * (hx * Pack<T>::to_f(r1[x0]) + lx * Pack<T>::to_f(r1[x1]));
+  }
+  uint2 out;
+  out.x = Pack<T>::from_f2(o[0], o[1]);
+  out.y = Pack<T>::from_f2(o[2], o[3]);
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(A.dst) + ((size_t)n * A.C + c) * (size_t)A.H * A.W + (size_t)oy * A.W + x) = out;
+}
+
 }  // namespace csnet

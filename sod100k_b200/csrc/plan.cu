@@ -666,6 +666,11 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
       const dim3 grid((D.H * (D.W / 4) + 255) / 256, D.C, N);    // avg_pool2d(2, 2) / max_pool2d(2, 2) of a 16-bit tensor
       if (D.dtype == CSNET_F16) csnet::pool2_fast_kernel<__half><<<grid, 256, 0, stream>>>(A, max2);
       else csnet::pool2_fast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(A, max2);
+    } else if (q.up > 1 && !q.pre_avg && q.pool == 1 && S.dtype == D.dtype && D.dtype != CSNET_F32 && D.W % 4 == 0 &&
+               op.bias_off < 0 && op.slope_off < 0) {
+      const dim3 grid((D.H * (D.W / 4) + 255) / 256, D.C, N);    // bilinear up-sampling, 16-bit to 16-bit
+      if (D.dtype == CSNET_F16) csnet::upsample_fast_kernel<__half><<<grid, 256, 0, stream>>>(A);
+      else csnet::upsample_fast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(A);
     } else {
       csnet::resample_fast_kernel<<<dim3((D.H * D.W + 255) / 256, D.C, N), 256, 0, stream>>>(A);
     }

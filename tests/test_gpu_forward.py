@@ -269,9 +269,9 @@ def test_materialised_avgpool_of_stride2_entry_blocks(tag, hw, dtype):
     p0.forward(x)
     rel = 4e-3 if dtype == "fp16" else 3e-2
     for name, blk in (("stage2.0.conv1x1", "stage2.0"), ("stage3.0.conv1x1", "stage3.0"), ("stage4.0.conv1x1", "stage4.0"),
-                      ("stage4.1.conv1x1", "stage4.1"), ("oct_fuse.fuse", "oct_fuse.fuse")):
+                      ("stage4.1.conv1x1", "stage4.1"), ("oct_fuse.fuse", "oct_fuse.fuse"), ("oct_fuse.fuse1x1", "oct_fuse.fuse1x1")):
         prog = compiler.compile_csnet(cfg, sd, h, w, dtype, reuse_arena=False, fuse={name}, tensor_core=False)
-        assert sum("pool" in o.name for o in prog.ops) >= 1
+        assert sum("pool" in o.name or ".up" in o.name for o in prog.ops) >= 1
         p1 = runtime.Plan(prog, max_batch=2)
         p1.forward(x)
         for b in (0, 1):
