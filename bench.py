@@ -273,6 +273,12 @@ def run_ours(a):
             print(f"{prog.ops[i].name:34s} {per_op[i]:8.3f} ms {100 * per_op[i] / tot:5.1f}%  {ob / per_op[i] / 1e6:8.1f} GB/s",
                   file=sys.stderr)
         print(f"sum of per-op times {tot:.3f} ms vs step {ms / a.steps:.3f} ms", file=sys.stderr)
+    # DRAM traffic of the dominant kernel: not measurable without a profiler, so it comes from the committed ncu capture of
+    # the same op / batch / size / dtype (profiles/traffic.json, written by scripts/ncu_traffic.sh), or stays null
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{a.model}:{prog.ops[top].name}:bs{B}:{S}x{S}:{a.dtype}")
     out = {
         "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -281,7 +287,7 @@ def run_ours(a):
                 "d2h_bytes_per_step": int(y_host.numel() * 4), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": plan.launches * a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": f"op {top} '{prog.ops[top].name}'", "kernel_ms": per_op[top],
+                     "traffic": traffic, "kernel": f"op {top} '{prog.ops[top].name}'", "kernel_ms": per_op[top],
                      "algorithmic_bytes_per_launch": top_bytes, "peak_source": peak_src,
                      "net": {"bytes_per_image_block_fused": net_bytes,
                              "achieved": ips / world * net_bytes / 1e9, "frac": ips / world * net_bytes / 1e9 / peak}},

@@ -46,7 +46,7 @@ def _check_grads(m, ref_grads, g64, floor=2 * GRAD_TOL, per_tensor=True):
     50x the fp32 oracle's own deviation.
     Globally: relative L2 error of the whole gradient vector <= max(1e-3, 10x the fp32 oracle's)."""
     num = den = nnum = 0.0
-    worst = ("", 0.0)
+    worst = ("", 0.0, 0.0)
     for name, p in m.named_parameters():
         g, r, r64 = p.grad.detach().cpu().double(), ref_grads[name].double(), g64[name]
         scale = max(r64.abs().max().item(), 1e-6)
@@ -54,12 +54,13 @@ def _check_grads(m, ref_grads, g64, floor=2 * GRAD_TOL, per_tensor=True):
         err = (g - r64).abs().max().item() / scale
         num += (g - r64).pow(2).sum().item(); nnum += (r - r64).pow(2).sum().item(); den += r64.pow(2).sum().item()
         if err > worst[1]:
-            worst = (name, err)
+            worst = (name, err, noise)
         if per_tensor:
             assert err <= (floor if noise <= 1e-4 else max(floor, 50.0 * noise)), (name, err, noise, scale)
     rel, rel_noise = (num / den) ** 0.5, (nnum / den) ** 0.5
     assert rel <= max(1e-3, 10.0 * rel_noise), (rel, rel_noise)
-    assert worst[1] <= 5e-2, worst                          # no tensor is structurally wrong
+    # no tensor is structurally wrong: 5 % of its scale, or 50x what fp32 rounding alone does to the oracle on that tensor
+    assert worst[1] <= max(5e-2, 50.0 * worst[2]), worst
     return worst
 
 
