@@ -46,26 +46,52 @@ __device__ __forceinline__ void block_sum3(float& a, float& b, float& c) {
 }
 
 // ---- BatchNorm (train) + PReLU ---------------------------------------------------------------------------
-// stats: per channel mean and biased variance over (N, H*W), two-pass (mean first) for accuracy.
-__global__ void __launch_bounds__(kT) bn_stats_kernel(const float* __restrict__ z, int N, int C, int HW, float* mean, float* var) {
-  const int c = blockIdx.x;
-  float s = 0.f, d0 = 0.f, d1 = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* p = z + ((size_t)n * C + c) * HW;
-    for (int i = threadIdx.x; i < HW; i += kT) s += p[i];
+// Per-channel reductions over (N, H*W) run on a (C, parts) grid — a channel-per-block grid would leave most of the 148 SMs
+// idle for 8..79-channel layers.  A block reduces one segment of one image plane, publishes its partial to a workspace,
+// and the last block to arrive for a channel (ticket counter) merges the partials IN PART ORDER, so the result does not
+// depend on scheduling.  Segments: S per plane, parts = N * S.
+__device__ __forceinline__ bool last_block_of(unsigned* counter, unsigned parts) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == parts - 1;
   }
+  __syncthreads();
+  return is_last;
+}
+
+// stats: per channel mean and biased variance.  Each part is reduced two-pass (its own mean first), parts are merged with
+// Chan's formula: M2 = sum M2_p + sum m_p (mean_p - mean)^2.
+__global__ void __launch_bounds__(kT) bn_stats_kernel(const float* __restrict__ z, int N, int C, int HW, int S, float* mean,
+                                                      float* var, float* ws, unsigned* cnt) {
+  const int c = blockIdx.x, part = blockIdx.y, parts = gridDim.y, n = part / S, sg = part - n * S;
+  const int seg = (HW + S - 1) / S, i0 = sg * seg, i1 = (i0 + seg) < HW ? (i0 + seg) : HW;
+  const float* p = z + ((size_t)n * C + c) * HW;
+  float s = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int i = i0 + threadIdx.x; i < i1; i += kT) s += p[i];
   block_sum3(s, d0, d1);
   __shared__ float mu_s;
-  if (threadIdx.x == 0) mu_s = s / ((float)N * (float)HW);
+  const float m = (float)(i1 > i0 ? i1 - i0 : 0);
+  if (threadIdx.x == 0) mu_s = m > 0.f ? s / m : 0.f;
   __syncthreads();
   const float mu = mu_s;
   float q = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* p = z + ((size_t)n * C + c) * HW;
-    for (int i = threadIdx.x; i < HW; i += kT) { const float d = p[i] - mu; q += d * d; }
-  }
+  for (int i = i0 + threadIdx.x; i < i1; i += kT) { const float d = p[i] - mu; q += d * d; }
   block_sum3(q, d0, d1);
-  if (threadIdx.x == 0) { mean[c] = mu; var[c] = q / ((float)N * (float)HW); }
+  float* w = ws + ((size_t)c * parts + part) * 3;
+  if (threadIdx.x == 0) { w[0] = mu; w[1] = q; w[2] = m; }
+  if (!last_block_of(cnt + c, parts)) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* v = ws + (size_t)c * parts * 3;
+    float tot = 0.f, acc = 0.f;
+    for (int k = 0; k < parts; ++k) { tot += v[3 * k + 2]; acc += v[3 * k + 2] * v[3 * k]; }
+    const float mean_c = acc / tot;
+    float m2 = 0.f;
+    for (int k = 0; k < parts; ++k) { const float d = v[3 * k] - mean_c; m2 += v[3 * k + 1] + v[3 * k + 2] * d * d; }
+    mean[c] = mean_c; var[c] = m2 / tot;
+    cnt[c] = 0u;                                            // ready for the next call on this stream
+  }
 }
 
 // y = prelu(gamma * (z - mean) * rsqrt(var + eps) + beta);  gap[n*C+c] = mean over HW of y (optional)
@@ -89,26 +115,37 @@ __global__ void __launch_bounds__(kT) bn_prelu_fwd_kernel(const float* __restric
   }
 }
 
-// backward reductions per channel: S1 = sum du, S2 = sum du * xhat, S3 = sum dy * u * [u <= 0]   (du = dy * prelu'(u))
+// backward reductions per channel: S1 = sum du, S2 = sum du * xhat, S3 = sum dy * u * [u <= 0]   (du = dy * prelu'(u));
+// same (C, parts) grid and ordered merge as bn_stats_kernel
 __global__ void __launch_bounds__(kT) bn_prelu_bwd_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, int N,
-                                                                 int C, int HW, const float* mean, const float* var,
+                                                                 int C, int HW, int S, const float* mean, const float* var,
                                                                  const float* gamma, const float* beta, const float* slope,
-                                                                 float eps, float* dgamma, float* dbeta, float* dslope) {
-  const int c = blockIdx.x;
+                                                                 float eps, float* dgamma, float* dbeta, float* dslope, float* ws,
+                                                                 unsigned* cnt) {
+  const int c = blockIdx.x, part = blockIdx.y, parts = gridDim.y, n = part / S, sg = part - n * S;
+  const int seg = (HW + S - 1) / S, i0 = sg * seg, i1 = (i0 + seg) < HW ? (i0 + seg) : HW;
   const float mu = mean[c], r = rsqrtf(var[c] + eps), g = gamma[c], b = beta[c], a = slope[c];
   float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* p = z + ((size_t)n * C + c) * HW;
-    const float* q = dy + ((size_t)n * C + c) * HW;
-    for (int i = threadIdx.x; i < HW; i += kT) {
-      const float xh = (p[i] - mu) * r, u = g * xh + b, d = q[i];
-      const float du = u > 0.f ? d : a * d;
-      s1 += du; s2 += du * xh;
-      if (!(u > 0.f)) s3 += d * u;
-    }
+  const float* p = z + ((size_t)n * C + c) * HW;
+  const float* q = dy + ((size_t)n * C + c) * HW;
+  for (int i = i0 + threadIdx.x; i < i1; i += kT) {
+    const float xh = (p[i] - mu) * r, u = g * xh + b, d = q[i];
+    const float du = u > 0.f ? d : a * d;
+    s1 += du; s2 += du * xh;
+    if (!(u > 0.f)) s3 += d * u;
   }
   block_sum3(s1, s2, s3);
-  if (threadIdx.x == 0) { dbeta[c] = s1; dgamma[c] = s2; dslope[c] = s3; }
+  float* w = ws + ((size_t)c * parts + part) * 3;
+  if (threadIdx.x == 0) { w[0] = s1; w[1] = s2; w[2] = s3; }
+  if (!last_block_of(cnt + c, parts)) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* v = ws + (size_t)c * parts * 3;
+    float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int k = 0; k < parts; ++k) { t1 += v[3 * k]; t2 += v[3 * k + 1]; t3 += v[3 * k + 2]; }
+    dbeta[c] = t1; dgamma[c] = t2; dslope[c] = t3;
+    cnt[c] = 0u;
+  }
 }
 
 // dz = gamma * r * (du - S1/M - xhat * S2/M)
@@ -360,8 +397,44 @@ extern "C" {
 
 const char* csnet_train_last_error(void) { return t_err.c_str(); }
 
+// Workspace of the channel reductions: partials [C][parts][3] + one ticket counter per channel.  One per process, grown on
+// demand; the training entry points are meant to be issued on ONE stream (calls serialise there, so sharing is safe).
+static float* g_red_ws = nullptr;
+static unsigned* g_red_cnt = nullptr;
+static size_t g_red_ws_cap = 0, g_red_cnt_cap = 0;
+
+static int reduce_workspace(int C, int parts, cudaStream_t st) {
+  const size_t need = (size_t)C * parts * 3;
+  if (need > g_red_ws_cap) {
+    TR_CHECK(cudaStreamSynchronize(st));
+    if (g_red_ws) cudaFree(g_red_ws);
+    g_red_ws = nullptr; g_red_ws_cap = 0;
+    TR_CHECK(cudaMalloc(&g_red_ws, need * 2 * sizeof(float)));
+    g_red_ws_cap = need * 2;
+  }
+  if ((size_t)C > g_red_cnt_cap) {
+    TR_CHECK(cudaStreamSynchronize(st));
+    if (g_red_cnt) cudaFree(g_red_cnt);
+    g_red_cnt = nullptr; g_red_cnt_cap = 0;
+    const size_t cap = (size_t)C * 2 < 1024 ? 1024 : (size_t)C * 2;
+    TR_CHECK(cudaMalloc(&g_red_cnt, cap * sizeof(unsigned)));
+    TR_CHECK(cudaMemset(g_red_cnt, 0, cap * sizeof(unsigned)));
+    g_red_cnt_cap = cap;
+  }
+  return CSNET_OK;
+}
+
+// segments per image plane: enough parts to fill the GPU for narrow layers and small batches, at most 64 per plane
+static int reduce_segments(int N, int C, int HW) {
+  int S = 1;
+  while ((long)N * C * S < 1184 && S < 64 && HW / (S * 2) >= 2048) S *= 2;
+  return S;
+}
+
 int csnet_train_bn_stats(const float* z, int32_t N, int32_t C, int32_t HW, float* mean, float* var, void* stream) {
-  bn_stats_kernel<<<C, kT, 0, (cudaStream_t)stream>>>(z, N, C, HW, mean, var);
+  const int S = reduce_segments(N, C, HW);
+  if (int rc = reduce_workspace(C, N * S, (cudaStream_t)stream)) return rc;
+  bn_stats_kernel<<<dim3(C, N * S), kT, 0, (cudaStream_t)stream>>>(z, N, C, HW, S, mean, var, g_red_ws, g_red_cnt);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
@@ -376,7 +449,10 @@ int csnet_train_bn_prelu_fwd(const float* z, float* y, int32_t N, int32_t C, int
 int csnet_train_bn_prelu_bwd(const float* z, const float* dy, float* dz, int32_t N, int32_t C, int32_t HW, const float* mean,
                              const float* var, const float* gamma, const float* beta, const float* slope, float eps,
                              float* dgamma, float* dbeta, float* dslope, int32_t frozen, void* stream) {
-  bn_prelu_bwd_reduce_kernel<<<C, kT, 0, (cudaStream_t)stream>>>(z, dy, N, C, HW, mean, var, gamma, beta, slope, eps, dgamma, dbeta, dslope);
+  const int S = reduce_segments(N, C, HW);
+  if (int rc = reduce_workspace(C, N * S, (cudaStream_t)stream)) return rc;
+  bn_prelu_bwd_reduce_kernel<<<dim3(C, N * S), kT, 0, (cudaStream_t)stream>>>(z, dy, N, C, HW, S, mean, var, gamma, beta, slope, eps,
+                                                                            dgamma, dbeta, dslope, g_red_ws, g_red_cnt);
   TR_CHECK(cudaGetLastError());
   bn_prelu_bwd_apply_kernel<<<dim3(C, N), kT, 0, (cudaStream_t)stream>>>(z, dy, dz, N, C, HW, mean, var, gamma, beta, slope, eps, dgamma, dbeta, frozen);
   TR_CHECK(cudaGetLastError());
