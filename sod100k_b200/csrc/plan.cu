@@ -826,7 +826,22 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
   // The batch is cut into chunks that flow through a three-stage pipeline: H2D copy (own stream) -> program
   // (caller's stream) -> D2H copy (own stream), with ping-pong device staging, so the PCIe copies of chunk i+1 / i-1
   // overlap the kernels of chunk i.  Pinned host memory is needed for the copies to be truly asynchronous.
-  const int chunk = N >= 64 ? (N + 3) / 4 : N;
+  // Schedule: a small first and last chunk (N/8 images) keep the exposed copies short — the first H2D and the last D2H are
+  // the only ones nothing overlaps — and one large middle chunk keeps the kernels at large-batch efficiency (measured at
+  // bs 256: 4 equal chunks 25.2 ms, 2 equal 24.5 ms).  CSNET_HOST_CHUNKS=k forces k equal chunks.
+  static const int n_equal = [] { const char* e = getenv("CSNET_HOST_CHUNKS"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
+  int sizes[16], n_sizes = 0;
+  if (N < 64) {
+    sizes[n_sizes++] = N;
+  } else if (n_equal > 0) {
+    const int c = (N + n_equal - 1) / n_equal;
+    for (int n0 = 0; n0 < N; n0 += c) sizes[n_sizes++] = (N - n0) < c ? (N - n0) : c;
+  } else {
+    const int edge = N / 8;
+    sizes[n_sizes++] = edge; sizes[n_sizes++] = N - 2 * edge; sizes[n_sizes++] = edge;
+  }
+  int chunk = 0;
+  for (int i = 0; i < n_sizes; ++i) chunk = sizes[i] > chunk ? sizes[i] : chunk;
   const size_t xin = (size_t)in->C * in->H * in->W * sizeof(float), yout = (size_t)lo->C * lo->H * lo->W * sizeof(float);
   if (!P->s_h2d) {
     CU_CHECK(cudaStreamCreateWithFlags(&P->s_h2d, cudaStreamNonBlocking));
@@ -847,9 +862,9 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
     P->h_in_bytes = (size_t)chunk * xin;
     P->h_out_bytes = (size_t)chunk * yout;
   }
-  int rc = CSNET_OK, it = 0;
-  for (int n0 = 0; n0 < N && rc == CSNET_OK; n0 += chunk, ++it) {
-    const int b = it & 1, nb = (N - n0) < chunk ? (N - n0) : chunk;
+  int rc = CSNET_OK;
+  for (int it = 0, n0 = 0; it < n_sizes && rc == CSNET_OK; n0 += sizes[it], ++it) {
+    const int b = it & 1, nb = sizes[it];
     if (it >= 2) CU_CHECK(cudaStreamWaitEvent(P->s_h2d, P->ev_comp[b], 0));     // staging input b was consumed
     CU_CHECK(cudaMemcpyAsync(P->h_in[b], x_host + (size_t)n0 * (xin / sizeof(float)), (size_t)nb * xin, cudaMemcpyHostToDevice, P->s_h2d));
     CU_CHECK(cudaEventRecord(P->ev_h2d[b], P->s_h2d));
