@@ -245,6 +245,14 @@ int csnet_train_bce(const float* logits, const float* target, float* dlogits, fl
 int csnet_train_adam(const void* chunk_table_device, int32_t n_chunks, float lr, float beta1, float beta2, float eps, int32_t step,
                      float grad_scale, void* stream);
 
+/* ---- evaluation: the counting part of SalMetric on the device (CSNet_training/SalMetric/src/sal_metric.cpp:86-120) ----
+ * prob: device float32 [N][HW] saliency in [0,1] (after sigmoid); gt: device uint8 [N][HW] ground truth.  Per image:
+ * q = (uint8)(prob * 255) (CSNet/test.py:94-96), hist_all[q]++, hist_pos[q]++ where gt > 128, abs_sum += |q - gt|.
+ * hist_all / hist_pos: device uint32 [N][256], abs_sum: device uint64 [N]; all three are zeroed by the call.  The caller
+ * turns them into precision / recall per threshold (suffix sums), F-measure and MAE (sod100k_b200/salmetric.py). */
+int csnet_salmetric_hist(const float* prob, const uint8_t* gt, int32_t N, int64_t HW, uint32_t* hist_all, uint32_t* hist_pos,
+                         unsigned long long* abs_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -391,6 +391,31 @@ csnet::MixPath to_path(const csnet_train_path& q) {
   return m;
 }
 
+// ---- SalMetric counting (sal_metric.cpp:86-120): per-image 256-bin histograms of the quantised saliency ----------------
+__global__ void __launch_bounds__(kT) salmetric_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, int64_t HW,
+                                                            uint32_t* hist_all, uint32_t* hist_pos, unsigned long long* abs_sum) {
+  __shared__ uint32_t ha[256], hp[256];
+  __shared__ unsigned long long sd;
+  const int n = blockIdx.y;
+  ha[threadIdx.x] = 0u; hp[threadIdx.x] = 0u;              // kT == 256
+  if (threadIdx.x == 0) sd = 0ull;
+  __syncthreads();
+  unsigned int d = 0;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < HW; i += (int64_t)gridDim.x * kT) {
+    const double v = (double)prob[n * HW + i] * 255.0;     // the reference multiplies a float64 array (skimage resize output)
+    const int q = v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (int)v);
+    const int g = gt[n * HW + i];
+    atomicAdd(&ha[q], 1u);
+    if (g > 128) atomicAdd(&hp[q], 1u);
+    d += (unsigned)(q > g ? q - g : g - q);
+  }
+  atomicAdd(&sd, (unsigned long long)d);
+  __syncthreads();
+  if (ha[threadIdx.x]) atomicAdd(hist_all + (size_t)n * 256 + threadIdx.x, ha[threadIdx.x]);
+  if (hp[threadIdx.x]) atomicAdd(hist_pos + (size_t)n * 256 + threadIdx.x, hp[threadIdx.x]);
+  if (threadIdx.x == 0) atomicAdd(abs_sum + n, sd);
+}
+
 }  // namespace
 
 extern "C" {
@@ -515,6 +540,21 @@ int csnet_train_adam(const void* chunk_table_device, int32_t n_chunks, float lr,
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<n_chunks, kT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamChunk*>(chunk_table_device), lr, beta1, beta2,
                                                         eps, bc1, sqrtf(bc2), grad_scale);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_salmetric_hist(const float* prob, const uint8_t* gt, int32_t N, int64_t HW, uint32_t* hist_all, uint32_t* hist_pos,
+                         unsigned long long* abs_sum, void* stream) {
+  if (!prob || !gt || !hist_all || !hist_pos || !abs_sum || N <= 0 || HW <= 0) { t_err = "csnet_salmetric_hist: bad arguments"; return CSNET_E_INVALID; }
+  static_assert(kT == 256, "one histogram bin per thread");
+  cudaStream_t st = (cudaStream_t)stream;
+  TR_CHECK(cudaMemsetAsync(hist_all, 0, (size_t)N * 256 * sizeof(uint32_t), st));
+  TR_CHECK(cudaMemsetAsync(hist_pos, 0, (size_t)N * 256 * sizeof(uint32_t), st));
+  TR_CHECK(cudaMemsetAsync(abs_sum, 0, (size_t)N * sizeof(unsigned long long), st));
+  const int64_t want = (HW + kT * 16 - 1) / (kT * 16);
+  const int bx = (int)(want < 1 ? 1 : (want > 64 ? 64 : want));
+  salmetric_hist_kernel<<<dim3(bx, N), kT, 0, st>>>(prob, gt, HW, hist_all, hist_pos, abs_sum);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
