@@ -26,6 +26,8 @@ constexpr int kTcTH = 8, kTcTW = 32;
 
 struct TcGeom {
   int32_t tiles_x;
+  int32_t rows;           // output rows per warp (R): the tile is 8*R x 32.  R > 1 for wide-halo (dilated) ops: an 8-row
+                          // tile with a 16-pixel halo stages 11x the pixels it produces, a 32-row tile 4x
   int32_t xs_halves;      // allocated halves per staged channel plane (max over groups)
   int32_t kc;             // input channels per staged chunk (8, 16 or 32)
   int32_t m16_total;      // output channels rounded up to the CTA slice (MT*16) multiple
@@ -40,8 +42,8 @@ struct TcGeom {
 __host__ __device__ inline int tc_pad_left(int pad) { return (pad + 3) & ~3; }
 __host__ __device__ inline int tc_xw_vec(int pad) { return pad == 0 ? 32 : 64; }
 __host__ __device__ inline int tc_xw_exact(int pad) { return (tc_pad_left(pad) + kTcTW + pad + 3) & ~3; }
-__host__ __device__ inline int tc_plane_halves(int pad) {
-  int n = (kTcTH + 2 * pad) * tc_xw_vec(pad);
+__host__ __device__ inline int tc_plane_halves(int pad, int rows = 1) {
+  int n = (kTcTH * rows + 2 * pad) * tc_xw_vec(pad);
   n = (n + 15) / 16 * 16 + 8;          // == 8 (mod 16): the four channel pairs of a B fragment hit distinct banks
   return n;
 }
@@ -113,8 +115,8 @@ __device__ __forceinline__ float fetch_pooled16(const MixPath& P, const uint16_t
   return m;
 }
 
-template <typename T, int MT>
-__global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(const __grid_constant__ MixArgs A, const TcGeom G) {
+template <typename T, int MT, int R = 1>
+__global__ void __launch_bounds__(kTcThreads, (MT * R <= 2 ? 3 : 2)) mix_tc_kernel(const __grid_constant__ MixArgs A, const TcGeom G) {
   extern __shared__ __align__(16) uint16_t tc_smem[];
   const int KC = G.kc, WR = tc_wrow(KC);
   uint16_t* Xs = tc_smem;                                  // [KC][xs_halves]
@@ -122,17 +124,20 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int n = blockIdx.z;
-  const int oy0 = (blockIdx.x / G.tiles_x) * kTcTH, ox0 = (blockIdx.x % G.tiles_x) * kTcTW;
+  constexpr int TH = kTcTH * R;                             // warp w owns output rows w, w + 8, ... of the tile
+  const int oy0 = (blockIdx.x / G.tiles_x) * TH, ox0 = (blockIdx.x % G.tiles_x) * kTcTW;
   constexpr int M16 = MT * 16;
   const int m_base = blockIdx.y * M16;                      // this CTA's slice of the output channels
 
-  float acc[MT][4][4];
+  float acc[R][MT][4][4];
 #pragma unroll
-  for (int a = 0; a < MT; ++a)
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int a = 0; a < MT; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][a][b][c] = 0.f;
 
   for (int p0 = 0; p0 < A.n_paths;) {
     const MixPath& P0 = A.p[p0];
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
     // typed 32-bit pair loads need 4-byte alignment: true for f = 2 (offset 0); f = 4 / 8 start at odd pixels
     const bool pooled16 = P0.dtype != DT_F32 && P0.up == 1 && (P0.pre_avg || P0.pool > 1) && (srcW & 1) == 0 && pre_factor(P0.pre_avg) <= 2;
     const bool up16 = P0.dtype != DT_F32 && P0.up > 1;
-    const int XH = kTcTH + 2 * pad, padL = tc_pad_left(pad), PS = tc_plane_halves(pad);
+    const int XH = TH + 2 * pad, padL = tc_pad_left(pad), PS = tc_plane_halves(pad, R);
     const int XW = vec ? tc_xw_vec(pad) : tc_xw_exact(pad);
     const int64_t src_base = ((int64_t)n * P0.C + P0.c0) * plane_sz;
     for (int c0 = 0; c0 < cin; c0 += KC) {
@@ -260,10 +265,13 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
             af[mt][1] = *reinterpret_cast<const uint32_t*>(wt + (mt * 16 + 8) * WR);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t b = __byte_perm((uint32_t)ra[j * 8], (uint32_t)rb[j * 8], 0x5410);
+          for (int r = 0; r < R; ++r) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) Pack<T>::mma(acc[mt][j], af[mt], b);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t b = __byte_perm((uint32_t)ra[r * 8 * XW + j * 8], (uint32_t)rb[r * 8 * XW + j * 8], 0x5410);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) Pack<T>::mma(acc[r][mt][j], af[mt], b);
+            }
           }
         };
         const int rstep = dil * XW, wstep = M16 * WR;
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
 #pragma unroll 1
             for (int ky = 0; ky < 3; ++ky, xa += rstep) {
               const uint16_t* ra = xa;
-#pragma unroll(MT <= 1 ? 3 : 1)
+#pragma unroll(MT * R <= 1 ? 3 : 1)
               for (int kx = 0; kx < 3; ++kx, ra += dil, wt += wstep) tap(ra, ra + PS, wt);
             }
           }
@@ -287,14 +295,16 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
   }
 
   // ---- epilogue ------------------------------------------------------------------------------------------
-  const int oy = oy0 + warp;
-  if (oy >= A.H) return;
   uint32_t rmask = 0;                                       // resample-add paths of this op
   for (int p = 0; p < A.n_paths; ++p)
     if (A.p[p].ksize == 0) rmask |= 1u << p;
   const int64_t out_plane = (int64_t)A.H * A.W;
   const bool pair_store = A.dtype != DT_F32 && (A.W & 1) == 0;
   const bool proj = A.proj_w != nullptr;                    // CSNET_OP_MIXPROJ: dot the channels with proj_w instead of storing
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+  const int oy = oy0 + warp + 8 * r;
+  if (oy >= A.H) break;                                     // warp-uniform
   float ps[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
       for (int j = 0; j < 4; ++j) {
         const int ox = ox0 + j * 8 + 2 * t;
         if (ox >= A.W) continue;
-        float v0 = acc[mt][j][2 * h] + bias, v1 = acc[mt][j][2 * h + 1] + bias;
+        float v0 = acc[r][mt][j][2 * h] + bias, v1 = acc[r][mt][j][2 * h + 1] + bias;
         for (uint32_t mk = rmask; mk; mk &= mk - 1) {
           const MixPath& P = A.p[__ffs(mk) - 1];
           if (m < P.cout0 || m >= P.cout0 + P.cout) continue;
@@ -352,6 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, (MT <= 2 ? 3 : 2)) mix_tc_kernel(c
         if (g == 0 && ox < A.W) st_elem(A.dst, A.dtype, orow + ox, v + pb);
       }
     }
+  }
   }
 }
 

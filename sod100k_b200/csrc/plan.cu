@@ -129,6 +129,7 @@ struct TcChoice {
   int mt = 0;            // 0: generic kernel; else number of m16 tiles of the tensor-core kernel
   int dtype = 0;         // CSNET_F16 / CSNET_BF16 operand type
   int xs_halves = 0;
+  int rows = 1;          // output rows per warp of mix_tc (tile height 8 * rows)
   int kc = 8;            // input channels per staged chunk
   int kk = 1;            // largest tap count among the conv paths
 };
@@ -456,7 +457,9 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
   if (dt < 0 || nconv == 0 || pad > csnet::kTcMaxPad) return c;
   c.mt = Cm > 80 ? 5 : (Cm + 15) / 16;               // more than 80 output channels: 80-channel slices over grid.y
   c.dtype = dt;
-  c.xs_halves = csnet::tc_plane_halves(pad);
+  // wide halos (dilated MS convs): taller tiles while the accumulators fit (MT * rows <= 4)
+  c.rows = pad >= 4 ? (c.mt == 1 ? 4 : (c.mt == 2 ? 2 : 1)) : 1;
+  c.xs_halves = csnet::tc_plane_halves(pad, c.rows);
   c.kk = kk;
   c.kc = 8;
   for (int kc : {32, 16}) {                       // the largest chunk that keeps two CTAs per SM resident
@@ -469,6 +472,8 @@ TcChoice choose_tc(const csnet_plan& P, const csnet_op_desc& op) {
 
 template <typename T>
 void launch_mix_tc_t(int mt, dim3 grid, size_t smem, cudaStream_t st, const csnet::MixArgs& A, const csnet::TcGeom& G) {
+  if (G.rows == 4) { csnet::mix_tc_kernel<T, 1, 4><<<grid, csnet::kTcThreads, smem, st>>>(A, G); return; }
+  if (G.rows == 2) { csnet::mix_tc_kernel<T, 2, 2><<<grid, csnet::kTcThreads, smem, st>>>(A, G); return; }
   switch (mt) {
     case 1: csnet::mix_tc_kernel<T, 1><<<grid, csnet::kTcThreads, smem, st>>>(A, G); break;
     case 2: csnet::mix_tc_kernel<T, 2><<<grid, csnet::kTcThreads, smem, st>>>(A, G); break;
@@ -490,6 +495,8 @@ cudaError_t set_tc_smem_t(int bytes) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::mix_tc_kernel<T, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   return e;
 }
 
@@ -650,10 +657,11 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     const TcChoice& tc = P->op_tc[i];
     const int Cm = A.C;
     csnet::TcGeom G{};
-    G.tiles_x = (D.W + csnet::kTcTW - 1) / csnet::kTcTW; G.xs_halves = tc.xs_halves; G.kc = tc.kc;
+    G.tiles_x = (D.W + csnet::kTcTW - 1) / csnet::kTcTW; G.xs_halves = tc.xs_halves; G.kc = tc.kc; G.rows = tc.rows;
+    const int th = csnet::kTcTH * tc.rows;
     G.m16_total = (Cm + tc.mt * 16 - 1) / (tc.mt * 16) * (tc.mt * 16);
     for (int p = 0; p < op.n_paths; ++p) G.w16[p] = P->op_w16[i][p];
-    dim3 grid(G.tiles_x * ((D.H + csnet::kTcTH - 1) / csnet::kTcTH), (Cm + tc.mt * 16 - 1) / (tc.mt * 16), N);
+    dim3 grid(G.tiles_x * ((D.H + th - 1) / th), (Cm + tc.mt * 16 - 1) / (tc.mt * 16), N);
     launch_mix_tc(tc, grid, P->op_smem[i], stream, A, G);
   } else if (op.kind == CSNET_OP_MIX && op.n_paths == 1 && op.paths[0].ksize == 0 && op.paths[0].cout0 == 0 &&
              op.paths[0].cout == D.C) {
