@@ -22,6 +22,7 @@
 //   lo region origin (ly0-2, lx0-4), size RHl x RWl = (TH/2+4 [+1]) x (TW/2+8) x origin kept a multiple of 4 (8-byte I/O)
 //   lo R(ry, rx)  <->  hi R(2ry, 2rx-4);  the optional +1 row only makes RH*RW/8 odd (conflict-free ldmatrix).
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -85,6 +86,12 @@ template <> struct Pack<__half> {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b));
   }
+  // acc += x * w with 16-bit x, w and fp32 accumulation in ONE instruction (sm_100 FHFMA): no operand conversions
+  static __device__ __forceinline__ float fma16(uint16_t x, uint16_t w, float acc) {
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(x), "h"(w));
+    return acc;
+  }
+  static __device__ __forceinline__ uint16_t bits(float v) { return __half_as_ushort(__float2half_rn(v)); }
 };
 template <> struct Pack<__nv_bfloat16> {
   static __device__ __forceinline__ float2 to_f2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
@@ -101,6 +108,11 @@ template <> struct Pack<__nv_bfloat16> {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b));
   }
+  static __device__ __forceinline__ float fma16(uint16_t x, uint16_t w, float acc) {
+    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(x), "h"(w));
+    return acc;
+  }
+  static __device__ __forceinline__ uint16_t bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -203,27 +215,34 @@ __device__ __forceinline__ void dw_task(int task, const uint16_t* in, uint16_t* 
   const int gi = task % G, rest = task / G;
   const int run = rest % NR, c = rest / NR;
   const int x = 4 * (GEO::G0 + gi), ra = GEO::R0 + run * RUN;
-  float w[9];
+  // fp16 planes: the 9 taps run as the mixed-precision FMA (Pack<T>::fma16: 16-bit x 16-bit + fp32 in one instruction), so
+  // no operand is converted; the weights are rounded to fp16 for it (measured: no change of the fp16 error figures).
+  // bf16 planes keep fp32 weights and converted operands — 8-bit-mantissa weights cost accuracy there.
+  constexpr bool kMixed = std::is_same<T, __half>::value;
+  float wf[9];
+  uint16_t wh[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) w[i] = __ldg(P.w + c * 9 + i);
+  for (int i = 0; i < 9; ++i) {
+    wf[i] = __ldg(P.w + c * 9 + i);
+    wh[i] = Pack<T>::bits(wf[i]);
+  }
   const float bias = __ldg(P.b + c), slope = __ldg(P.s + c);
   const uint16_t* plane = in + c * NP + x;
   const int gx = ox0 + x;
   const bool col_in = gx >= 0 && gx < imgW;            // imgW % 4 == 0 and gx % 4 == 0: a group is all in or all out
-  float rows[RUN + 2][6];
+  uint16_t rows[RUN + 2][6];                           // pixels x-1 .. x+4 of every input row
 #pragma unroll
   for (int i = 0; i < RUN + 2; ++i) {
     const int r = ra - 1 + i;
+    uint32_t lft = 0u, rgt = 0u;
+    uint2 mid = make_uint2(0u, 0u);
     if (r <= r1) {                                      // row R1 exists (R1 <= RH - 1)
-      const uint2 mid = *reinterpret_cast<const uint2*>(plane + r * RW);            // x .. x+3 (8-byte aligned)
-      const uint32_t lft = *reinterpret_cast<const uint32_t*>(plane + r * RW - 2);  // x-2, x-1
-      const uint32_t rgt = *reinterpret_cast<const uint32_t*>(plane + r * RW + 4);  // x+4, x+5
-      const float2 a = Pack<T>::to_f2(lft), b = Pack<T>::to_f2(mid.x), c2 = Pack<T>::to_f2(mid.y), d = Pack<T>::to_f2(rgt);
-      rows[i][0] = a.y; rows[i][1] = b.x; rows[i][2] = b.y; rows[i][3] = c2.x; rows[i][4] = c2.y; rows[i][5] = d.x;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) rows[i][k] = 0.f;
+      mid = *reinterpret_cast<const uint2*>(plane + r * RW);            // x .. x+3 (8-byte aligned)
+      lft = *reinterpret_cast<const uint32_t*>(plane + r * RW - 2);     // x-2, x-1
+      rgt = *reinterpret_cast<const uint32_t*>(plane + r * RW + 4);     // x+4, x+5
     }
+    rows[i][0] = (uint16_t)(lft >> 16); rows[i][1] = (uint16_t)mid.x; rows[i][2] = (uint16_t)(mid.x >> 16);
+    rows[i][3] = (uint16_t)mid.y; rows[i][4] = (uint16_t)(mid.y >> 16); rows[i][5] = (uint16_t)rgt;
   }
 #pragma unroll
   for (int i = 0; i < RUN; ++i) {
@@ -233,9 +252,13 @@ __device__ __forceinline__ void dw_task(int task, const uint16_t* in, uint16_t* 
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float v = bias;
-        v = fmaf(rows[i][k], w[0], v); v = fmaf(rows[i][k + 1], w[1], v); v = fmaf(rows[i][k + 2], w[2], v);
-        v = fmaf(rows[i + 1][k], w[3], v); v = fmaf(rows[i + 1][k + 1], w[4], v); v = fmaf(rows[i + 1][k + 2], w[5], v);
-        v = fmaf(rows[i + 2][k], w[6], v); v = fmaf(rows[i + 2][k + 1], w[7], v); v = fmaf(rows[i + 2][k + 2], w[8], v);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            if constexpr (kMixed) v = Pack<T>::fma16(rows[i + dy][k + dx], wh[dy * 3 + dx], v);
+            else v = fmaf(Pack<T>::to_f(rows[i + dy][k + dx]), wf[dy * 3 + dx], v);
+          }
         o[k] = prelu(v, slope);
       }
       const int gy = oy0 + r;
