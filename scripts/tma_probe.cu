@@ -2,6 +2,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -66,7 +67,9 @@ int main(int argc, char** argv) {
   CK(cudaMemset(o, 0xff, 65536));
   const int nbytes = bw * bh * bc * 2;
   const bool pos = strstr(mode, "pos") != nullptr;
-  const int cx = pos ? 8 : -4, cy = pos ? 2 : -4, n = 1;
+  int cx = pos ? 8 : -4, cy = pos ? 2 : -4;          // or explicit: tma_probe <mode> <cx> <cy>
+  const int n = 1;
+  if (argc > 3) { cx = atoi(argv[2]); cy = atoi(argv[3]); }
   CUtensorMap tm;
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r;

@@ -152,11 +152,13 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// D[M16 x NP] = Ws[M16 x K8] . X[K8 x NP], result handed to epi() pair-wise; X may be overwritten by epi() for the
-// SAME pixel columns (each warp owns its columns and holds all their B fragments in registers before writing).
-template <typename T, typename Coord, typename RowP, typename Epi>
+// X[m][p] <- 16-bit(prelu(bias[m] + sum_k Ws[m][k] X[k][p])) for the pixels inside the image, 0 outside: D[M16 x NP] =
+// Ws[M16 x K8] . X[K8 x NP] IN PLACE — each warp owns its pixel columns and holds all their B fragments in registers
+// before it overwrites them.  coord(p) tells whether the pixel pair (p, p+1) is inside the image (rows are even-sized and
+// p is even, so a pair is all in or all out); rowp(m, bias, slope) whether output row m exists.
+template <typename T, typename Coord, typename RowP>
 __device__ __forceinline__ void gemm_pixels_inplace(const uint16_t* Ws, int M16, int K8, uint16_t* X, int NP, int warp,
-                                                    int nwarps, int lane, Coord coord, RowP rowp, Epi epi) {
+                                                    int nwarps, int lane, Coord coord, RowP rowp) {
   const int ntiles = NP >> 3, ksteps = K8 >> 3;
   const int g = lane >> 2, t = lane & 3;
   for (int nt0 = warp * 4; nt0 < ntiles; nt0 += nwarps * 4) {
@@ -167,15 +169,15 @@ __device__ __forceinline__ void gemm_pixels_inplace(const uint16_t* Ws, int M16,
     for (int ks = 0; ks < kIlMaxK8; ++ks)
       if (ks < ksteps) ldmatrix_x4_trans(bf[ks], X + (size_t)(ks * 8 + (lane & 7)) * NP + ntl * 8);
     __syncwarp();
-    int cy[4], cx[4];
+    bool inb[4];                                        // is the pixel pair (p, p+1) of n tile j inside the image?
 #pragma unroll
-    for (int j = 0; j < 4; ++j) coord((nt0 + j) * 8 + 2 * t, cy[j], cx[j]);
+    for (int j = 0; j < 4; ++j) inb[j] = coord((nt0 + j) * 8 + 2 * t);
     for (int mt = 0; mt < (M16 >> 4); ++mt) {
-      float acc[4][4];
+      float b0, s0, b1, s1;                               // per-row epilogue parameters, loaded once per m tile
+      const bool live0 = rowp(mt * 16 + g, b0, s0), live1 = rowp(mt * 16 + g + 8, b1, s1);
+      float acc[4][4];                                    // the bias is the accumulator's initial value
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[b][c] = 0.f;
+      for (int b = 0; b < 4; ++b) { acc[b][0] = acc[b][1] = live0 ? b0 : 0.f; acc[b][2] = acc[b][3] = live1 ? b1 : 0.f; }
 #pragma unroll
       for (int ks = 0; ks < kIlMaxK8; ++ks) {
         if (ks < ksteps) {
@@ -185,14 +187,19 @@ __device__ __forceinline__ void gemm_pixels_inplace(const uint16_t* Ws, int M16,
           for (int j = 0; j < 4; ++j) Pack<T>::mma(acc[j], af, bf[ks][j]);
         }
       }
-      float b0, s0, b1, s1;                               // per-row epilogue parameters, loaded once per m tile
-      const bool live0 = rowp(mt * 16 + g, b0, s0), live1 = rowp(mt * 16 + g + 8, b1, s1);
+      const float m0 = s0 - 1.f, m1 = s1 - 1.f;           // prelu(v) = v + (slope - 1) * min(v, 0): two instructions
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (nt0 + j < ntiles) {
           const int p = (nt0 + j) * 8 + 2 * t;
-          if (live0) epi(mt * 16 + g, p, cy[j], cx[j], acc[j][0], acc[j][1], b0, s0);
-          if (live1) epi(mt * 16 + g + 8, p, cy[j], cx[j], acc[j][2], acc[j][3], b1, s1);
+          if (live0) {
+            const uint32_t v = Pack<T>::from_f2(fmaf(fminf(acc[j][0], 0.f), m0, acc[j][0]), fmaf(fminf(acc[j][1], 0.f), m0, acc[j][1]));
+            *reinterpret_cast<uint32_t*>(X + (size_t)(mt * 16 + g) * NP + p) = inb[j] ? v : 0u;
+          }
+          if (live1) {
+            const uint32_t v = Pack<T>::from_f2(fmaf(fminf(acc[j][2], 0.f), m1, acc[j][2]), fmaf(fminf(acc[j][3], 0.f), m1, acc[j][3]));
+            *reinterpret_cast<uint32_t*>(X + (size_t)(mt * 16 + g + 8) * NP + p) = inb[j] ? v : 0u;
+          }
         }
       }
     }
@@ -446,44 +453,49 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   }
   // (b) bilinear x2 of x_l -> AH rows [Chi, Chi+Cli): F.interpolate(scale_factor=2, align_corners=False) has the
   //     fixed taps dst 2j: (1/4, 3/4) of src (j-1, j); dst 2j+1: (3/4, 1/4) of src (j, j+1), indices clamped to the
-  //     image.  A task = 2 hi rows x 4 hi columns of one channel.
+  //     image.  A task = 4 hi rows x 4 hi columns of one channel (lo rows a-1 .. a+2, lo columns j0-1 .. j0+2): the 16
+  //     horizontal blends are shared by the 4 output rows; the 16-bit values go straight into the mixed-precision FMA
+  //     (weights 0.25 / 0.75 are exact in both 16-bit types, so the result equals the fp32 expression).
   {
     constexpr int quads_row = RWh >> 2;
-    constexpr int row_pairs = RHh >> 1;               // hi rows (2a, 2a+1), a < RHh/2 (an odd last row stays zero-filled)
-    constexpr int per_plane = row_pairs * quads_row;
+    constexpr int row_quads = RHh >> 2;               // hi rows 4b .. 4b+3; RHh = 4k + 1: the odd last row stays zero-filled
+    static_assert((RHh & 3) == 1, "hi region rows = 4k + 1");
+    constexpr int per_plane = row_quads * quads_row;
+    const uint16_t w25 = Pack<T>::bits(0.25f), w75 = Pack<T>::bits(0.75f);
     for (int i = tid; i < Cli * per_plane; i += NT) {
       const int c = i / per_plane, rem = i - c * per_plane;
-      const int a = rem / quads_row, q = rem - a * quads_row;
-      // hi rows (2a, 2a+1) <-> image rows gy = hy0-4+2a (even) and gy+1; lo image row of gy/2: li = ly0-2+a
-      const int li = ly0 - 2 + a;
+      const int b4 = rem / quads_row, q = rem - b4 * quads_row;
+      // hi rows 4b..4b+3 <-> image rows hy0-4+4b ..; lo image rows li = ly0-2+2b and li+1
+      const int li = ly0 - 2 + 2 * b4;
       auto clampy = [&](int y) { y = y < 0 ? 0 : (y > Hl - 1 ? Hl - 1 : y); int r = y - (ly0 - 2); return r < 0 ? 0 : (r > RHl - 1 ? RHl - 1 : r); };
-      const int ra = clampy(li - 1), rb = clampy(li), rc = clampy(li + 1);
       // hi cols 4q..4q+3 <-> image cols gx0 = hx0-4+4q = 2*j0; lo image cols j0-1 .. j0+2
       const int j0 = ((hx0 - 4) >> 1) + 2 * q;
       auto clampx = [&](int xx) { xx = xx < 0 ? 0 : (xx > Wl - 1 ? Wl - 1 : xx); int r = xx - (lx0 - 4); return r < 0 ? 0 : (r > RWl - 1 ? RWl - 1 : r); };
       const int c0 = clampx(j0 - 1), c1 = clampx(j0), c2 = clampx(j0 + 1), c3 = clampx(j0 + 2);
       const uint16_t* src = bufAl + (size_t)c * NPL;
-      float h[3][4];                                  // horizontally blended rows a-1, a, a+1 at the 4 hi columns
+      float h[4][4];                                  // horizontally blended lo rows li-1 .. li+2 at the 4 hi columns
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const uint16_t* r = src + (k == 0 ? ra : (k == 1 ? rb : rc)) * RWl;
-        const float v0 = Pack<T>::to_f(r[c0]), v1 = Pack<T>::to_f(r[c1]), v2 = Pack<T>::to_f(r[c2]), v3 = Pack<T>::to_f(r[c3]);
-        h[k][0] = 0.75f * v1 + 0.25f * v0;            // col 2*j0     : hx*v[x0=j0-1]... x0=j0-1 weight .25, x1=j0 weight .75
-        h[k][1] = 0.75f * v1 + 0.25f * v2;            // col 2*j0 + 1 : x0=j0 weight .75, x1=j0+1 weight .25
-        h[k][2] = 0.75f * v2 + 0.25f * v1;            // col 2*j0 + 2
-        h[k][3] = 0.75f * v2 + 0.25f * v3;            // col 2*j0 + 3
+      for (int k = 0; k < 4; ++k) {
+        const uint16_t* r = src + clampy(li - 1 + k) * RWl;
+        const uint16_t v0 = r[c0], v1 = r[c1], v2 = r[c2], v3 = r[c3];
+        h[k][0] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v0, w25, 0.f));   // col 2*j0    : (1/4, 3/4) of (j0-1, j0)
+        h[k][1] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v2, w25, 0.f));   // col 2*j0 + 1: (3/4, 1/4) of (j0, j0+1)
+        h[k][2] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v1, w25, 0.f));   // col 2*j0 + 2
+        h[k][3] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v3, w25, 0.f));   // col 2*j0 + 3
       }
-      uint2 o0, o1;                                   // hi row 2a (even): rows (li-1, li) w (.25, .75); row 2a+1: (li, li+1) w (.75, .25)
-      o0.x = Pack<T>::from_f2(0.75f * h[1][0] + 0.25f * h[0][0], 0.75f * h[1][1] + 0.25f * h[0][1]);
-      o0.y = Pack<T>::from_f2(0.75f * h[1][2] + 0.25f * h[0][2], 0.75f * h[1][3] + 0.25f * h[0][3]);
-      o1.x = Pack<T>::from_f2(0.75f * h[1][0] + 0.25f * h[2][0], 0.75f * h[1][1] + 0.25f * h[2][1]);
-      o1.y = Pack<T>::from_f2(0.75f * h[1][2] + 0.25f * h[2][2], 0.75f * h[1][3] + 0.25f * h[2][3]);
-      uint16_t* dst = bufAh + (size_t)(Chi + c) * NPH + (2 * a) * RWh + 4 * q;
-      *reinterpret_cast<uint2*>(dst) = o0;
-      *reinterpret_cast<uint2*>(dst + RWh) = o1;
+      // hi row 4b: lo rows (li-1, li) w (.25, .75); 4b+1: (li, li+1) w (.75, .25); 4b+2: (li, li+1) w (.25, .75); 4b+3: (li+1, li+2) w (.75, .25)
+      uint16_t* dst = bufAh + (size_t)(Chi + c) * NPH + (4 * b4) * RWh + 4 * q;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int km = rr < 2 ? 1 : 2, ko = rr == 0 ? 0 : (rr == 3 ? 3 : (rr == 1 ? 2 : 1));   // main (3/4) and other (1/4) row
+        uint2 o;
+        o.x = Pack<T>::from_f2(0.75f * h[km][0] + 0.25f * h[ko][0], 0.75f * h[km][1] + 0.25f * h[ko][1]);
+        o.y = Pack<T>::from_f2(0.75f * h[km][2] + 0.25f * h[ko][2], 0.75f * h[km][3] + 0.25f * h[ko][3]);
+        *reinterpret_cast<uint2*>(dst + rr * RWh) = o;
+      }
     }
     // rows of the hi planes not covered above (odd last row, padded tail): zero
-    constexpr int covered = (RHh >> 1) * 2 * RWh;
+    constexpr int covered = (RHh >> 2) * 4 * RWh;
     constexpr int tailh = (NPH - covered) >> 1;
     for (int i = tid; i < Cli * tailh; i += NT) {
       const int c = i / tailh, k = i - c * tailh;
@@ -497,43 +509,32 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
   if (Clo > 0) {
     const float* bl = A.bias_l;
     const float* sl = A.slope_l;
-    auto coord = [&](int p, int& cy, int& cx) {
+    auto coord = [&](int p) {                           // lo region pixel p (even): is the pair inside the lo image?
       const int ry = p / RWl;
-      cy = ly0 - 2 + ry; cx = lx0 - 4 + (p - ry * RWl);
-      if (ry >= RHl) cy = -1;
+      const int cy = ly0 - 2 + ry, cx = lx0 - 4 + (p - ry * RWl);
+      return ry < RHl && cy >= 0 && cy < Hl && cx >= 0 && cx < Wl;   // Wl and cx are even: cx + 1 is inside too
     };
     auto rowp = [&](int m, float& b, float& s) {
       if (m >= Clo) return false;
       b = __ldg(bl + m); s = __ldg(sl + m);
       return true;
     };
-    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1, float b, float s) {
-      const bool rin = gy >= 0 && gy < Hl;
-      const float o0 = (rin && gx >= 0 && gx < Wl) ? prelu(v0 + b, s) : 0.f;
-      const float o1 = (rin && gx + 1 >= 0 && gx + 1 < Wl) ? prelu(v1 + b, s) : 0.f;
-      *reinterpret_cast<uint32_t*>(bufAl + (size_t)m * NPL + p) = Pack<T>::from_f2(o0, o1);
-    };
-    gemm_pixels_inplace<T>(wsL, A.ML16, A.K8, bufAl, NPL, warp, nwarps, lane, coord, rowp, epi);
+    gemm_pixels_inplace<T>(wsL, A.ML16, A.K8, bufAl, NPL, warp, nwarps, lane, coord, rowp);
   }
   {
     const float* bh = A.bias_h;
     const float* sh = A.slope_h;
-    auto coord = [&](int p, int& cy, int& cx) {
+    auto coord = [&](int p) {
       const int ry = p / RWh;
-      cy = hy0 - 4 + ry; cx = hx0 - 4 + (p - ry * RWh);
-      if (ry >= RHh) cy = -1;
+      const int cy = hy0 - 4 + ry, cx = hx0 - 4 + (p - ry * RWh);
+      return ry < RHh && cy >= 0 && cy < H && cx >= 0 && cx < W;     // W even, cx even: cx + 1 is inside too
     };
     auto rowp = [&](int m, float& b, float& s) {
       if (m >= Cho) return false;
       b = __ldg(bh + m); s = __ldg(sh + m);
       return true;
     };
-    auto epi = [&](int m, int p, int gy, int gx, float v0, float v1, float b, float s) {
-      const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;      // W even, gx even: gx+1 is inside too
-      const float o0 = in ? prelu(v0 + b, s) : 0.f, o1 = in ? prelu(v1 + b, s) : 0.f;
-      *reinterpret_cast<uint32_t*>(bufAh + (size_t)m * NPH + p) = Pack<T>::from_f2(o0, o1);
-    };
-    gemm_pixels_inplace<T>(wsH, A.MH16, A.K8, bufAh, NPH, warp, nwarps, lane, coord, rowp, epi);
+    gemm_pixels_inplace<T>(wsH, A.MH16, A.K8, bufAh, NPH, warp, nwarps, lane, coord, rowp);
   }
   __syncthreads();
 
