@@ -357,27 +357,33 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     const int y0 = kl * (NPL >> 1), y1 = A.rowsAl * (NPL >> 1);
     for (int i = y0 + tid; i < y1; i += NT) reinterpret_cast<uint32_t*>(bufAl)[i] = 0u;
   }
-  // cp.async fallback loaders (8-byte chunks, zero fill outside the image)
+  // cp.async loaders (8-byte chunks, zero fill outside the image).  A thread owns one 4-pixel position of the region and
+  // walks the channels: validity, source offset and destination are computed once, a copy then costs a pointer bump.
+  // The lo positions are taken from the top thread indices, so the warps the hi loop leaves idle start with them.
   if (!A.tma_h && !A.first) {
     const uint16_t* xh = reinterpret_cast<const uint16_t*>(A.xh) + (size_t)n * Chi * H * W;
     constexpr int quads_row = RWh >> 2, quads_plane = NPH >> 2;
-    for (int i = tid; i < Chi * quads_plane; i += NT) {
-      const int c = i / quads_plane, pq = i - c * quads_plane;
+    for (int pq = tid; pq < quads_plane; pq += NT) {
       const int ry = pq / quads_row, rx = (pq - ry * quads_row) * 4;
       const int gy = hy0 - 4 + ry, gx = hx0 - 4 + rx;
       const bool ok = ry < RHh && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      cp_async8(bufAh + (size_t)c * NPH + pq * 4, ok ? xh + ((size_t)c * H + gy) * W + gx : xh, ok);
+      const uint16_t* src = ok ? xh + (size_t)gy * W + gx : xh;
+      const size_t sstep = ok ? (size_t)H * W : 0;
+      uint16_t* dst = bufAh + pq * 4;
+      for (int c = 0; c < Chi; ++c, src += sstep, dst += NPH) cp_async8(dst, src, ok);
     }
   }
   if (!A.tma_l && !A.first) {
     const uint16_t* xl = reinterpret_cast<const uint16_t*>(A.xl) + (size_t)n * Cli * Hl * Wl;
     constexpr int quads_row = RWl >> 2, quads_plane = NPL >> 2;
-    for (int i = tid; i < Cli * quads_plane; i += NT) {
-      const int c = i / quads_plane, pq = i - c * quads_plane;
+    for (int pq = NT - 1 - tid; pq < quads_plane; pq += NT) {
       const int ry = pq / quads_row, rx = (pq - ry * quads_row) * 4;
       const int gy = ly0 - 2 + ry, gx = lx0 - 4 + rx;
       const bool ok = ry < RHl && gy >= 0 && gy < Hl && gx >= 0 && gx < Wl;
-      cp_async8(bufAl + (size_t)c * NPL + pq * 4, ok ? xl + ((size_t)c * Hl + gy) * Wl + gx : xl, ok);
+      const uint16_t* src = ok ? xl + (size_t)gy * Wl + gx : xl;
+      const size_t sstep = ok ? (size_t)Hl * Wl : 0;
+      uint16_t* dst = bufAl + pq * 4;
+      for (int c = 0; c < Cli; ++c, src += sstep, dst += NPL) cp_async8(dst, src, ok);
     }
   }
   cp_async_wait_all();
@@ -433,23 +439,30 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     }
   } else {
   // ---- phase 1: resample both ways --------------------------------------------------------------------
-  // (a) max_pool2d 2x2 of x_h -> AL rows [Cli, Cli+Chi): two lo pixels per task from 2 hi rows x 4 hi pixels
+  // (a) max_pool2d 2x2 of x_h -> AL rows [Cli, Cli+Chi): two lo pixels per step from 2 hi rows x 4 hi pixels.  A thread
+  //     owns one lo pixel-pair position and a residue class of the channels: index arithmetic once per thread.
   if (Clo > 0) {
     constexpr int pairs_row = RWl >> 1, pairs_plane = NPL >> 1;
     constexpr int umax = RWh >> 2;
-    for (int i = tid; i < Chi * pairs_plane; i += NT) {
-      const int c = i / pairs_plane, pp = i - c * pairs_plane;
+    constexpr int groups = NT / pairs_plane > 0 ? NT / pairs_plane : 1;        // channel residue classes
+    const int pp = tid % pairs_plane, cg = tid / pairs_plane;
+    if (cg < groups) {
       const int ry = pp / pairs_row, u = pp - ry * pairs_row;
-      uint32_t v = 0u;
-      if (ry < RHl && 2 * ry + 1 < RHh && u >= 1 && u <= umax) {
-        const uint16_t* r0 = bufAh + (size_t)c * NPH + (2 * ry) * RWh + 4 * u - 4;
-        const uint2 a = *reinterpret_cast<const uint2*>(r0), b = *reinterpret_cast<const uint2*>(r0 + RWh);
-        const uint32_t m0 = Pack<T>::max2(a.x, b.x), m1 = Pack<T>::max2(a.y, b.y);
-        const float2 f0 = Pack<T>::to_f2(m0), f1 = Pack<T>::to_f2(m1);
-        v = Pack<T>::from_f2(fmaxf(f0.x, f0.y), fmaxf(f1.x, f1.y));
+      const bool ok = ry < RHl && 2 * ry + 1 < RHh && u >= 1 && u <= umax;
+      const uint16_t* r0 = bufAh + (size_t)cg * NPH + (ok ? (2 * ry) * RWh + 4 * u - 4 : 0);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(bufAl + (size_t)(Cli + cg) * NPL) + pp;
+      for (int c = cg; c < Chi; c += groups, r0 += (size_t)groups * NPH, dst += (size_t)groups * (NPL >> 1)) {
+        uint32_t v = 0u;
+        if (ok) {
+          const uint2 a = *reinterpret_cast<const uint2*>(r0), b = *reinterpret_cast<const uint2*>(r0 + RWh);
+          const uint32_t m0 = Pack<T>::max2(a.x, b.x), m1 = Pack<T>::max2(a.y, b.y);
+          // horizontal maximum of each 16-bit pair: max2 against the pair with its halves swapped
+          v = __byte_perm(Pack<T>::max2(m0, __byte_perm(m0, 0u, 0x1032)), Pack<T>::max2(m1, __byte_perm(m1, 0u, 0x1032)), 0x5410);
+        }
+        *dst = v;
       }
-      reinterpret_cast<uint32_t*>(bufAl + (size_t)(Cli + c) * NPL)[pp] = v;
     }
+    static_assert(pairs_plane <= NT, "one pass over the lo pixel pairs");
   }
   // (b) bilinear x2 of x_l -> AH rows [Chi, Chi+Cli): F.interpolate(scale_factor=2, align_corners=False) has the
   //     fixed taps dst 2j: (1/4, 3/4) of src (j-1, j); dst 2j+1: (3/4, 1/4) of src (j, j+1), indices clamped to the
@@ -462,9 +475,13 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
     static_assert((RHh & 3) == 1, "hi region rows = 4k + 1");
     constexpr int per_plane = row_quads * quads_row;
     const uint16_t w25 = Pack<T>::bits(0.25f), w75 = Pack<T>::bits(0.75f);
-    for (int i = tid; i < Cli * per_plane; i += NT) {
-      const int c = i / per_plane, rem = i - c * per_plane;
-      const int b4 = rem / quads_row, q = rem - b4 * quads_row;
+    // a thread owns one (row quad, column quad) position and a residue class of the channels: the clamped source
+    // offsets are computed once
+    constexpr int groups = NT / per_plane > 0 ? NT / per_plane : 1;
+    static_assert(per_plane <= NT, "one pass over the bilinear positions");
+    const int pos = tid % per_plane, cg = tid / per_plane;
+    if (cg < groups) {
+      const int b4 = pos / quads_row, q = pos - b4 * quads_row;
       // hi rows 4b..4b+3 <-> image rows hy0-4+4b ..; lo image rows li = ly0-2+2b and li+1
       const int li = ly0 - 2 + 2 * b4;
       auto clampy = [&](int y) { y = y < 0 ? 0 : (y > Hl - 1 ? Hl - 1 : y); int r = y - (ly0 - 2); return r < 0 ? 0 : (r > RHl - 1 ? RHl - 1 : r); };
@@ -472,26 +489,31 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
       const int j0 = ((hx0 - 4) >> 1) + 2 * q;
       auto clampx = [&](int xx) { xx = xx < 0 ? 0 : (xx > Wl - 1 ? Wl - 1 : xx); int r = xx - (lx0 - 4); return r < 0 ? 0 : (r > RWl - 1 ? RWl - 1 : r); };
       const int c0 = clampx(j0 - 1), c1 = clampx(j0), c2 = clampx(j0 + 1), c3 = clampx(j0 + 2);
-      const uint16_t* src = bufAl + (size_t)c * NPL;
-      float h[4][4];                                  // horizontally blended lo rows li-1 .. li+2 at the 4 hi columns
+      int ro[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint16_t* r = src + clampy(li - 1 + k) * RWl;
-        const uint16_t v0 = r[c0], v1 = r[c1], v2 = r[c2], v3 = r[c3];
-        h[k][0] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v0, w25, 0.f));   // col 2*j0    : (1/4, 3/4) of (j0-1, j0)
-        h[k][1] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v2, w25, 0.f));   // col 2*j0 + 1: (3/4, 1/4) of (j0, j0+1)
-        h[k][2] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v1, w25, 0.f));   // col 2*j0 + 2
-        h[k][3] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v3, w25, 0.f));   // col 2*j0 + 3
-      }
-      // hi row 4b: lo rows (li-1, li) w (.25, .75); 4b+1: (li, li+1) w (.75, .25); 4b+2: (li, li+1) w (.25, .75); 4b+3: (li+1, li+2) w (.75, .25)
-      uint16_t* dst = bufAh + (size_t)(Chi + c) * NPH + (4 * b4) * RWh + 4 * q;
+      for (int k = 0; k < 4; ++k) ro[k] = clampy(li - 1 + k) * RWl;
+      const uint16_t* src = bufAl + (size_t)cg * NPL;
+      uint16_t* dst = bufAh + (size_t)(Chi + cg) * NPH + (4 * b4) * RWh + 4 * q;
+      for (int c = cg; c < Cli; c += groups, src += (size_t)groups * NPL, dst += (size_t)groups * NPH) {
+        float h[4][4];                                // horizontally blended lo rows li-1 .. li+2 at the 4 hi columns
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int km = rr < 2 ? 1 : 2, ko = rr == 0 ? 0 : (rr == 3 ? 3 : (rr == 1 ? 2 : 1));   // main (3/4) and other (1/4) row
-        uint2 o;
-        o.x = Pack<T>::from_f2(0.75f * h[km][0] + 0.25f * h[ko][0], 0.75f * h[km][1] + 0.25f * h[ko][1]);
-        o.y = Pack<T>::from_f2(0.75f * h[km][2] + 0.25f * h[ko][2], 0.75f * h[km][3] + 0.25f * h[ko][3]);
-        *reinterpret_cast<uint2*>(dst + rr * RWh) = o;
+        for (int k = 0; k < 4; ++k) {
+          const uint16_t* r = src + ro[k];
+          const uint16_t v0 = r[c0], v1 = r[c1], v2 = r[c2], v3 = r[c3];
+          h[k][0] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v0, w25, 0.f));   // col 2*j0    : (1/4, 3/4) of (j0-1, j0)
+          h[k][1] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v2, w25, 0.f));   // col 2*j0 + 1: (3/4, 1/4) of (j0, j0+1)
+          h[k][2] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v1, w25, 0.f));   // col 2*j0 + 2
+          h[k][3] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v3, w25, 0.f));   // col 2*j0 + 3
+        }
+        // hi row 4b: lo rows (li-1, li) w (.25, .75); 4b+1: (li, li+1) w (.75, .25); 4b+2: (li, li+1) w (.25, .75); 4b+3: (li+1, li+2) w (.75, .25)
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int km = rr < 2 ? 1 : 2, ko = rr == 0 ? 0 : (rr == 3 ? 3 : (rr == 1 ? 2 : 1));   // main (3/4) and other (1/4) row
+          uint2 o;
+          o.x = Pack<T>::from_f2(0.75f * h[km][0] + 0.25f * h[ko][0], 0.75f * h[km][1] + 0.25f * h[ko][1]);
+          o.y = Pack<T>::from_f2(0.75f * h[km][2] + 0.25f * h[ko][2], 0.75f * h[km][3] + 0.25f * h[ko][3]);
+          *reinterpret_cast<uint2*>(dst + rr * RWh) = o;
+        }
       }
     }
     // rows of the hi planes not covered above (odd last row, padded tail): zero
