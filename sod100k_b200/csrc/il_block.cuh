@@ -412,29 +412,45 @@ il_block_kernel(const __grid_constant__ IlArgs A, const __grid_constant__ CUtens
       *reinterpret_cast<float4*>(img + (c * IH + iy) * IW + ix) = v;
     }
     __syncthreads();
-    // hi planes: row k = (ci, ky, kx) holds the image shifted by (ky-1, kx-1); region (ry, rx) = image (hy0-4+ry, hx0-4+rx)
-    for (int i = tid; i < Chi * (NPH / 2); i += NT) {
-      const int k = i / (NPH / 2), pp = i - k * (NPH / 2);
-      const int ci = k / 9, t9 = k - ci * 9, ky = t9 / 3, kx = t9 - ky * 3;
+    // hi planes: row k = (ci, ky, kx) holds the image shifted by (ky-1, kx-1); region (ry, rx) = image (hy0-4+ry, hx0-4+rx).
+    // A thread owns pixel-pair positions and walks the 9 * Ci planes with compile-time tap offsets.
+    const int Cin = Chi / 9;
+    for (int pp = tid; pp < NPH / 2; pp += NT) {
       const int ry = (2 * pp) / RWh, rx = 2 * pp - ry * RWh;
-      const float* src = img + (ci * IH + ry + 1 + ky) * IW + rx + 7 + kx;
-      reinterpret_cast<uint32_t*>(bufAh + (size_t)k * NPH)[pp] = Pack<T>::from_f2(src[0], src[1]);
+      const float* base = img + (ry + 1) * IW + rx + 7;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(bufAh) + pp;
+      for (int ci = 0; ci < Cin; ++ci, base += IH * IW) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx, dst += NPH / 2) {
+            const float* src = base + ky * IW + kx;
+            *dst = Pack<T>::from_f2(src[0], src[1]);
+          }
+      }
     }
-    // lo planes: 2x2 max-pool of the image, shifted by (ky-1, kx-1) lo pixels, zero outside the lo image (conv padding)
+    // lo planes: 2x2 max-pool of the image, shifted by (ky-1, kx-1) lo pixels, zero outside the lo image (conv padding).
+    // A thread owns lo pixels: the 3 x 3 pooled neighbourhood is computed once per input channel and fans out to 9 planes.
     if (Clo > 0) {
       constexpr int rl_ = TH / 2 + 4;
-      for (int i = tid; i < Chi * NPL; i += NT) {
-        const int k = i / NPL, p = i - k * NPL;
-        const int ci = k / 9, t9 = k - ci * 9, ky = t9 / 3, kx = t9 - ky * 3;
+      for (int p = NT - 1 - tid; p < NPL; p += NT) {
         const int ry = p / RWl, rx = p - ry * RWl;
-        const int gy = ly0 - 3 + ry + ky, gx = lx0 - 5 + rx + kx;
-        float v = 0.f;
-        if (ry < rl_ && gy >= 0 && gy < Hl && gx >= 0 && gx < Wl) {
-          const float* src = img + (ci * IH + 2 * (ry + ky)) * IW + 2 * (rx + kx) + 2;
-          v = fmaxf(fmaxf(src[0], src[1]), fmaxf(src[IW], src[IW + 1]));
+        const float* base = img + (2 * ry) * IW + 2 * rx + 2;
+        uint16_t* dst = bufAl + p;
+        for (int ci = 0; ci < Cin; ++ci, base += IH * IW) {
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx, dst += NPL) {
+              const int gy = ly0 - 3 + ry + ky, gx = lx0 - 5 + rx + kx;
+              float v = 0.f;
+              if (ry < rl_ && gy >= 0 && gy < Hl && gx >= 0 && gx < Wl) {
+                const float* src = base + 2 * ky * IW + 2 * kx;
+                v = fmaxf(fmaxf(src[0], src[1]), fmaxf(src[IW], src[IW + 1]));
+              }
+              *dst = (uint16_t)(Pack<T>::from_f2(v, 0.f) & 0xffffu);
+            }
         }
-        uint16_t h = (uint16_t)(Pack<T>::from_f2(v, 0.f) & 0xffffu);
-        bufAl[(size_t)k * NPL + p] = h;
       }
     }
   } else {
