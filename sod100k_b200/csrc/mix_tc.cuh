@@ -86,6 +86,25 @@ __device__ __forceinline__ void bilinear_up2_pair_f32(const float* plane, int Hs
   v1 += wa * (0.75f * a0 + 0.25f * ap) + wb * (0.75f * b0 + 0.25f * bp);
 }
 
+// Up-sampling by a multiple of 4 of an fp32 plane for the output pixel pair (ox even, ox+1): both pixels fall between the same
+// two source columns (and the same two rows), so the four source values are loaded once; the blend is bilinear_up()'s
+// expression with its own weights, i.e. the same values.
+__device__ __forceinline__ void bilinear_up4n_pair_f32(const float* plane, int Hs, int Ws, int up, int oy, int ox, float& v0, float& v1) {
+  const float inv = 1.0f / (float)up;
+  float sy = ((float)oy + 0.5f) * inv - 0.5f, sa = ((float)ox + 0.5f) * inv - 0.5f, sb = ((float)(ox + 1) + 0.5f) * inv - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sa = sa < 0.f ? 0.f : sa;
+  sb = sb < 0.f ? 0.f : sb;
+  const int y0 = (int)sy, x0 = (int)sa;                    // (int)sb == x0 for even ox and up % 4 == 0
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, hy = 1.f - ly;
+  const float la = sa - (float)x0, ha = 1.f - la, lb = sb - (float)x0, hb = 1.f - lb;
+  const float *r0 = plane + (size_t)y0 * Ws, *r1 = plane + (size_t)y1 * Ws;
+  const float v00 = r0[x0], v01 = r0[x1], v10 = r1[x0], v11 = r1[x1];
+  v0 += hy * (ha * v00 + la * v01) + ly * (ha * v10 + la * v11);
+  v1 += hy * (hb * v00 + lb * v01) + ly * (hb * v10 + lb * v11);
+}
+
 // Same as fetch_pooled() for a 16-bit source of type T with an even row length: pixel pairs come in as one
 // 32-bit load (a 2x2 average = 2 loads, a 2x2 max of plain pixels = 2 loads), no per-load dtype dispatch.
 template <typename T>
@@ -328,6 +347,8 @@ __global__ void __launch_bounds__(kTcThreads, (MT * R <= 2 ? 3 : 2)) mix_tc_kern
           const int64_t plane = ((int64_t)n * P.C + P.c0 + (m - P.cout0)) * (int64_t)P.H * P.W;
           if (P.up == 2 && P.dtype == DT_F32 && ox + 1 < A.W) {
             bilinear_up2_pair_f32(reinterpret_cast<const float*>(P.src) + plane, P.H, P.W, oy, ox, v0, v1);
+          } else if (P.up >= 4 && (P.up & 3) == 0 && P.dtype == DT_F32 && ox + 1 < A.W) {
+            bilinear_up4n_pair_f32(reinterpret_cast<const float*>(P.src) + plane, P.H, P.W, P.up, oy, ox, v0, v1);
           } else {
             v0 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox);
             if (ox + 1 < A.W) v1 += bilinear_up(P.src, P.dtype, plane, P.H, P.W, P.up, oy, ox + 1);
