@@ -345,7 +345,10 @@ def run_train(a):
     for _ in range(a.warmup):
         step()
     clocks = ClockSampler(local) if rank == 0 else None
+    from sod100k_b200 import train_ops
+    launches0 = train_ops.LAUNCHES
     ms = timed(step, a.steps)
+    train_launches = train_ops.LAUNCHES - launches0          # csnet_train_* kernels of the timed steps (memsets not counted)
     clk = clocks.stop() if clocks else None
     e2e()
     ms_e2e = timed(e2e, a.steps)
@@ -364,7 +367,7 @@ def run_train(a):
                        f"{tr.flat.bucket.numel()} fp32 gradients", "l2": "activations exceed L2"},
             "clocks": clk,
             "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": int((xh.numel() + th.numel()) * 4), "d2h_bytes_per_step": 4},
-            "gpu_launches": None,
+            "gpu_launches": train_launches,
             "roofline": {"bound": "hbm", "achieved": ips / world * train_bytes / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": ips / world * train_bytes / 1e9 / peak, "traffic": None,
                          "kernel": "whole train step (module-fused algorithmic bytes, fp32)"}}))
