@@ -125,6 +125,8 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t* r, const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
 }
 __device__ __forceinline__ float prelu(float v, float s) { return v > 0.f ? v : s * v; }
+// the same with m = slope - 1 precomputed: v + m * min(v, 0) — two instructions instead of three
+__device__ __forceinline__ float prelu_m1(float v, float m) { return fmaf(fminf(v, 0.f), m, v); }
 
 // ---- TMA / mbarrier / cp.async ------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -233,7 +235,7 @@ __device__ __forceinline__ void dw_task(int task, const uint16_t* in, uint16_t* 
     wf[i] = __ldg(P.w + c * 9 + i);
     wh[i] = Pack<T>::bits(wf[i]);
   }
-  const float bias = __ldg(P.b + c), slope = __ldg(P.s + c);
+  const float bias = __ldg(P.b + c), slope_m1 = __ldg(P.s + c) - 1.f;
   const uint16_t* plane = in + c * NP + x;
   const int gx = ox0 + x;
   const bool col_in = gx >= 0 && gx < imgW;            // imgW % 4 == 0 and gx % 4 == 0: a group is all in or all out
@@ -266,7 +268,7 @@ __device__ __forceinline__ void dw_task(int task, const uint16_t* in, uint16_t* 
             if constexpr (kMixed) v = Pack<T>::fma16(rows[i + dy][k + dx], wh[dy * 3 + dx], v);
             else v = fmaf(Pack<T>::to_f(rows[i + dy][k + dx]), wf[dy * 3 + dx], v);
           }
-        o[k] = prelu(v, slope);
+        o[k] = prelu_m1(v, slope_m1);
       }
       const int gy = oy0 + r;
       const bool in_img = col_in && gy >= 0 && gy < imgH;
