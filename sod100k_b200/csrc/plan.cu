@@ -845,8 +845,15 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
     const int c = (N + n_equal - 1) / n_equal;
     for (int n0 = 0; n0 < N; n0 += c) sizes[n_sizes++] = (N - n0) < c ? (N - n0) : c;
   } else {
-    const int edge = N / 8;
-    sizes[n_sizes++] = edge; sizes[n_sizes++] = N - 2 * edge; sizes[n_sizes++] = edge;
+    // first / last chunk in 256ths of the batch (CSNET_HOST_SPLIT="first,last", 0 = no such chunk); default 32 / 32
+    static int f256 = 32, l256 = 32;
+    static const bool parsed = [] { const char* e = getenv("CSNET_HOST_SPLIT"); if (e) sscanf(e, "%d,%d", &f256, &l256); return true; }();
+    (void)parsed;
+    const int first = N * f256 / 256, last = N * l256 / 256;
+    if (first > 0 && first < N) sizes[n_sizes++] = first;
+    const int mid = N - (first > 0 && first < N ? first : 0) - (last > 0 && last < N - first ? last : 0);
+    sizes[n_sizes++] = mid;
+    if (last > 0 && last < N - first) sizes[n_sizes++] = last;
   }
   int chunk = 0;
   for (int i = 0; i < n_sizes; ++i) chunk = sizes[i] > chunk ? sizes[i] : chunk;
