@@ -60,3 +60,34 @@ def test_emulated_input_side_upsample_paths():
     assert any(q.ksize == 1 and q.up > 1 for o in prog.ops for q in o.paths)
     y, _ = emu.run(prog, x)
     assert np.abs(y - _oracle(cfg, sd, x)).max() <= 1e-4
+
+
+def test_emulated_resample_paths_pool_upsample_and_copy():
+    """A `ksize = 0` path adds its source avg-pooled (pre_avg), max-pooled (pool), bilinearly up-sampled (up) or as it is:
+    the single-path MIX ops the compiler emits for materialised branches (generic_ops.cuh: mix_finish).  fp32 program on
+    the host emulation against torch."""
+    import torch
+    import torch.nn.functional as F
+    from sod100k_b200 import ir
+    b = ir.Builder()
+    C_, H, W = 3, 16, 24
+    x = b.tensor(C_, H, W, ir.F32, external=0, name="x")
+    outs = {
+        "avg": (b.tensor(C_, H // 2, W // 2, ir.F32, external=1), ir.Path(x, C_, C_, ksize=0, pre_avg=1)),
+        "max": (b.tensor(C_, H // 2, W // 2, ir.F32, external=2), ir.Path(x, C_, C_, ksize=0, pool=2)),
+        "max4": (b.tensor(C_, H // 4, W // 4, ir.F32, external=3), ir.Path(x, C_, C_, ksize=0, pool=4)),
+        "up2": (b.tensor(C_, H * 2, W * 2, ir.F32, external=4), ir.Path(x, C_, C_, ksize=0, up=2)),
+        "copy": (b.tensor(C_, H, W, ir.F32, external=5), ir.Path(x, C_, C_, ksize=0)),
+    }
+    for name, (t, path) in outs.items():
+        b.op(ir.OP_MIX, t, [path], name=name)
+    prog = b.finish(reuse=False)
+    rng = np.random.default_rng(5)
+    xv = rng.standard_normal((2, C_, H, W)).astype(np.float32)
+    arrays = [xv] + [np.zeros((2, prog.tensors[t].C, prog.tensors[t].H, prog.tensors[t].W), np.float32) for t, _ in outs.values()]
+    emu.run_ext(prog, arrays, 2)
+    xt = torch.from_numpy(xv)
+    want = [F.avg_pool2d(xt, 2), F.max_pool2d(xt, 2), F.max_pool2d(xt, 4),
+            F.interpolate(xt, scale_factor=2, mode="bilinear", align_corners=False), xt]
+    for (name, _), got, ref in zip(outs.items(), arrays[1:], want):
+        assert np.abs(got - ref.numpy()).max() <= 1e-6, name

@@ -129,3 +129,27 @@ def test_simplesum_reproduces_the_reference_counters():
         assert p == params and abs(f / 1e9 - gflops) < 5e-5
         assert "Number of params" in out.getvalue() and "Number of FLOPs" in out.getvalue()
         assert not any(x._forward_hooks for x in m.modules())
+
+
+def test_lowering_choices_by_dtype():
+    """16-bit programs use the fused forms (ILBlock kernels incl. the stem, cls_layer folded into fuse1x1, pooled /
+    up-sampled branches materialised once); fp32 programs — the 1e-3 parity path — keep the reference's op order."""
+    from sod100k_b200 import compiler, ir
+    from tests import fixtures
+    cfg, sd = fixtures.checkpoint("csnet-L-x2")
+    p16 = compiler.compile_csnet(cfg, sd, 224, 224, "fp16")
+    kinds = [o.kind for o in p16.ops]
+    names = [o.name for o in p16.ops]
+    assert kinds.count(ir.OP_ILBLOCK) == 12 and names[0] == "stage0.0" and p16.ops[0].paths[0].ksize == 3      # stem form first
+    assert kinds.count(ir.OP_MIXPROJ) == 1 and "cls_layer" not in names
+    assert sum(".pool" in n for n in names) >= 4 and sum(".maxpool" in n for n in names) >= 5 and sum(".up" in n for n in names) == 2
+    computed = [o.name for o in p16.ops if o.kind != ir.OP_ILBLOCK for q in o.paths if q.ksize > 0 and (q.pre_avg or q.pool > 1 or q.up > 1)]
+    assert computed == [], "every conv path of a 16-bit program reads a plain tensor"
+    assert len(p16.ops) == 74
+    p32 = compiler.compile_csnet(cfg, sd, 224, 224, "fp32")
+    assert all(o.kind in (ir.OP_MIX, ir.OP_DW) for o in p32.ops) and "cls_layer" in [o.name for o in p32.ops]
+    assert not any("pool" in o.name or ".up" in o.name for o in p32.ops)
+    # gating by name: only the requested module changes
+    p = compiler.compile_csnet(cfg, sd, 224, 224, "fp16", fuse={"stage2.0.conv1x1"}, tensor_core=False)
+    pooled = [o.name for o in p.ops if "pool" in o.name]
+    assert len(pooled) == 3 and all(n.startswith("stage2.0.conv1x1.") for n in pooled)
