@@ -1,12 +1,21 @@
-"""Tiny forward for compute-sanitizer runs."""
+"""Tiny forwards for compute-sanitizer runs: fp32 generic path, fp16 / bf16 fused path at two sizes (boundary tiles only and
+interior + boundary tiles), the pipelined host call, and the device SalMetric."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from sod100k_b200 import checkpoints, synth
-for tag, dt in (("csnet-L-x2", "fp32"), ("csnet-L-x1", "fp16")):
+from sod100k_b200 import checkpoints, synth, salmetric
+for tag, dt, hw in (("csnet-L-x2", "fp32", (64, 96)), ("csnet-L-x1", "fp16", (64, 96)), ("csnet-L-x2", "fp16", (224, 224)),
+                    ("csnet-L-x2", "bf16", (96, 160))):
     m, cfg, sd = checkpoints.build_from_npz(tag)
     m.cuda().eval().set_precision(dt)
     with torch.no_grad():
-        y = m(torch.from_numpy(synth.randn_images(2, 64, 96, 5)).cuda())
+        y = m(torch.from_numpy(synth.randn_images(2, hw[0], hw[1], 5)).cuda())
     torch.cuda.synchronize()
-    print(tag, dt, float(y.mean()))
+    print(tag, dt, hw, float(y.mean()))
+with torch.no_grad():
+    x = torch.from_numpy(synth.randn_images(70, 64, 64, 6)).pin_memory()
+    y = m.engine().forward_host(x)
+torch.cuda.synchronize()
+sm = salmetric.SalMetric()
+sm.update(torch.rand(3, 1, 40, 56, device="cuda"), (torch.rand(3, 1, 40, 56, device="cuda") > 0.5).to(torch.uint8) * 255)
+print("salmetric", sm.compute()["max_f"])
