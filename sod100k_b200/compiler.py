@@ -91,6 +91,7 @@ class _Lowering:
         self.tensor_core = tensor_core       # True / False / collection of op-name prefixes allowed on the fast kernels
         # 1x1 up-paths with cin <= cout: up-sample the conv input instead of its output (default: 16-bit programs)
         self.upsample_inputs = (act_dtype != ir.F32) if upsample_inputs is None else upsample_inputs
+        self._pooled: Dict[tuple, int] = {}            # (source tensor, factor) -> materialised max-pooled tensor
         self.b = ir.Builder()
         self._wmax: Dict[int, float] = {}
 
@@ -207,8 +208,6 @@ class _Lowering:
     def maxpooled(self, x: int, f: int, prefix: str) -> int:
         """max_pool2d(f, f) of a whole 16-bit tensor as its own bandwidth-bound op(s) (a chain of 2x2 steps, exact for a
         maximum), cached per source: several conv paths (oct_fuse.fuse.1 / .2) read the same pooled branch."""
-        if not hasattr(self, "_pooled"):
-            self._pooled: Dict[tuple, int] = {}
         if f == 1:
             return x
         key = (x, f)
