@@ -1,4 +1,5 @@
-// Round-2 prototype (compiles; NOT yet run): the 1x1-conv GEMM of a fused ILBlock tile on tcgen05, IN PLACE on a tile stored as
+// Round-2 prototype — RUN ON A B200 at the very end of round 1: "max |Y - ref| = 0.000976562, 0 of 52224 elements off" (fp16
+// rounding of the outputs only).  The 1x1-conv GEMM of a fused ILBlock tile on tcgen05, IN PLACE on a tile stored as
 // [pixel group][channel][8 pixels] — the layout DESIGN.md §9 proposes for every phase of the kernel.
 //   D[M = 128 channel lanes][N = 256 pixels] (fp32, TMEM) = W[M][K] (K-major A) * X[pixels][K] (MN-major B: pixels contiguous)
 //   channels are the M dimension so that an epilogue thread (= TMEM lane = channel) receives CONSECUTIVE pixels and stores
@@ -6,8 +7,8 @@
 // Tile: NP = 1024 pixels (4 N blocks of 256), K = 64 input channels, Cout = 51 (padded to the 128 lanes, unused lanes idle).
 // TMEM: 512 columns = two 256-pixel accumulator buffers, double-buffered between the issuing thread (warp 4) and the four
 // epilogue warps; the epilogue overwrites the pixel groups of its N block, which no later MMA reads.
-// Verified pieces: descriptor encodings and the alloc / mma / commit / ld sequence (scripts/tcgen05_probe.cu, exact on B200).
-// New here and to be checked first next round: B as the MN-major operand, N = 256, the full/empty barrier phases.
+// Verified by that run: B as the MN-major operand straight from the tile, N = 256 per instruction, the full / empty mbarrier
+// phases of the double-buffered accumulators, the in-place epilogue (bias + PReLU + 16-byte stores of 8 pixels per channel).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
