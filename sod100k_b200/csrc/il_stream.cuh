@@ -1,0 +1,457 @@
+// il_stream.cuh — the 1x1-kind ILBlock as ONE persistent, streaming kernel on the Blackwell data path
+// (reference: ILBlock.forward, CSNet/model/csnet.py:72-76 = gOctaveCBR :778-792 over gOctaveConv.forward :664-726,
+// then two SimplifiedGOctConvBR.forward :838-851).
+//
+// A CTA walks a contiguous range of the batch's (image, 4-row chunk) sequence top to bottom, full image width:
+//
+//   TMA        x_h rows [4c, 4c+4) and x_l rows [2c, 2c+2) arrive by cp.async.bulk.tensor.5d straight in the
+//              tensor-core operand layout  [row][8-pixel group][channel slot][8 px]  (a core matrix of the MN-major
+//              A operand = 8 channel slots x 16 bytes); the map splits W into (W/8, 8), channel slots past the
+//              tensor's C are zero-filled by the TMA unit = the K padding of the GEMM.  2 hi / 4 lo stages.
+//   resample   bilinear x2 of x_l -> slots [Chi, Chi+Cli) of the hi chunk (lo -> hi path, csnet.py:702-707; the
+//              up-sample commutes with the 1x1 conv), max-pool 2x2 of x_h -> slots [Cli, Cli+Chi) of the lo chunk
+//              (hi -> lo path, :709-712).
+//   GEMM       one elected thread issues tcgen05.mma (kind::f16, M = 128 pixels, N = ru16(Cout), K = 16 per
+//              instruction) per 16 pixel groups; fp32 accumulators of the whole chunk live in TMEM.
+//   epilogue   tcgen05.ld (a thread = a pixel), + bias, PReLU, 16-bit, written IN PLACE over the chunk (T1).
+//   dw tail    a thread owns (channel, 8-pixel column) for the whole walk and keeps the 3-row windows of T1 and T2
+//              in registers: dw3x3+BN+PReLU twice with no halo recomputation in y, no shared-memory round trip for
+//              T2, 16-byte coalesced stores of the block output.  (mixed-precision FMA: fp16 x fp16 + fp32.)
+//
+// No halo is ever re-read from HBM (except one warm-up chunk where a CTA's range starts inside an image); the
+// work split is a flat division of N * H/4 chunks over the SMs.  Needs W % 16 == 0, H % 4 == 0,
+// Cho * W/8 + Clo * W/16 <= 768 dw threads, K = Chi + Cli <= 64.  Other shapes use il_block.cuh.
+#pragma once
+#include "il_block.cuh"
+
+namespace csnet {
+
+constexpr int kIlsMaxThreads = 768;
+constexpr int kIlsMaxC = 64;          // output channels per branch (epilogue parameter tables in the kernel arguments)
+constexpr int kIlsHiStages = 2, kIlsLoStages = 4;
+
+struct IlsArgs {
+  void* yh;
+  void* yl;                           // nullptr when Clo == 0
+  const uint32_t* wh;                 // packed 16-bit [NH][K8]  columns [x_h | up(x_l)]
+  const uint32_t* wl;                 // packed 16-bit [NL][K8]  columns [x_l | pool(x_h)]
+  DwParams dw1h, dw1l, dw2h, dw2l;
+  float bias_h[kIlsMaxC], sm1_h[kIlsMaxC], bias_l[kIlsMaxC], sm1_l[kIlsMaxC];   // conv bias, PReLU slope - 1
+  int32_t N, H, W;
+  int32_t Chi, Cli, Cho, Clo;
+  int32_t K8, K16, NH, NL;            // NH / NL = ru16(Cho / Clo): the N of the MMAs (NL = 0 without a lo output)
+  int32_t SH, SL, ST;                 // channel slots per pixel group: hi chunk, lo chunk, T1L buffer (all odd)
+  int32_t GH, GL;                     // pixel groups per row: W/8, W/16
+  int32_t cpi, total_chunks;          // chunks per image (H/4), N * cpi
+  int32_t hi_warps, lo_warps;         // warps of the depthwise tail
+  int32_t hi_stage_bytes, lo_stage_bytes;
+  int32_t off_xl, off_xh, off_t1l, off_wbh, off_wbl, off_bar, off_zero, smem_bytes;
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// parity wait with a wall-clock bound: a lost TMA / MMA must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // shared-memory matrix descriptor, no swizzle, version 1 (sm_100): start / LBO / SBO in 16-byte units
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint16_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;\n" ::"r"(a), "h"(v) : "memory"); }
+
+// element j of a row of packed 16-bit pairs
+__device__ __forceinline__ uint16_t h16(const uint32_t* row, int j) { return (j & 1) ? (uint16_t)(row[j >> 1] >> 16) : (uint16_t)row[j >> 1]; }
+
+// One step of the depthwise tail: T1 row r arrives (n1: pixels x0-2 .. x0+9 of this thread's channel), T2 row r-1 is
+// made from T1 rows r-2, r-1, r (10 pixels: x0-1 .. x0+8), the block output row r-2 from T2 rows r-3, r-2, r-1.
+template <typename T>
+__device__ __forceinline__ void ils_dw_push(uint32_t (&t1)[2][6], uint32_t (&t2)[2][5], const uint32_t (&n1)[6],
+                                            const uint32_t (&w1)[5], float b1, float s1, const uint32_t (&w2)[5], float b2, float s2,
+                                            bool make_t2, float mL, float mR, bool make_out, uint16_t* out) {
+  uint32_t q[5];
+  if (make_t2) {
+#pragma unroll
+    for (int i = 0; i < 10; i += 2) {
+      float v0 = b1, v1 = b1;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const uint32_t* row = dy == 0 ? t1[0] : (dy == 1 ? t1[1] : n1);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint16_t w = h16(w1, dy * 3 + dx);
+          v0 = Pack<T>::fma16(h16(row, i + dx), w, v0);
+          v1 = Pack<T>::fma16(h16(row, i + 1 + dx), w, v1);
+        }
+      }
+      v0 = prelu_m1(v0, s1);
+      v1 = prelu_m1(v1, s1);
+      if (i == 0) v0 *= mL;          // T2 at x0-1 is conv padding when the column is the image's first
+      if (i == 8) v1 *= mR;          // T2 at x0+8 likewise on the right
+      q[i >> 1] = Pack<T>::from_f2(v0, v1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) q[i] = 0u;
+  }
+  if (make_out) {
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      float v0 = b2, v1 = b2;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const uint32_t* row = dy == 0 ? t2[0] : (dy == 1 ? t2[1] : q);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint16_t w = h16(w2, dy * 3 + dx);
+          v0 = Pack<T>::fma16(h16(row, k + dx), w, v0);
+          v1 = Pack<T>::fma16(h16(row, k + 1 + dx), w, v1);
+        }
+      }
+      o[k >> 1] = Pack<T>::from_f2(prelu_m1(v0, s2), prelu_m1(v1, s2));
+    }
+    *reinterpret_cast<uint4*>(out) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { t1[0][i] = t1[1][i]; t1[1][i] = n1[i]; }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { t2[0][i] = t2[1][i]; t2[1][i] = q[i]; }
+}
+
+// Epilogue of one 128-pixel accumulator block: this thread's pixel (TMEM lane), channels [0, C): bias, PReLU, 16-bit store
+// at dst + 16 * channel.  bias / sm1 live in the kernel-argument constant bank (indexed by unrolled constants).
+template <typename T>
+__device__ __forceinline__ void ils_epilogue_block(uint32_t taddr, uint32_t dst, int C, bool valid, const float (&bias)[kIlsMaxC],
+                                                   const float (&sm1)[kIlsMaxC]) {
+#pragma unroll
+  for (int cc = 0; cc < kIlsMaxC / 16; ++cc) {
+    if (cc * 16 < C) {                                                 // warp-uniform
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)(cc * 16), r);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int ch = cc * 16 + j;
+        if (ch < C) {
+          const float v = prelu_m1(__uint_as_float(r[j]) + bias[ch], sm1[ch]);
+          if (valid) sts16(dst + (uint32_t)ch * 16u, Pack<T>::bits(v));
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kIlsMaxThreads, 1)
+il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t XL = sbase + A.off_xl, XH = sbase + A.off_xh, T1L = sbase + A.off_t1l, WBH = sbase + A.off_wbh,
+                 WBL = sbase + A.off_wbl, BAR = sbase + A.off_bar, ZERO = sbase + A.off_zero;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));      // generic pointer to the same place
+  // barriers: [0,2) hi stage full, [2,6) lo stage full, [6] MMAs of the chunk done; then the TMEM base slot
+  const uint32_t bar_h = BAR, bar_l = BAR + 16, bar_m = BAR + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + A.off_bar + 64);
+
+  const int H = A.H, W = A.W, Hl = H >> 1, Wl = W >> 1;
+  const int Chi = A.Chi, Cli = A.Cli, Cho = A.Cho, Clo = A.Clo;
+  const int GH = A.GH, GL = A.GL, SH = A.SH, SL = A.SL, ST = A.ST, NH = A.NH, NL = A.NL, K16 = A.K16;
+  const int cpi = A.cpi;
+
+  // ---- one-time setup -----------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(BAR + 8 * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(BAR + 64) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  // weights -> K-major B operand: core matrices [n group][k group][8 n][8 k]
+  {
+    uint16_t* wb = reinterpret_cast<uint16_t*>(gbase + A.off_wbh);
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(A.wh);
+    for (int i = tid; i < NH * K16; i += nthreads) {
+      const int n = i / K16, k = i - n * K16;
+      wb[(((n >> 3) * (K16 >> 3) + (k >> 3)) * 8 + (n & 7)) * 8 + (k & 7)] = k < A.K8 ? src[n * A.K8 + k] : (uint16_t)0;
+    }
+    if (NL > 0) {
+      wb = reinterpret_cast<uint16_t*>(gbase + A.off_wbl);
+      src = reinterpret_cast<const uint16_t*>(A.wl);
+      for (int i = tid; i < NL * K16; i += nthreads) {
+        const int n = i / K16, k = i - n * K16;
+        wb[(((n >> 3) * (K16 >> 3) + (k >> 3)) * 8 + (n & 7)) * 8 + (k & 7)] = k < A.K8 ? src[n * A.K8 + k] : (uint16_t)0;
+      }
+    }
+    if (tid < 16) reinterpret_cast<uint32_t*>(gbase + A.off_zero)[tid] = 0u;
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  // depthwise-tail role of this thread (fixed for the whole kernel): a channel and an 8-pixel column
+  const bool dw_hi = warp < A.hi_warps;
+  const int dwt = dw_hi ? tid : tid - A.hi_warps * 32;
+  const int Gd = dw_hi ? GH : GL, Cd = dw_hi ? Cho : Clo, Sd = dw_hi ? SH : ST;
+  const bool dw_live = dwt < Cd * Gd;
+  const int dc = dw_live ? dwt / Gd : 0, dg = dw_live ? dwt - dc * Gd : 0;
+  uint32_t w1[5], w2[5];
+  float b1, s1, b2, s2;
+  {
+    const DwParams& P1 = dw_hi ? A.dw1h : A.dw1l;
+    const DwParams& P2 = dw_hi ? A.dw2h : A.dw2l;
+    float f1[10], f2[10];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      f1[i] = dw_live ? __ldg(P1.w + dc * 9 + i) : 0.f;
+      f2[i] = dw_live ? __ldg(P2.w + dc * 9 + i) : 0.f;
+    }
+    f1[9] = f2[9] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { w1[i] = Pack<T>::from_f2(f1[2 * i], f1[2 * i + 1]); w2[i] = Pack<T>::from_f2(f2[2 * i], f2[2 * i + 1]); }
+    b1 = dw_live ? __ldg(P1.b + dc) : 0.f; s1 = dw_live ? __ldg(P1.s + dc) - 1.f : 0.f;
+    b2 = dw_live ? __ldg(P2.b + dc) : 0.f; s2 = dw_live ? __ldg(P2.s + dc) - 1.f : 0.f;
+  }
+  const float mL = dg == 0 ? 0.f : 1.f, mR = dg == Gd - 1 ? 0.f : 1.f;
+  const int dw_rows = dw_hi ? 4 : 2;                      // T1 rows per chunk of this role
+  const int dHd = dw_hi ? H : Hl, dWd = dw_hi ? W : Wl;
+  // byte offsets inside a T1 chunk of this thread's 16-byte row (row 0) and of its two halo pairs
+  const uint32_t dw_off = (uint32_t)(dg * Sd + dc) * 16u, dw_rowstep = (uint32_t)(Gd * Sd) * 16u;
+  const bool edgeL = dg == 0, edgeR = dg == Gd - 1;
+
+  const uint32_t idesc_h = (1u << 4) | (1u << 15) | ((uint32_t)(NH >> 3) << 17) | (8u << 24);   // f16 x f16 -> f32, A MN-major, M = 128
+  const uint32_t idesc_l = (1u << 4) | (1u << 15) | ((uint32_t)(NL >> 3) << 17) | (8u << 24);
+  const int nbh = (4 * GH + 15) >> 4, nbl = NL > 0 ? (2 * GL + 15) >> 4 : 0;
+  const uint32_t hi_tx = (uint32_t)(64 * SH * GH), lo_tx = (uint32_t)(32 * SL * GL);
+
+  // ---- the CTA's range of the (image, chunk) sequence ------------------------------------------------
+  int ra = (int)((long long)blockIdx.x * A.total_chunks / gridDim.x);
+  const int rb = (int)((long long)(blockIdx.x + 1) * A.total_chunks / gridDim.x);
+  uint32_t hq = 0, lq = 0, mq = 0;                       // running counts: hi loads, lo loads, MMA commits
+
+  while (ra < rb) {
+    const int n = ra / cpi, ca = ra - n * cpi;
+    const int cb = (ca + (rb - ra)) < cpi ? (ca + (rb - ra)) : cpi;
+    ra += cb - ca;
+    const int c0 = ca > 0 ? ca - 1 : 0, c1 = cb < cpi ? cb : cpi - 1;              // hi chunks walked (warm-up / look-ahead)
+    const int cl0 = c0 > 0 ? c0 - 1 : 0, cl1 = c1 + 1 < cpi ? c1 + 1 : cpi - 1;    // lo chunks loaded
+    const int out_lo = dw_hi ? 4 * ca : 2 * ca, out_hi = dw_hi ? 4 * cb : 2 * cb;  // rows this role stores
+    const uint32_t hq0 = hq, lq0 = lq;
+    hq += (uint32_t)(c1 - c0 + 1);
+    lq += (uint32_t)(cl1 - cl0 + 1);
+    auto hi_stage = [&](int c) { return XH + ((hq0 + (uint32_t)(c - c0)) & 1u) * (uint32_t)A.hi_stage_bytes; };
+    auto lo_stage = [&](int cl) { return XL + ((lq0 + (uint32_t)(cl - cl0)) & 3u) * (uint32_t)A.lo_stage_bytes; };
+    auto issue_hi = [&](int c) {
+      const uint32_t q = hq0 + (uint32_t)(c - c0), bar = bar_h + 8 * (q & 1u);
+      mbar_expect_tx_a(bar, hi_tx);
+      tma_load_5d(hi_stage(c), &tmH, bar, 0, 0, 0, 4 * c, n);
+    };
+    auto issue_lo = [&](int cl) {
+      const uint32_t q = lq0 + (uint32_t)(cl - cl0), bar = bar_l + 8 * (q & 3u);
+      mbar_expect_tx_a(bar, lo_tx);
+      tma_load_5d(lo_stage(cl), &tmL, bar, 0, 0, 0, 2 * cl, n);
+    };
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      issue_hi(c0);
+      if (c0 + 1 <= c1) issue_hi(c0 + 1);
+      for (int cl = cl0; cl <= cl1 && cl <= c0 + 2; ++cl) issue_lo(cl);
+    }
+    int lo_waited = 0;
+    uint32_t t1w[2][6], t2w[2][5];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) t1w[0][i] = t1w[1][i] = 0u;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) t2w[0][i] = t2w[1][i] = 0u;
+    uint16_t* ybase = reinterpret_cast<uint16_t*>(dw_hi ? A.yh : A.yl) + ((size_t)n * Cd + dc) * dHd * dWd + 8 * dg;
+
+    for (int c = c0; c <= c1; ++c) {
+      // ---- 1. the chunk's inputs have landed -----------------------------------------------------------
+      {
+        const uint32_t q = hq0 + (uint32_t)(c - c0);
+        mbar_wait_a(bar_h + 8 * (q & 1u), (q >> 1) & 1u);
+        const int need = (c + 1 < cpi ? c + 1 : cpi - 1) - cl0 + 1;
+        while (lo_waited < need) {
+          const uint32_t ql = lq0 + (uint32_t)lo_waited;
+          mbar_wait_a(bar_l + 8 * (ql & 3u), (ql >> 2) & 1u);
+          ++lo_waited;
+        }
+      }
+      const uint32_t xh = hi_stage(c), xl = lo_stage(c);
+      // ---- 2. resample both ways ------------------------------------------------------------------------
+      {
+        const int n_up = Cli * GH, n_pool = Clo > 0 ? Chi * GL : 0;
+        for (int task = tid; task < n_up + n_pool; task += nthreads) {
+          if (task < n_up) {
+            // bilinear x2 (align_corners=False): hi pixel 2j = 1/4 lo[j-1] + 3/4 lo[j], 2j+1 = 3/4 lo[j] + 1/4 lo[j+1], clamped
+            const int cl_ = task / GH, g = task - cl_ * GH;
+            const int gl = g >> 1, hf = g & 1;
+            const uint32_t offM = (uint32_t)(gl * SL + cl_) * 16u + 8u * hf;
+            const uint32_t offL = hf ? offM - 2u : (g == 0 ? offM : offM - (uint32_t)SL * 16u + 14u);
+            const uint32_t offR = hf ? (g == GH - 1 ? offM + 6u : offM + (uint32_t)SL * 16u - 8u) : offM + 8u;
+            float hrow[4][8];
+            const uint16_t w25 = Pack<T>::bits(0.25f), w75 = Pack<T>::bits(0.75f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              int R = 2 * c - 1 + k;
+              R = R < 0 ? 0 : (R > Hl - 1 ? Hl - 1 : R);
+              const uint32_t rowb = lo_stage(R >> 1) + (uint32_t)((R & 1) * GL * SL) * 16u;
+              const uint2 m = lds64(rowb + offM);
+              const uint16_t vl = lds16(rowb + offL), vr = lds16(rowb + offR);
+              const uint16_t v0 = (uint16_t)m.x, v1 = (uint16_t)(m.x >> 16), v2 = (uint16_t)m.y, v3 = (uint16_t)(m.y >> 16);
+              hrow[k][0] = Pack<T>::fma16(v0, w75, Pack<T>::fma16(vl, w25, 0.f));
+              hrow[k][1] = Pack<T>::fma16(v0, w75, Pack<T>::fma16(v1, w25, 0.f));
+              hrow[k][2] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v0, w25, 0.f));
+              hrow[k][3] = Pack<T>::fma16(v1, w75, Pack<T>::fma16(v2, w25, 0.f));
+              hrow[k][4] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v1, w25, 0.f));
+              hrow[k][5] = Pack<T>::fma16(v2, w75, Pack<T>::fma16(v3, w25, 0.f));
+              hrow[k][6] = Pack<T>::fma16(v3, w75, Pack<T>::fma16(v2, w25, 0.f));
+              hrow[k][7] = Pack<T>::fma16(v3, w75, Pack<T>::fma16(vr, w25, 0.f));
+            }
+            const uint32_t dst = xh + (uint32_t)(g * SH + Chi + cl_) * 16u;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              // hi row 4c+rr: rr 0: (k0 1/4, k1 3/4); 1: (k1 3/4, k2 1/4); 2: (k1 1/4, k2 3/4); 3: (k2 3/4, k3 1/4)
+              const int km = rr < 2 ? 1 : 2, ko = rr == 0 ? 0 : (rr == 3 ? 3 : (rr == 1 ? 2 : 1));
+              uint4 o;
+              o.x = Pack<T>::from_f2(0.75f * hrow[km][0] + 0.25f * hrow[ko][0], 0.75f * hrow[km][1] + 0.25f * hrow[ko][1]);
+              o.y = Pack<T>::from_f2(0.75f * hrow[km][2] + 0.25f * hrow[ko][2], 0.75f * hrow[km][3] + 0.25f * hrow[ko][3]);
+              o.z = Pack<T>::from_f2(0.75f * hrow[km][4] + 0.25f * hrow[ko][4], 0.75f * hrow[km][5] + 0.25f * hrow[ko][5]);
+              o.w = Pack<T>::from_f2(0.75f * hrow[km][6] + 0.25f * hrow[ko][6], 0.75f * hrow[km][7] + 0.25f * hrow[ko][7]);
+              sts128(dst + (uint32_t)(rr * GH * SH) * 16u, o);
+            }
+          } else {
+            // max_pool2d 2x2: lo group gl of lo rows 2c, 2c+1 from hi groups 2gl, 2gl+1 of the 4 hi rows
+            const int t = task - n_up, ch = t / GL, gl = t - ch * GL;
+            const uint32_t src = xh + (uint32_t)(2 * gl * SH + ch) * 16u;
+            const uint32_t dst = xl + (uint32_t)(gl * SL + Cli + ch) * 16u;
+#pragma unroll
+            for (int lr = 0; lr < 2; ++lr) {
+              const uint32_t r0 = src + (uint32_t)(2 * lr * GH * SH) * 16u, r1 = r0 + (uint32_t)(GH * SH) * 16u;
+              const uint4 a0 = lds128(r0), a1 = lds128(r0 + (uint32_t)SH * 16u), c0_ = lds128(r1), c1_ = lds128(r1 + (uint32_t)SH * 16u);
+              auto hmax = [](uint32_t u, uint32_t v) {       // two lo pixels from the vertical maxima of 4 hi pixels
+                return __byte_perm(Pack<T>::max2(u, __byte_perm(u, 0u, 0x1032)), Pack<T>::max2(v, __byte_perm(v, 0u, 0x1032)), 0x5410);
+              };
+              uint4 o;
+              o.x = hmax(Pack<T>::max2(a0.x, c0_.x), Pack<T>::max2(a0.y, c0_.y));
+              o.y = hmax(Pack<T>::max2(a0.z, c0_.z), Pack<T>::max2(a0.w, c0_.w));
+              o.z = hmax(Pack<T>::max2(a1.x, c1_.x), Pack<T>::max2(a1.y, c1_.y));
+              o.w = hmax(Pack<T>::max2(a1.z, c1_.z), Pack<T>::max2(a1.w, c1_.w));
+              sts128(dst + (uint32_t)(lr * GL * SL) * 16u, o);
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");    // generic writes -> visible to the tensor core / TMA
+      __syncthreads();                                                    // (A)
+      // ---- 3. one thread: next loads, then the chunk's MMAs ------------------------------------------------
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (c >= c0 + 1 && c + 1 <= c1) issue_hi(c + 1);                 // stage of chunk c-1: its T1 was consumed
+        if (c + 3 <= cl1) issue_lo(c + 3);                               // stage of lo chunk c-1: last read by this chunk's up-sample
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const int ksteps = K16 >> 4;
+        for (int blk = 0; blk < nbh; ++blk)
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_f16(tmem + (uint32_t)(blk * NH), umma_desc(xh + (uint32_t)(blk * 16 * SH) * 16u + (uint32_t)ks * 256u, 128u, (uint32_t)SH * 16u),
+                     umma_desc(WBH + (uint32_t)ks * 256u, 128u, (uint32_t)(K16 >> 3) * 128u), idesc_h, ks > 0);
+        for (int blk = 0; blk < nbl; ++blk)
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_f16(tmem + (uint32_t)(nbh * NH + blk * NL), umma_desc(xl + (uint32_t)(blk * 16 * SL) * 16u + (uint32_t)ks * 256u, 128u, (uint32_t)SL * 16u),
+                     umma_desc(WBL + (uint32_t)ks * 256u, 128u, (uint32_t)(K16 >> 3) * 128u), idesc_l, ks > 0);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_m) : "memory");
+      }
+      mbar_wait_a(bar_m, mq & 1u);
+      ++mq;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // ---- 4. epilogue: TMEM -> bias, PReLU, 16-bit -> T1 (hi: in place over the chunk; lo: its own buffer) ----
+      if (warp < (nwarps & ~3)) {
+        const int qd = warp & 3, wstep = nwarps >> 2;
+        for (int b = warp >> 2; b < nbh + nbl; b += wstep) {
+          if (b < nbh) {
+            const int pg = b * 16 + qd * 4 + (lane >> 3);
+            ils_epilogue_block<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * NH), xh + (uint32_t)(pg * SH) * 16u + 2u * (lane & 7), Cho,
+                                  pg < 4 * GH, A.bias_h, A.sm1_h);
+          } else {
+            const int lb = b - nbh, pg = lb * 16 + qd * 4 + (lane >> 3);
+            ils_epilogue_block<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(nbh * NH + lb * NL), T1L + (uint32_t)(pg * ST) * 16u + 2u * (lane & 7),
+                                  Clo, pg < 2 * GL, A.bias_l, A.sm1_l);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncthreads();                                                    // (B)
+      // ---- 5. depthwise tail over the chunk's rows --------------------------------------------------------
+      if (dw_live) {
+        const uint32_t t1b = (dw_hi ? xh : T1L) + dw_off;
+        for (int rr = 0; rr < dw_rows; ++rr) {
+          const int r = dw_rows * c + rr;                                // T1 row arriving; T2 row r-1; output row r-2
+          const uint32_t p = t1b + (uint32_t)rr * dw_rowstep;
+          uint32_t n1[6];
+          const uint4 m = lds128(p);
+          n1[0] = lds32(edgeL ? ZERO : p - (uint32_t)Sd * 16u + 12u);
+          n1[1] = m.x; n1[2] = m.y; n1[3] = m.z; n1[4] = m.w;
+          n1[5] = lds32(edgeR ? ZERO : p + (uint32_t)Sd * 16u);
+          const int tr = r - 1, orow = r - 2;
+          const bool make_t2 = tr >= 0 && tr >= out_lo - 1 && tr <= out_hi;
+          const bool make_out = orow >= out_lo && orow < out_hi;
+          ils_dw_push<T>(t1w, t2w, n1, w1, b1, s1, w2, b2, s2, make_t2, mL, mR, make_out, ybase + (size_t)orow * dWd);
+        }
+      }
+    }
+    // ---- image bottom: two rows of zero padding flush the last two output rows ----------------------------
+    if (cb == cpi && dw_live) {
+      const uint32_t z[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = dHd + rr, tr = r - 1, orow = r - 2;
+        ils_dw_push<T>(t1w, t2w, z, w1, b1, s1, w2, b2, s2, tr < dHd, mL, mR, orow >= out_lo, ybase + (size_t)orow * dWd);
+      }
+    }
+    __syncthreads();          // every shared-memory read of this piece is done before the next piece's loads overwrite it
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+}  // namespace csnet

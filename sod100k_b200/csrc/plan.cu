@@ -15,6 +15,7 @@
 #include "../../include/csnet_b200.h"
 #include "generic_ops.cuh"
 #include "il_block.cuh"
+#include "il_stream.cuh"
 #include "mix_tc.cuh"
 #include "dw_fast.cuh"
 
@@ -152,6 +153,11 @@ struct csnet_plan {
   std::vector<size_t> op_smem;
   std::vector<TcChoice> op_tc;
   std::vector<std::vector<uint16_t*>> op_w16;     // per tensor-core MIX op, per path: packed 16-bit weights (device)
+  std::vector<float> h_blob;                      // host copy of the blob (epilogue tables of the streaming ILBlock kernel)
+  std::vector<char> op_ils;                       // per op: the streaming ILBlock kernel (il_stream.cuh) can run it
+  int num_sms = 148;
+  bool ils_enabled = true;                        // CSNET_ILS=0 at plan creation: tiled kernel only
+  int ils_min_chunks = 592;                       // batches with fewer 4-row chunks per ILBlock run the tiled kernel
   // host-buffer pipeline (csnet_plan_run_host): copy streams, ping-pong staging, ordering events
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   void* h_in[2] = {nullptr, nullptr};
@@ -414,6 +420,71 @@ size_t il_smem_of(const csnet::IlArgs& A) {
   return csnet::il_smem_bytes(A, ((A.TH + 8) | 1) * (A.TW + 8), ((A.TH / 2 + 4) | 1) * (A.TW / 2 + 8));
 }
 
+// 5-D map over a planar [N][C][H][W] 16-bit tensor with W split into (W/8, 8): dims (8 px, C, W/8, H, N).  A box
+// (8, slots, groups, rows, 1) lands in shared memory as [row][group][slot][8 px] — the tensor-core operand layout of
+// il_stream.cuh; slots past C are zero-filled.
+bool encode_group_map(CUtensorMap* tm, const void* base, int N, int C, int H, int W, int slots, int groups, int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[5] = {8, (cuuint64_t)C, (cuuint64_t)(W / 8), (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[4] = {(cuuint64_t)H * W * 2, 16, (cuuint64_t)W * 2, (cuuint64_t)C * H * W * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)slots, (cuuint32_t)groups, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Geometry of the streaming ILBlock kernel for an op; false if the op does not qualify (the tiled kernel runs it).
+bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out) {
+  if (!P.ils_enabled || op.kind != CSNET_OP_ILBLOCK || op.paths[0].ksize != 1 || encode_tiled_fn() == nullptr) return false;
+  const csnet_tensor_desc &Xh = P.tensors[op.paths[0].src], &Xl = P.tensors[op.paths[1].src], &Yh = P.tensors[op.dst];
+  if (Yh.dtype != CSNET_F16) return false;
+  csnet::IlsArgs A{};
+  A.H = Yh.H; A.W = Yh.W;
+  A.Chi = Xh.C; A.Cli = Xl.C; A.Cho = Yh.C; A.Clo = op.dst2 >= 0 ? P.tensors[op.dst2].C : 0;
+  if (A.W % 16 || A.H % 4 || A.Cho > csnet::kIlsMaxC || A.Clo > csnet::kIlsMaxC || A.Chi + A.Cli > 64) return false;
+  A.K8 = round_up(A.Chi + A.Cli, 8);
+  A.K16 = round_up(A.Chi + A.Cli, 16);
+  A.NH = round_up(A.Cho, 16);
+  A.NL = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
+  A.GH = A.W / 8; A.GL = A.W / 16;
+  A.SH = (A.K16 + 1 > (A.Cho | 1)) ? A.K16 + 1 : (A.Cho | 1);
+  A.SL = A.Clo > 0 ? A.K16 + 1 : (A.Cli | 1);
+  A.ST = A.Clo > 0 ? (A.Clo | 1) : 1;
+  A.cpi = A.H / 4;
+  A.hi_warps = (A.Cho * A.GH + 31) / 32;
+  A.lo_warps = (A.Clo * A.GL + 31) / 32;
+  if (A.hi_warps + A.lo_warps < 4) A.hi_warps = 4 - A.lo_warps;       // the epilogue needs one warp per TMEM lane quarter
+  const int warps = A.hi_warps + A.lo_warps;
+  if (warps * 32 > csnet::kIlsMaxThreads || A.SH > 256 || A.SL > 256 || A.GH > 256) return false;
+  const int nbh = (4 * A.GH + 15) / 16, nbl = A.Clo > 0 ? (2 * A.GL + 15) / 16 : 0;
+  if (nbh * A.NH + nbl * A.NL > 512) return false;                       // fp32 accumulators of a chunk: TMEM columns
+  auto r128 = [](int v) { return (v + 127) / 128 * 128; };
+  A.lo_stage_bytes = r128(2 * A.GL * A.SL * 16);
+  A.hi_stage_bytes = r128(4 * A.GH * A.SH * 16);
+  A.off_xl = 0;
+  A.off_xh = csnet::kIlsLoStages * A.lo_stage_bytes;
+  A.off_t1l = A.off_xh + csnet::kIlsHiStages * A.hi_stage_bytes;
+  A.off_wbh = A.off_t1l + r128(2 * A.GL * A.ST * 16);
+  A.off_wbl = A.off_wbh + r128(A.NH * A.K16 * 2);
+  A.off_bar = A.off_wbl + r128(A.NL * A.K16 * 2);
+  A.off_zero = A.off_bar + 128;
+  // the last accumulator block of a chunk may read (never use) up to 15 pixel groups past the chunk: keep them inside
+  A.smem_bytes = A.off_zero + 128 + 16 * 65 * 16 + 128;
+  if (A.smem_bytes > 227 * 1024) return false;
+  // epilogue tables
+  if ((int64_t)P.h_blob.size() != P.blob_floats) {
+    // geometry query before the blob exists (csnet_plan_create): tables stay zero
+  } else {
+    auto f = [&](int e) { return op.ext_off[e] >= 0 ? P.h_blob.data() + op.ext_off[e] : nullptr; };
+    for (int c = 0; c < A.Cho; ++c) { A.bias_h[c] = f(2)[c]; A.sm1_h[c] = f(3)[c] - 1.f; }
+    for (int c = 0; c < A.Clo; ++c) { A.bias_l[c] = f(4)[c]; A.sm1_l[c] = f(5)[c] - 1.f; }
+  }
+  *out = A;
+  return true;
+}
+
 template <typename T>
 void launch_il_t(const csnet::IlArgs& A, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& h, const CUtensorMap& l) {
   if (A.TH == 32) csnet::il_block_kernel<T, 32, 32><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
@@ -596,6 +667,26 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     P->op_smem[i] = il_smem_of(A);
     P->il_smem_max = P->op_smem[i] > P->il_smem_max ? P->op_smem[i] : P->il_smem_max;
   }
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) P->num_sms = prop.multiProcessorCount;
+  }
+  P->op_ils.assign(P->ops.size(), 0);
+  P->ils_min_chunks = 4 * P->num_sms;
+  if (const char* e1 = getenv("CSNET_ILS")) P->ils_enabled = e1[0] != '0';
+  if (const char* e2 = getenv("CSNET_ILS_MIN_CHUNKS")) P->ils_min_chunks = atoi(e2);
+  int ils_smem_max = 0;
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    csnet::IlsArgs S;
+    if (!make_ils(*P, P->ops[i], &S)) continue;
+    P->op_ils[i] = 1;
+    ils_smem_max = S.smem_bytes > ils_smem_max ? S.smem_bytes : ils_smem_max;
+  }
+  if (ils_smem_max > 0) {
+    // always the architectural maximum: plans created later must not lower the limit an earlier plan relies on
+    e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(il_stream): ") + cudaGetErrorString(e));
+  }
   if (P->il_smem_max > 0) {
     e = set_il_smem_t<__half>((int)P->il_smem_max);
     if (e == cudaSuccess) e = set_il_smem_t<__nv_bfloat16>((int)P->il_smem_max);
@@ -609,6 +700,7 @@ int csnet_plan_set_blob(csnet_plan* P, const float* host_blob, int64_t n, void* 
   if (!P || !host_blob || n != P->blob_floats) return fail(CSNET_E_INVALID, "csnet_plan_set_blob: size mismatch");
   CU_CHECK(cudaSetDevice(P->device));
   CU_CHECK(cudaMemcpyAsync(P->blob, host_blob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  P->h_blob.assign(host_blob, host_blob + n);
   // tensor-core MIX ops read their weights as 16-bit [chunk][tap][m16_total][kc + 8] blocks: pack them here, once per
   // weight update, so the kernels stage them with plain 16-byte copies
   std::vector<std::vector<uint16_t>> keep;
@@ -699,6 +791,26 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     gn_stats_kernel<<<dim3(A.groups, N), kThreads, 0, stream>>>(A);
     const int bx = (A.HW + kThreads * 4 - 1) / (kThreads * 4);
     gn_apply_kernel<<<dim3(bx < 1 ? 1 : bx, D.C, N), kThreads, 0, stream>>>(A);
+  } else if (op.kind == CSNET_OP_ILBLOCK && P->op_ils[i] && (int64_t)N * (D.H / 4) >= (int64_t)P->ils_min_chunks) {
+    // streaming kernel (il_stream.cuh): TMA operand tiles, tcgen05 GEMM, register-resident depthwise tail
+    csnet::IlsArgs A;
+    if (!make_ils(*P, op, &A)) return fail(CSNET_E_UNSUPPORTED, "ILBLOCK op no longer qualifies for the streaming kernel");
+    auto f = [&](int e) { return op.ext_off[e] >= 0 ? P->blob + op.ext_off[e] : nullptr; };
+    A.yh = P->tensor_ptr(op.dst, N, ext_ptrs);
+    A.yl = op.dst2 >= 0 ? P->tensor_ptr(op.dst2, N, ext_ptrs) : nullptr;
+    A.wh = reinterpret_cast<const uint32_t*>(f(0));
+    A.wl = reinterpret_cast<const uint32_t*>(f(1));
+    A.dw1h = {f(6), f(7), f(8)};   A.dw1l = {f(9), f(10), f(11)};
+    A.dw2h = {f(12), f(13), f(14)}; A.dw2l = {f(15), f(16), f(17)};
+    A.N = N;
+    A.total_chunks = N * A.cpi;
+    CUtensorMap tmH, tmL;
+    if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GH, 4) ||
+        !encode_group_map(&tmL, P->tensor_ptr(op.paths[1].src, N, ext_ptrs), N, A.Cli, A.H / 2, A.W / 2, A.SL, A.GL, 2))
+      return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock)");
+    int grid = A.total_chunks / 4;
+    grid = grid < 1 ? 1 : (grid > P->num_sms ? P->num_sms : grid);
+    csnet::il_stream_kernel<__half><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
   } else if (op.kind == CSNET_OP_ILBLOCK) {
     csnet::IlArgs A;
     if (!make_il(*P, op, N, ext_ptrs, &A)) return fail(CSNET_E_UNSUPPORTED, "ILBLOCK op does not fit shared memory");
