@@ -45,7 +45,7 @@ struct IlsArgs {
   int32_t cpi, total_chunks;          // chunks per image (H/4), N * cpi
   int32_t hi_warps, lo_warps;         // warps of the depthwise tail
   int32_t hi_stage_bytes, lo_stage_bytes;
-  int32_t off_xl, off_xh, off_t1l, off_wbh, off_wbl, off_bar, off_zero, smem_bytes;
+  int32_t off_xl, off_xh, off_t1l, off_wbh, off_wbl, off_bar, off_zero, off_epi, smem_bytes;
 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
@@ -155,24 +155,45 @@ __device__ __forceinline__ void ils_dw_push(uint32_t (&t1)[2][6], uint32_t (&t2)
   for (int i = 0; i < 5; ++i) { t2[0][i] = t2[1][i]; t2[1][i] = q[i]; }
 }
 
-// Epilogue of one 128-pixel accumulator block: this thread's pixel (TMEM lane), channels [0, C): bias, PReLU, 16-bit store
-// at dst + 16 * channel.  bias / sm1 live in the kernel-argument constant bank (indexed by unrolled constants).
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void stsm_x4_trans(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Epilogue of one warp's 32 accumulator rows (= 32 pixels = 4 pixel groups, TMEM lanes [32 q, 32 q + 32)) of a 128-pixel
+// block: tcgen05.ld in the 16x256b shape hands a thread the mma-style fragment (row lane/4 and lane/4 + 8, columns
+// 2 (lane % 4) + {0, 1} of every 8-column slab) = pixel rows x channel pairs; + bias, PReLU, pack to 16 bits, then
+// stmatrix.trans writes each 8 px x 8 channel fragment as 8 channel rows of 8 contiguous pixels — exactly the
+// [group][slot][8 px] tile.  16 channels x 16 pixels per round trip.  g0: first pixel group of the warp's 4,
+// ngroups: groups of the chunk (later ones are MMA padding: stored to `dummy`), gstride = slots * 16 bytes.
+// eb / es: shared-memory tables of bias and (slope - 1) per channel.
 template <typename T>
-__device__ __forceinline__ void ils_epilogue_block(uint32_t taddr, uint32_t dst, int C, bool valid, const float (&bias)[kIlsMaxC],
-                                                   const float (&sm1)[kIlsMaxC]) {
+__device__ __forceinline__ void ils_epilogue_warp(uint32_t taddr, uint32_t tile, uint32_t gstride, int g0, int ngroups, int C,
+                                                  uint32_t eb, uint32_t es, uint32_t dummy, int lane) {
+  const int q = lane & 3, mrow = lane & 7, mat = lane >> 3;
+#pragma unroll 1
+  for (int cc = 0; cc * 16 < C; ++cc) {
+    const uint32_t co = (uint32_t)(cc * 16 + 2 * q) * 4u;
+    const uint2 bA = lds64(eb + co), bB = lds64(eb + co + 32u), sA = lds64(es + co), sB = lds64(es + co + 32u);
+    const float b0 = __uint_as_float(bA.x), b1 = __uint_as_float(bA.y), b2 = __uint_as_float(bB.x), b3 = __uint_as_float(bB.y);
+    const float s0 = __uint_as_float(sA.x), s1 = __uint_as_float(sA.y), s2 = __uint_as_float(sB.x), s3 = __uint_as_float(sB.y);
 #pragma unroll
-  for (int cc = 0; cc < kIlsMaxC / 16; ++cc) {
-    if (cc * 16 < C) {                                                 // warp-uniform
-      uint32_t r[16];
-      tmem_ld16(taddr + (uint32_t)(cc * 16), r);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int ch = cc * 16 + j;
-        if (ch < C) {
-          const float v = prelu_m1(__uint_as_float(r[j]) + bias[ch], sm1[ch]);
-          if (valid) sts16(dst + (uint32_t)ch * 16u, Pack<T>::bits(v));
-        }
-      }
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[8];
+      tmem_ld_16x256b_x2(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(cc * 16), r);
+      const uint32_t m0 = Pack<T>::from_f2(prelu_m1(__uint_as_float(r[0]) + b0, s0), prelu_m1(__uint_as_float(r[1]) + b1, s1));
+      const uint32_t m1 = Pack<T>::from_f2(prelu_m1(__uint_as_float(r[2]) + b0, s0), prelu_m1(__uint_as_float(r[3]) + b1, s1));
+      const uint32_t m2 = Pack<T>::from_f2(prelu_m1(__uint_as_float(r[4]) + b2, s2), prelu_m1(__uint_as_float(r[5]) + b3, s3));
+      const uint32_t m3 = Pack<T>::from_f2(prelu_m1(__uint_as_float(r[6]) + b2, s2), prelu_m1(__uint_as_float(r[7]) + b3, s3));
+      // matrix `mat` of the x4 store: pixel group g0 + 2h + (mat & 1), channels 16 cc + 8 (mat >> 1) ..; this lane addresses row mrow
+      const int pg = g0 + 2 * h + (mat & 1);
+      const uint32_t addr = pg < ngroups ? tile + (uint32_t)pg * gstride + (uint32_t)(cc * 16 + 8 * (mat >> 1) + mrow) * 16u
+                                         : dummy + (uint32_t)(mat * 8 + mrow) * 16u;
+      stsm_x4_trans(addr, m0, m1, m2, m3);
     }
   }
 }
@@ -186,9 +207,10 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
   const uint32_t XL = sbase + A.off_xl, XH = sbase + A.off_xh, T1L = sbase + A.off_t1l, WBH = sbase + A.off_wbh,
                  WBL = sbase + A.off_wbl, BAR = sbase + A.off_bar, ZERO = sbase + A.off_zero;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));      // generic pointer to the same place
-  // barriers: [0,2) hi stage full, [2,6) lo stage full, [6] MMAs of the chunk done; then the TMEM base slot
-  const uint32_t bar_h = BAR, bar_l = BAR + 16, bar_m = BAR + 48;
+  // barriers: [0,2) hi stage full, [2,6) lo stage full; +64 the TMEM base slot; +128: one per accumulator block (16)
+  const uint32_t bar_h = BAR, bar_l = BAR + 16, bar_m = BAR + 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + A.off_bar + 64);
+  const uint32_t EPI = sbase + A.off_epi, DUMMY = EPI + 1024;     // bias_h, sm1_h, bias_l, sm1_l (64 floats each); scratch rows
 
   const int H = A.H, W = A.W, Hl = H >> 1, Wl = W >> 1;
   const int Chi = A.Chi, Cli = A.Cli, Cho = A.Cho, Clo = A.Clo;
@@ -197,7 +219,8 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
 
   // ---- one-time setup -----------------------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(BAR + 8 * i) : "memory");
+    for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(BAR + 8 * i) : "memory");
+    for (int i = 0; i < 16; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_m + 8 * i) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -221,6 +244,10 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       }
     }
     if (tid < 16) reinterpret_cast<uint32_t*>(gbase + A.off_zero)[tid] = 0u;
+    if (tid < kIlsMaxC) {
+      float* ep = reinterpret_cast<float*>(gbase + A.off_epi);
+      ep[tid] = A.bias_h[tid]; ep[kIlsMaxC + tid] = A.sm1_h[tid]; ep[2 * kIlsMaxC + tid] = A.bias_l[tid]; ep[3 * kIlsMaxC + tid] = A.sm1_l[tid];
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -390,34 +417,34 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
         if (c + 3 <= cl1) issue_lo(c + 3);                               // stage of lo chunk c-1: last read by this chunk's up-sample
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const int ksteps = K16 >> 4;
-        for (int blk = 0; blk < nbh; ++blk)
+        const uint64_t dbh = umma_desc(WBH, 128u, (uint32_t)(K16 >> 3) * 128u), dbl = umma_desc(WBL, 128u, (uint32_t)(K16 >> 3) * 128u);
+        uint64_t da = umma_desc(xh, 128u, (uint32_t)SH * 16u);
+        for (int blk = 0; blk < nbh; ++blk, da += (uint64_t)(16 * SH)) {            // descriptor addresses count 16-byte units
+          for (int ks = 0; ks < ksteps; ++ks) umma_f16(tmem + (uint32_t)(blk * NH), da + (uint64_t)(16 * ks), dbh + (uint64_t)(16 * ks), idesc_h, ks > 0);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_m + 8u * blk) : "memory");
+        }
+        da = umma_desc(xl, 128u, (uint32_t)SL * 16u);
+        for (int blk = 0; blk < nbl; ++blk, da += (uint64_t)(16 * SL)) {
           for (int ks = 0; ks < ksteps; ++ks)
-            umma_f16(tmem + (uint32_t)(blk * NH), umma_desc(xh + (uint32_t)(blk * 16 * SH) * 16u + (uint32_t)ks * 256u, 128u, (uint32_t)SH * 16u),
-                     umma_desc(WBH + (uint32_t)ks * 256u, 128u, (uint32_t)(K16 >> 3) * 128u), idesc_h, ks > 0);
-        for (int blk = 0; blk < nbl; ++blk)
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_f16(tmem + (uint32_t)(nbh * NH + blk * NL), umma_desc(xl + (uint32_t)(blk * 16 * SL) * 16u + (uint32_t)ks * 256u, 128u, (uint32_t)SL * 16u),
-                     umma_desc(WBL + (uint32_t)ks * 256u, 128u, (uint32_t)(K16 >> 3) * 128u), idesc_l, ks > 0);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_m) : "memory");
+            umma_f16(tmem + (uint32_t)(nbh * NH + blk * NL), da + (uint64_t)(16 * ks), dbl + (uint64_t)(16 * ks), idesc_l, ks > 0);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_m + 8u * (nbh + blk)) : "memory");
+        }
       }
-      mbar_wait_a(bar_m, mq & 1u);
-      ++mq;
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       // ---- 4. epilogue: TMEM -> bias, PReLU, 16-bit -> T1 (hi: in place over the chunk; lo: its own buffer) ----
       if (warp < (nwarps & ~3)) {
         const int qd = warp & 3, wstep = nwarps >> 2;
         for (int b = warp >> 2; b < nbh + nbl; b += wstep) {
-          if (b < nbh) {
-            const int pg = b * 16 + qd * 4 + (lane >> 3);
-            ils_epilogue_block<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * NH), xh + (uint32_t)(pg * SH) * 16u + 2u * (lane & 7), Cho,
-                                  pg < 4 * GH, A.bias_h, A.sm1_h);
-          } else {
-            const int lb = b - nbh, pg = lb * 16 + qd * 4 + (lane >> 3);
-            ils_epilogue_block<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(nbh * NH + lb * NL), T1L + (uint32_t)(pg * ST) * 16u + 2u * (lane & 7),
-                                  Clo, pg < 2 * GL, A.bias_l, A.sm1_l);
-          }
+          mbar_wait_a(bar_m + 8u * b, mq & 1u);                      // the block's MMAs (and all earlier ones) have completed
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (b < nbh)
+            ils_epilogue_warp<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * NH), xh, (uint32_t)SH * 16u, b * 16 + qd * 4, 4 * GH, Cho,
+                                 EPI, EPI + 256u, DUMMY, lane);
+          else
+            ils_epilogue_warp<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(nbh * NH + (b - nbh) * NL), T1L, (uint32_t)ST * 16u,
+                                 (b - nbh) * 16 + qd * 4, 2 * GL, Clo, EPI + 512u, EPI + 768u, DUMMY, lane);
         }
       }
+      ++mq;
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();                                                    // (B)
       // ---- 5. depthwise tail over the chunk's rows --------------------------------------------------------

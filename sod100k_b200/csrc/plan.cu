@@ -449,9 +449,9 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   A.NH = round_up(A.Cho, 16);
   A.NL = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
   A.GH = A.W / 8; A.GL = A.W / 16;
-  A.SH = (A.K16 + 1 > (A.Cho | 1)) ? A.K16 + 1 : (A.Cho | 1);
+  A.SH = (A.K16 > A.NH ? A.K16 : A.NH) + 1;            // odd: consecutive pixel groups start in different bank groups
   A.SL = A.Clo > 0 ? A.K16 + 1 : (A.Cli | 1);
-  A.ST = A.Clo > 0 ? (A.Clo | 1) : 1;
+  A.ST = A.NL + 1;
   A.cpi = A.H / 4;
   A.hi_warps = (A.Cho * A.GH + 31) / 32;
   A.lo_warps = (A.Clo * A.GL + 31) / 32;
@@ -459,7 +459,7 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   const int warps = A.hi_warps + A.lo_warps;
   if (warps * 32 > csnet::kIlsMaxThreads || A.SH > 256 || A.SL > 256 || A.GH > 256) return false;
   const int nbh = (4 * A.GH + 15) / 16, nbl = A.Clo > 0 ? (2 * A.GL + 15) / 16 : 0;
-  if (nbh * A.NH + nbl * A.NL > 512) return false;                       // fp32 accumulators of a chunk: TMEM columns
+  if (nbh * A.NH + nbl * A.NL > 512 || nbh + nbl > 16) return false;                       // fp32 accumulators of a chunk: TMEM columns
   auto r128 = [](int v) { return (v + 127) / 128 * 128; };
   A.lo_stage_bytes = r128(2 * A.GL * A.SL * 16);
   A.hi_stage_bytes = r128(4 * A.GH * A.SH * 16);
@@ -469,9 +469,10 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   A.off_wbh = A.off_t1l + r128(2 * A.GL * A.ST * 16);
   A.off_wbl = A.off_wbh + r128(A.NH * A.K16 * 2);
   A.off_bar = A.off_wbl + r128(A.NL * A.K16 * 2);
-  A.off_zero = A.off_bar + 128;
+  A.off_zero = A.off_bar + 256;
+  A.off_epi = A.off_zero + 128;                          // 4 tables of 64 floats + 512 bytes of scratch rows
   // the last accumulator block of a chunk may read (never use) up to 15 pixel groups past the chunk: keep them inside
-  A.smem_bytes = A.off_zero + 128 + 16 * 65 * 16 + 128;
+  A.smem_bytes = A.off_epi + 1536 + 16 * 65 * 16 + 128;
   if (A.smem_bytes > 227 * 1024) return false;
   // epilogue tables
   if ((int64_t)P.h_blob.size() != P.blob_floats) {
