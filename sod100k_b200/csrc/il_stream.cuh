@@ -45,6 +45,7 @@ struct IlsArgs {
   int32_t cpi, total_chunks;          // chunks per image (H/4), N * cpi
   int32_t hi_warps, lo_warps;         // warps of the depthwise tail
   int32_t hi_stage_bytes, lo_stage_bytes;
+  unsigned long long* dbg;             // optional: per-CTA phase cycle counters [grid][8] (CSNET_ILS_DBG=1)
   int32_t off_xl, off_xh, off_t1l, off_wbh, off_wbl, off_bar, off_zero, off_epi, smem_bytes;
 };
 
@@ -198,7 +199,7 @@ __device__ __forceinline__ void ils_epilogue_warp(uint32_t taddr, uint32_t tile,
   }
 }
 
-template <typename T>
+template <typename T, bool kTiming = false>
 __global__ void __launch_bounds__(kIlsMaxThreads, 1)
 il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL) {
   extern __shared__ uint8_t smem_raw[];
@@ -294,6 +295,9 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
   int ra = (int)((long long)blockIdx.x * A.total_chunks / gridDim.x);
   const int rb = (int)((long long)(blockIdx.x + 1) * A.total_chunks / gridDim.x);
   uint32_t hq = 0, lq = 0, mq = 0;                       // running counts: hi loads, lo loads, MMA commits
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+  const bool timing = kTiming && A.dbg != nullptr && tid == 0;
+#define ILS_MARK(i) do { if (kTiming && timing) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
 
   while (ra < rb) {
     const int n = ra / cpi, ca = ra - n * cpi;
@@ -343,6 +347,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
           ++lo_waited;
         }
       }
+      ILS_MARK(0);
       const uint32_t xh = hi_stage(c), xl = lo_stage(c);
       // ---- 2. resample both ways ------------------------------------------------------------------------
       {
@@ -408,28 +413,30 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
           }
         }
       }
+      ILS_MARK(1);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");    // generic writes -> visible to the tensor core / TMA
       __syncthreads();                                                    // (A)
-      // ---- 3. one thread: next loads, then the chunk's MMAs ------------------------------------------------
-      if (tid == 0) {
+      ILS_MARK(2);
+      // ---- 3. next loads (one thread of the last warp); the chunk's MMAs: warp b's elected lane issues block b ----
+      if (warp == nwarps - 1 && lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         if (c >= c0 + 1 && c + 1 <= c1) issue_hi(c + 1);                 // stage of chunk c-1: its T1 was consumed
         if (c + 3 <= cl1) issue_lo(c + 3);                               // stage of lo chunk c-1: last read by this chunk's up-sample
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const int ksteps = K16 >> 4;
-        const uint64_t dbh = umma_desc(WBH, 128u, (uint32_t)(K16 >> 3) * 128u), dbl = umma_desc(WBL, 128u, (uint32_t)(K16 >> 3) * 128u);
-        uint64_t da = umma_desc(xh, 128u, (uint32_t)SH * 16u);
-        for (int blk = 0; blk < nbh; ++blk, da += (uint64_t)(16 * SH)) {            // descriptor addresses count 16-byte units
-          for (int ks = 0; ks < ksteps; ++ks) umma_f16(tmem + (uint32_t)(blk * NH), da + (uint64_t)(16 * ks), dbh + (uint64_t)(16 * ks), idesc_h, ks > 0);
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_m + 8u * blk) : "memory");
-        }
-        da = umma_desc(xl, 128u, (uint32_t)SL * 16u);
-        for (int blk = 0; blk < nbl; ++blk, da += (uint64_t)(16 * SL)) {
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_f16(tmem + (uint32_t)(nbh * NH + blk * NL), da + (uint64_t)(16 * ks), dbl + (uint64_t)(16 * ks), idesc_l, ks > 0);
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_m + 8u * (nbh + blk)) : "memory");
+      }
+      if (lane == 0) {
+        for (int b = warp; b < nbh + nbl; b += nwarps) {
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const bool hb = b < nbh;
+          const int lb = hb ? b : b - nbh, S_ = hb ? SH : SL;
+          const uint64_t da = umma_desc((hb ? xh : xl) + (uint32_t)(lb * 16 * S_) * 16u, 128u, (uint32_t)S_ * 16u);
+          const uint64_t db = umma_desc(hb ? WBH : WBL, 128u, (uint32_t)(K16 >> 3) * 128u);
+          const uint32_t tm = tmem + (uint32_t)(hb ? lb * NH : nbh * NH + lb * NL), idesc = hb ? idesc_h : idesc_l;
+          for (int ks = 0; ks < (K16 >> 4); ++ks) umma_f16(tm, da + (uint64_t)(16 * ks), db + (uint64_t)(16 * ks), idesc, ks > 0);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_m + 8u * b) : "memory");
         }
       }
+      __syncwarp();
+      ILS_MARK(3);
       // ---- 4. epilogue: TMEM -> bias, PReLU, 16-bit -> T1 (hi: in place over the chunk; lo: its own buffer) ----
       if (warp < (nwarps & ~3)) {
         const int qd = warp & 3, wstep = nwarps >> 2;
@@ -445,8 +452,10 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
         }
       }
       ++mq;
+      ILS_MARK(4);
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();                                                    // (B)
+      ILS_MARK(5);
       // ---- 5. depthwise tail over the chunk's rows --------------------------------------------------------
       if (dw_live) {
         const uint32_t t1b = (dw_hi ? xh : T1L) + dw_off;
@@ -464,6 +473,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
           ils_dw_push<T>(t1w, t2w, n1, w1, b1, s1, w2, b2, s2, make_t2, mL, mR, make_out, ybase + (size_t)orow * dWd);
         }
       }
+      ILS_MARK(6);
     }
     // ---- image bottom: two rows of zero padding flush the last two output rows ----------------------------
     if (cb == cpi && dw_live) {
@@ -476,6 +486,11 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
     __syncthreads();          // every shared-memory read of this piece is done before the next piece's loads overwrite it
   }
 
+  if (timing) {
+    ILS_MARK(7);
+    for (int i = 0; i < 8; ++i) A.dbg[(size_t)blockIdx.x * 8 + i] = (unsigned long long)tph[i];
+  }
+#undef ILS_MARK
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");

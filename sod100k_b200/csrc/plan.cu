@@ -685,7 +685,8 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   }
   if (ils_smem_max > 0) {
     // always the architectural maximum: plans created later must not lower the limit an earlier plan relies on
-    e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(il_stream): ") + cudaGetErrorString(e));
   }
   if (P->il_smem_max > 0) {
@@ -811,7 +812,21 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
       return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock)");
     int grid = A.total_chunks / 4;
     grid = grid < 1 ? 1 : (grid > P->num_sms ? P->num_sms : grid);
-    csnet::il_stream_kernel<__half><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    static const bool dbg = [] { const char* e = getenv("CSNET_ILS_DBG"); return e && e[0] == '1'; }();
+    static unsigned long long* dbg_buf = nullptr;
+    if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(unsigned long long));
+    A.dbg = dbg ? dbg_buf : nullptr;
+    if (dbg) csnet::il_stream_kernel<__half, true><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    else csnet::il_stream_kernel<__half, false><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    if (dbg) {        // debugging aid: mean cycles per phase over the CTAs (synchronises)
+      std::vector<unsigned long long> h((size_t)grid * 8);
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) m[k] += (double)h[(size_t)b * 8 + k] / grid;
+      fprintf(stderr, "[ils %dx%d C %d+%d->%d+%d] cycles/CTA: load-wait %.0f resample %.0f syncA %.0f issue %.0f epilogue %.0f syncB %.0f dw %.0f tail %.0f\n",
+              A.H, A.W, A.Chi, A.Cli, A.Cho, A.Clo, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+    }
   } else if (op.kind == CSNET_OP_ILBLOCK) {
     csnet::IlArgs A;
     if (!make_il(*P, op, N, ext_ptrs, &A)) return fail(CSNET_E_UNSUPPORTED, "ILBLOCK op does not fit shared memory");
