@@ -19,6 +19,14 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, float a0, uint32_t h0) 
   uint16_t x = (uint16_t)(h0 & 0xffff), w = (uint16_t)(h0 >> 16);
   float xf = a0 * 0.5f, wf = a0 * 0.25f;
   float2 x2 = make_float2(xf, wf), w2 = make_float2(wf, xf);
+  uint16_t xs[CH], ws[CH], xs2[CH];
+  float xfs[CH], wfs[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const uint32_t v = h0 + 0x00010001u * (uint32_t)(i + (threadIdx.x & 1)), u = (h0 >> 3) + 0x00030001u * (uint32_t)(i + (threadIdx.x & 3));
+    xs[i] = (uint16_t)v; xs2[i] = (uint16_t)(v >> 16); ws[i] = (uint16_t)u;
+    xfs[i] = a0 * (i + 1); wfs[i] = a0 / (i + 2 + (threadIdx.x & 1));
+  }
   for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
@@ -43,6 +51,10 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, float a0, uint32_t h0) 
         asm volatile("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc[i]) : "h"(x), "h"(w));
         acc2[i].x = fmaf(acc2[i].x, xf, wf);
       }
+      if (MODE == 8) asm volatile("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc[i]) : "h"(xs[i]), "h"(ws[i]));        // FHFMA, 3 distinct regs / instr
+      if (MODE == 9) asm volatile("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc[i]) : "h"(xs[i]), "h"(w));            // FHFMA, shared weight operand
+      if (MODE == 10) acc[i] = fmaf(xfs[i], wfs[i], acc[i]);                                                          // FFMA, 3 distinct regs / instr
+      if (MODE == 11) asm volatile("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc[i]) : "h"(xs[i]), "h"(xs2[i]));      // FHFMA, .H1 of the same regs as 8's pairs
       if (MODE == 7) {                                                                                           // FHFMA + HFMA2 1:1
         asm volatile("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc[i]) : "h"(x), "h"(w));
         asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(hacc[i]) : "r"(h0), "r"(h0 ^ 0x11u));
@@ -80,5 +92,9 @@ int main() {
   run<5>("FFMA + FMNMX", 2);
   run<6>("FHFMA + FFMA", 2);
   run<7>("FHFMA + HFMA2", 2);
+  run<8>("FHFMA 3 distinct regs", 1);
+  run<9>("FHFMA shared weight reg", 1);
+  run<10>("FFMA 3 distinct regs", 1);
+  run<11>("FHFMA H0/H1 of one reg pair", 1);
   return 0;
 }

@@ -7,7 +7,7 @@
 //   TMA        x_h rows [4c, 4c+4) and x_l rows [2c, 2c+2) arrive by cp.async.bulk.tensor.5d straight in the
 //              tensor-core operand layout  [row][8-pixel group][channel slot][8 px]  (a core matrix of the MN-major
 //              A operand = 8 channel slots x 16 bytes); the map splits W into (W/8, 8), channel slots past the
-//              tensor's C are zero-filled by the TMA unit = the K padding of the GEMM.  2 hi / 4 lo stages.
+//              tensor's C are zero-filled by the TMA unit = the K padding of the GEMM.  2 hi / 3 lo stages.
 //   resample   bilinear x2 of x_l -> slots [Chi, Chi+Cli) of the hi chunk (lo -> hi path, csnet.py:702-707; the
 //              up-sample commutes with the 1x1 conv), max-pool 2x2 of x_h -> slots [Cli, Cli+Chi) of the lo chunk
 //              (hi -> lo path, :709-712).
@@ -18,9 +18,12 @@
 //              in registers: dw3x3+BN+PReLU twice with no halo recomputation in y, no shared-memory round trip for
 //              T2, 16-byte coalesced stores of the block output.  (mixed-precision FMA: fp16 x fp16 + fp32.)
 //
-// No halo is ever re-read from HBM (except one warm-up chunk where a CTA's range starts inside an image); the
-// work split is a flat division of N * H/4 chunks over the SMs.  Needs W % 16 == 0, H % 4 == 0,
-// Cho * W/8 + Clo * W/16 <= 768 dw threads, K = Chi + Cli <= 64.  Other shapes use il_block.cuh.
+// An image is cut into `ns` column strips of gsn 8-pixel groups (gsn even); a CTA's tile of a strip carries one halo
+// group on each side when ns > 1 (hl = 1: the TMA box starts one group early, out-of-image groups arrive as zeros).
+// Narrow strips let two CTAs share an SM (<= 113 KB shared memory, <= 256 TMEM columns each), so one CTA's waits
+// (TMA, MMA, barriers) are filled by the other's depthwise phase.  No row halo is ever re-read from HBM (except one
+// warm-up chunk where a CTA's range starts inside an image); the work split is a flat division of the
+// N * ns * H/4 chunks over the CTAs.  Needs W % 16 == 0, H % 4 == 0, K = Chi + Cli <= 64.  Other shapes: il_block.cuh.
 #pragma once
 #include "il_block.cuh"
 
@@ -28,7 +31,7 @@ namespace csnet {
 
 constexpr int kIlsMaxThreads = 768;
 constexpr int kIlsMaxC = 64;          // output channels per branch (epilogue parameter tables in the kernel arguments)
-constexpr int kIlsHiStages = 2, kIlsLoStages = 4;
+constexpr int kIlsHiStages = 2, kIlsLoStages = 3;
 
 struct IlsArgs {
   void* yh;
@@ -41,8 +44,11 @@ struct IlsArgs {
   int32_t Chi, Cli, Cho, Clo;
   int32_t K8, K16, NH, NL;            // NH / NL = ru16(Cho / Clo): the N of the MMAs (NL = 0 without a lo output)
   int32_t SH, SL, ST;                 // channel slots per pixel group: hi chunk, lo chunk, T1L buffer (all odd)
-  int32_t GH, GL;                     // pixel groups per row: W/8, W/16
-  int32_t cpi, total_chunks;          // chunks per image (H/4), N * cpi
+  int32_t GH, GL;                     // pixel groups per image row: W/8, W/16
+  int32_t ns, gsn, hl;                // column strips per image, hi groups per strip (even), halo groups per side (0 / 1)
+  int32_t GR, GLR;                    // groups per row of a CTA's tile: gsn + 2 hl, gsn/2 + 2 hl
+  int32_t tmem_cols;                  // TMEM columns to allocate (power of two >= the chunk's accumulators)
+  int32_t cpi, total_chunks;          // chunks per image strip (H/4), N * ns * cpi
   int32_t hi_warps, lo_warps;         // warps of the depthwise tail
   int32_t hi_stage_bytes, lo_stage_bytes;
   unsigned long long* dbg;             // optional: per-CTA phase cycle counters [grid][8] (CSNET_ILS_DBG=1)
@@ -208,7 +214,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
   const uint32_t XL = sbase + A.off_xl, XH = sbase + A.off_xh, T1L = sbase + A.off_t1l, WBH = sbase + A.off_wbh,
                  WBL = sbase + A.off_wbl, BAR = sbase + A.off_bar, ZERO = sbase + A.off_zero;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));      // generic pointer to the same place
-  // barriers: [0,2) hi stage full, [2,6) lo stage full; +64 the TMEM base slot; +128: one per accumulator block (16)
+  // barriers: [0,2) hi stage full, [2,5) lo stage full; +64 the TMEM base slot; +128: one per accumulator block (16)
   const uint32_t bar_h = BAR, bar_l = BAR + 16, bar_m = BAR + 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + A.off_bar + 64);
   const uint32_t EPI = sbase + A.off_epi, DUMMY = EPI + 1024;     // bias_h, sm1_h, bias_l, sm1_l (64 floats each); scratch rows
@@ -216,6 +222,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
   const int H = A.H, W = A.W, Hl = H >> 1, Wl = W >> 1;
   const int Chi = A.Chi, Cli = A.Cli, Cho = A.Cho, Clo = A.Clo;
   const int GH = A.GH, GL = A.GL, SH = A.SH, SL = A.SL, ST = A.ST, NH = A.NH, NL = A.NL, K16 = A.K16;
+  const int GR = A.GR, GLR = A.GLR, hl = A.hl, gsn = A.gsn;
   const int cpi = A.cpi;
 
   // ---- one-time setup -----------------------------------------------------------------------------------
@@ -225,7 +232,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(BAR + 64) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(BAR + 64), "r"(A.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   // weights -> K-major B operand: core matrices [n group][k group][8 n][8 k]
@@ -259,7 +266,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
   // depthwise-tail role of this thread (fixed for the whole kernel): a channel and an 8-pixel column
   const bool dw_hi = warp < A.hi_warps;
   const int dwt = dw_hi ? tid : tid - A.hi_warps * 32;
-  const int Gd = dw_hi ? GH : GL, Cd = dw_hi ? Cho : Clo, Sd = dw_hi ? SH : ST;
+  const int Gd = dw_hi ? gsn : gsn >> 1, Cd = dw_hi ? Cho : Clo, Sd = dw_hi ? SH : ST;   // Gd: this role's groups per strip row
   const bool dw_live = dwt < Cd * Gd;
   const int dc = dw_live ? dwt / Gd : 0, dg = dw_live ? dwt - dc * Gd : 0;
   uint32_t w1[5], w2[5];
@@ -279,17 +286,16 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
     b1 = dw_live ? __ldg(P1.b + dc) : 0.f; s1 = dw_live ? __ldg(P1.s + dc) - 1.f : 0.f;
     b2 = dw_live ? __ldg(P2.b + dc) : 0.f; s2 = dw_live ? __ldg(P2.s + dc) - 1.f : 0.f;
   }
-  const float mL = dg == 0 ? 0.f : 1.f, mR = dg == Gd - 1 ? 0.f : 1.f;
   const int dw_rows = dw_hi ? 4 : 2;                      // T1 rows per chunk of this role
   const int dHd = dw_hi ? H : Hl, dWd = dw_hi ? W : Wl;
   // byte offsets inside a T1 chunk of this thread's 16-byte row (row 0) and of its two halo pairs
-  const uint32_t dw_off = (uint32_t)(dg * Sd + dc) * 16u, dw_rowstep = (uint32_t)(Gd * Sd) * 16u;
-  const bool edgeL = dg == 0, edgeR = dg == Gd - 1;
+  const uint32_t dw_off = (uint32_t)((dg + hl) * Sd + dc) * 16u, dw_rowstep = (uint32_t)((dw_hi ? GR : GLR) * Sd) * 16u;
+  const int Gimg = dw_hi ? GH : GL;                       // groups per image row of this role
 
   const uint32_t idesc_h = (1u << 4) | (1u << 15) | ((uint32_t)(NH >> 3) << 17) | (8u << 24);   // f16 x f16 -> f32, A MN-major, M = 128
   const uint32_t idesc_l = (1u << 4) | (1u << 15) | ((uint32_t)(NL >> 3) << 17) | (8u << 24);
-  const int nbh = (4 * GH + 15) >> 4, nbl = NL > 0 ? (2 * GL + 15) >> 4 : 0;
-  const uint32_t hi_tx = (uint32_t)(64 * SH * GH), lo_tx = (uint32_t)(32 * SL * GL);
+  const int nbh = (4 * GR + 15) >> 4, nbl = NL > 0 ? (2 * GLR + 15) >> 4 : 0;
+  const uint32_t hi_tx = (uint32_t)(64 * SH * GR), lo_tx = (uint32_t)(32 * SL * GLR);
 
   // ---- the CTA's range of the (image, chunk) sequence ------------------------------------------------
   int ra = (int)((long long)blockIdx.x * A.total_chunks / gridDim.x);
@@ -300,7 +306,8 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
 #define ILS_MARK(i) do { if (kTiming && timing) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
 
   while (ra < rb) {
-    const int n = ra / cpi, ca = ra - n * cpi;
+    const int item = ra / cpi, ca = ra - item * cpi;
+    const int n = item / A.ns, gs0 = (item - n * A.ns) * gsn;                      // image, first hi group of the column strip
     const int cb = (ca + (rb - ra)) < cpi ? (ca + (rb - ra)) : cpi;
     ra += cb - ca;
     const int c0 = ca > 0 ? ca - 1 : 0, c1 = cb < cpi ? cb : cpi - 1;              // hi chunks walked (warm-up / look-ahead)
@@ -310,22 +317,22 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
     hq += (uint32_t)(c1 - c0 + 1);
     lq += (uint32_t)(cl1 - cl0 + 1);
     auto hi_stage = [&](int c) { return XH + ((hq0 + (uint32_t)(c - c0)) & 1u) * (uint32_t)A.hi_stage_bytes; };
-    auto lo_stage = [&](int cl) { return XL + ((lq0 + (uint32_t)(cl - cl0)) & 3u) * (uint32_t)A.lo_stage_bytes; };
+    auto lo_stage = [&](int cl) { return XL + ((lq0 + (uint32_t)(cl - cl0)) % 3u) * (uint32_t)A.lo_stage_bytes; };
     auto issue_hi = [&](int c) {
       const uint32_t q = hq0 + (uint32_t)(c - c0), bar = bar_h + 8 * (q & 1u);
       mbar_expect_tx_a(bar, hi_tx);
-      tma_load_5d(hi_stage(c), &tmH, bar, 0, 0, 0, 4 * c, n);
+      tma_load_5d(hi_stage(c), &tmH, bar, 0, 0, gs0 - hl, 4 * c, n);
     };
     auto issue_lo = [&](int cl) {
-      const uint32_t q = lq0 + (uint32_t)(cl - cl0), bar = bar_l + 8 * (q & 3u);
+      const uint32_t q = lq0 + (uint32_t)(cl - cl0), bar = bar_l + 8 * (q % 3u);
       mbar_expect_tx_a(bar, lo_tx);
-      tma_load_5d(lo_stage(cl), &tmL, bar, 0, 0, 0, 2 * cl, n);
+      tma_load_5d(lo_stage(cl), &tmL, bar, 0, 0, (gs0 >> 1) - hl, 2 * cl, n);
     };
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       issue_hi(c0);
       if (c0 + 1 <= c1) issue_hi(c0 + 1);
-      for (int cl = cl0; cl <= cl1 && cl <= c0 + 2; ++cl) issue_lo(cl);
+      for (int cl = cl0; cl <= cl1 && cl <= c0 + 1; ++cl) issue_lo(cl);
     }
     int lo_waited = 0;
     uint32_t t1w[2][6], t2w[2][5];
@@ -333,7 +340,10 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
     for (int i = 0; i < 6; ++i) t1w[0][i] = t1w[1][i] = 0u;
 #pragma unroll
     for (int i = 0; i < 5; ++i) t2w[0][i] = t2w[1][i] = 0u;
-    uint16_t* ybase = reinterpret_cast<uint16_t*>(dw_hi ? A.yh : A.yl) + ((size_t)n * Cd + dc) * dHd * dWd + 8 * dg;
+    const int gimg = (dw_hi ? gs0 : gs0 >> 1) + dg;                                // this thread's group in the image row
+    const bool edgeL = gimg == 0, edgeR = gimg == Gimg - 1;
+    const float mL = edgeL ? 0.f : 1.f, mR = edgeR ? 0.f : 1.f;
+    uint16_t* ybase = reinterpret_cast<uint16_t*>(dw_hi ? A.yh : A.yl) + ((size_t)n * Cd + dc) * dHd * dWd + 8 * gimg;
 
     for (int c = c0; c <= c1; ++c) {
       // ---- 1. the chunk's inputs have landed -----------------------------------------------------------
@@ -343,7 +353,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
         const int need = (c + 1 < cpi ? c + 1 : cpi - 1) - cl0 + 1;
         while (lo_waited < need) {
           const uint32_t ql = lq0 + (uint32_t)lo_waited;
-          mbar_wait_a(bar_l + 8 * (ql & 3u), (ql >> 2) & 1u);
+          mbar_wait_a(bar_l + 8 * (ql % 3u), (ql / 3u) & 1u);
           ++lo_waited;
         }
       }
@@ -351,13 +361,15 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       const uint32_t xh = hi_stage(c), xl = lo_stage(c);
       // ---- 2. resample both ways ------------------------------------------------------------------------
       {
-        const int n_up = Cli * GH, n_pool = Clo > 0 ? Chi * GL : 0;
+        const int n_up = Cli * GR, n_pool = Clo > 0 ? Chi * GLR : 0;
         for (int task = tid; task < n_up + n_pool; task += nthreads) {
           if (task < n_up) {
             // bilinear x2 (align_corners=False): hi pixel 2j = 1/4 lo[j-1] + 3/4 lo[j], 2j+1 = 3/4 lo[j] + 1/4 lo[j+1], clamped
-            const int cl_ = task / GH, g = task - cl_ * GH;
-            const int gl = g >> 1, hf = g & 1;
-            const uint32_t offM = (uint32_t)(gl * SL + cl_) * 16u + 8u * hf;
+            const int cl_ = task / GR, gr = task - cl_ * GR;                    // gr: group in the tile row; g: in the image row
+            const int g = gs0 - hl + gr;
+            if (g < 0 || g >= GH) continue;                                       // halo group outside the image: stays zero, never read
+            const int glr = (g >> 1) - (gs0 >> 1) + hl, hf = g & 1;               // lo group in the lo tile row
+            const uint32_t offM = (uint32_t)(glr * SL + cl_) * 16u + 8u * hf;
             const uint32_t offL = hf ? offM - 2u : (g == 0 ? offM : offM - (uint32_t)SL * 16u + 14u);
             const uint32_t offR = hf ? (g == GH - 1 ? offM + 6u : offM + (uint32_t)SL * 16u - 8u) : offM + 8u;
             float hrow[4][8];
@@ -366,7 +378,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
             for (int k = 0; k < 4; ++k) {
               int R = 2 * c - 1 + k;
               R = R < 0 ? 0 : (R > Hl - 1 ? Hl - 1 : R);
-              const uint32_t rowb = lo_stage(R >> 1) + (uint32_t)((R & 1) * GL * SL) * 16u;
+              const uint32_t rowb = lo_stage(R >> 1) + (uint32_t)((R & 1) * GLR * SL) * 16u;
               const uint2 m = lds64(rowb + offM);
               const uint16_t vl = lds16(rowb + offL), vr = lds16(rowb + offR);
               const uint16_t v0 = (uint16_t)m.x, v1 = (uint16_t)(m.x >> 16), v2 = (uint16_t)m.y, v3 = (uint16_t)(m.y >> 16);
@@ -379,7 +391,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
               hrow[k][6] = Pack<T>::fma16(v3, w75, Pack<T>::fma16(v2, w25, 0.f));
               hrow[k][7] = Pack<T>::fma16(v3, w75, Pack<T>::fma16(vr, w25, 0.f));
             }
-            const uint32_t dst = xh + (uint32_t)(g * SH + Chi + cl_) * 16u;
+            const uint32_t dst = xh + (uint32_t)(gr * SH + Chi + cl_) * 16u;
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
               // hi row 4c+rr: rr 0: (k0 1/4, k1 3/4); 1: (k1 3/4, k2 1/4); 2: (k1 1/4, k2 3/4); 3: (k2 3/4, k3 1/4)
@@ -389,17 +401,21 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
               o.y = Pack<T>::from_f2(0.75f * hrow[km][2] + 0.25f * hrow[ko][2], 0.75f * hrow[km][3] + 0.25f * hrow[ko][3]);
               o.z = Pack<T>::from_f2(0.75f * hrow[km][4] + 0.25f * hrow[ko][4], 0.75f * hrow[km][5] + 0.25f * hrow[ko][5]);
               o.w = Pack<T>::from_f2(0.75f * hrow[km][6] + 0.25f * hrow[ko][6], 0.75f * hrow[km][7] + 0.25f * hrow[ko][7]);
-              sts128(dst + (uint32_t)(rr * GH * SH) * 16u, o);
+              sts128(dst + (uint32_t)(rr * GR * SH) * 16u, o);
             }
           } else {
-            // max_pool2d 2x2: lo group gl of lo rows 2c, 2c+1 from hi groups 2gl, 2gl+1 of the 4 hi rows
-            const int t = task - n_up, ch = t / GL, gl = t - ch * GL;
-            const uint32_t src = xh + (uint32_t)(2 * gl * SH + ch) * 16u;
-            const uint32_t dst = xl + (uint32_t)(gl * SL + Cli + ch) * 16u;
+            // max_pool2d 2x2: lo group glr of lo rows 2c, 2c+1 from the two hi groups under it, 4 hi rows.  With a halo the
+            // outer hi group of the tile's first / last lo group is not in the tile: that half is never read downstream.
+            const int t = task - n_up, ch = t / GLR, glr = t - ch * GLR;
+            const int ga = 2 * glr - hl;                                          // tile index of the left hi group
+            const bool okA = ga >= 0, okB = ga + 1 < GR;
+            const uint32_t src = xh + (uint32_t)(ga * SH + ch) * 16u;
+            const uint32_t dst = xl + (uint32_t)(glr * SL + Cli + ch) * 16u;
 #pragma unroll
             for (int lr = 0; lr < 2; ++lr) {
-              const uint32_t r0 = src + (uint32_t)(2 * lr * GH * SH) * 16u, r1 = r0 + (uint32_t)(GH * SH) * 16u;
-              const uint4 a0 = lds128(r0), a1 = lds128(r0 + (uint32_t)SH * 16u), c0_ = lds128(r1), c1_ = lds128(r1 + (uint32_t)SH * 16u);
+              const uint32_t r0 = src + (uint32_t)(2 * lr * GR * SH) * 16u, r1 = r0 + (uint32_t)(GR * SH) * 16u;
+              const uint4 a0 = lds128(okA ? r0 : ZERO), a1 = lds128(okB ? r0 + (uint32_t)SH * 16u : ZERO), c0_ = lds128(okA ? r1 : ZERO),
+                          c1_ = lds128(okB ? r1 + (uint32_t)SH * 16u : ZERO);
               auto hmax = [](uint32_t u, uint32_t v) {       // two lo pixels from the vertical maxima of 4 hi pixels
                 return __byte_perm(Pack<T>::max2(u, __byte_perm(u, 0u, 0x1032)), Pack<T>::max2(v, __byte_perm(v, 0u, 0x1032)), 0x5410);
               };
@@ -408,7 +424,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
               o.y = hmax(Pack<T>::max2(a0.z, c0_.z), Pack<T>::max2(a0.w, c0_.w));
               o.z = hmax(Pack<T>::max2(a1.x, c1_.x), Pack<T>::max2(a1.y, c1_.y));
               o.w = hmax(Pack<T>::max2(a1.z, c1_.z), Pack<T>::max2(a1.w, c1_.w));
-              sts128(dst + (uint32_t)(lr * GL * SL) * 16u, o);
+              sts128(dst + (uint32_t)(lr * GLR * SL) * 16u, o);
             }
           }
         }
@@ -421,7 +437,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       if (warp == nwarps - 1 && lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         if (c >= c0 + 1 && c + 1 <= c1) issue_hi(c + 1);                 // stage of chunk c-1: its T1 was consumed
-        if (c + 3 <= cl1) issue_lo(c + 3);                               // stage of lo chunk c-1: last read by this chunk's up-sample
+        if (c + 2 <= cl1) issue_lo(c + 2);                               // stage of lo chunk c-1: last read by this chunk's up-sample
       }
       if (lane == 0) {
         for (int b = warp; b < nbh + nbl; b += nwarps) {
@@ -444,11 +460,11 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
           mbar_wait_a(bar_m + 8u * b, mq & 1u);                      // the block's MMAs (and all earlier ones) have completed
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           if (b < nbh)
-            ils_epilogue_warp<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * NH), xh, (uint32_t)SH * 16u, b * 16 + qd * 4, 4 * GH, Cho,
+            ils_epilogue_warp<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * NH), xh, (uint32_t)SH * 16u, b * 16 + qd * 4, 4 * GR, Cho,
                                  EPI, EPI + 256u, DUMMY, lane);
           else
             ils_epilogue_warp<T>(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(nbh * NH + (b - nbh) * NL), T1L, (uint32_t)ST * 16u,
-                                 (b - nbh) * 16 + qd * 4, 2 * GL, Clo, EPI + 512u, EPI + 768u, DUMMY, lane);
+                                 (b - nbh) * 16 + qd * 4, 2 * GLR, Clo, EPI + 512u, EPI + 768u, DUMMY, lane);
         }
       }
       ++mq;
@@ -493,7 +509,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
 #undef ILS_MARK
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(A.tmem_cols) : "memory");
 }
 
 }  // namespace csnet

@@ -156,6 +156,7 @@ struct csnet_plan {
   std::vector<float> h_blob;                      // host copy of the blob (epilogue tables of the streaming ILBlock kernel)
   std::vector<char> op_ils;                       // per op: the streaming ILBlock kernel (il_stream.cuh) can run it
   int num_sms = 148;
+  int ils_force_ns = 0;                           // CSNET_ILS_NS=k: force k column strips (0: automatic)
   bool ils_enabled = true;                        // CSNET_ILS=0 at plan creation: tiled kernel only
   int ils_min_chunks = 592;                       // batches with fewer 4-row chunks per ILBlock run the tiled kernel
   // host-buffer pipeline (csnet_plan_run_host): copy streams, ping-pong staging, ordering events
@@ -436,6 +437,7 @@ bool encode_group_map(CUtensorMap* tm, const void* base, int N, int C, int H, in
 }
 
 // Geometry of the streaming ILBlock kernel for an op; false if the op does not qualify (the tiled kernel runs it).
+// Picks the column-strip split: the fewest strips that fit the thread / shared-memory / TMEM limits.
 bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out) {
   if (!P.ils_enabled || op.kind != CSNET_OP_ILBLOCK || op.paths[0].ksize != 1 || encode_tiled_fn() == nullptr) return false;
   const csnet_tensor_desc &Xh = P.tensors[op.paths[0].src], &Xl = P.tensors[op.paths[1].src], &Yh = P.tensors[op.dst];
@@ -453,31 +455,52 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   A.SL = A.Clo > 0 ? A.K16 + 1 : (A.Cli | 1);
   A.ST = A.NL + 1;
   A.cpi = A.H / 4;
-  A.hi_warps = (A.Cho * A.GH + 31) / 32;
-  A.lo_warps = (A.Clo * A.GL + 31) / 32;
-  if (A.hi_warps + A.lo_warps < 4) A.hi_warps = 4 - A.lo_warps;       // the epilogue needs one warp per TMEM lane quarter
-  const int warps = A.hi_warps + A.lo_warps;
-  if (warps * 32 > csnet::kIlsMaxThreads || A.SH > 256 || A.SL > 256 || A.GH > 256) return false;
-  const int nbh = (4 * A.GH + 15) / 16, nbl = A.Clo > 0 ? (2 * A.GL + 15) / 16 : 0;
-  if (nbh * A.NH + nbl * A.NL > 512 || nbh + nbl > 16) return false;                       // fp32 accumulators of a chunk: TMEM columns
   auto r128 = [](int v) { return (v + 127) / 128 * 128; };
-  A.lo_stage_bytes = r128(2 * A.GL * A.SL * 16);
-  A.hi_stage_bytes = r128(4 * A.GH * A.SH * 16);
-  A.off_xl = 0;
-  A.off_xh = csnet::kIlsLoStages * A.lo_stage_bytes;
-  A.off_t1l = A.off_xh + csnet::kIlsHiStages * A.hi_stage_bytes;
-  A.off_wbh = A.off_t1l + r128(2 * A.GL * A.ST * 16);
-  A.off_wbl = A.off_wbh + r128(A.NH * A.K16 * 2);
-  A.off_bar = A.off_wbl + r128(A.NL * A.K16 * 2);
-  A.off_zero = A.off_bar + 256;
-  A.off_epi = A.off_zero + 128;                          // 4 tables of 64 floats + 512 bytes of scratch rows
-  // the last accumulator block of a chunk may read (never use) up to 15 pixel groups past the chunk: keep them inside
-  A.smem_bytes = A.off_epi + 1536 + 16 * 65 * 16 + 128;
-  if (A.smem_bytes > 227 * 1024) return false;
-  // epilogue tables
-  if ((int64_t)P.h_blob.size() != P.blob_floats) {
-    // geometry query before the blob exists (csnet_plan_create): tables stay zero
-  } else {
+  bool found = false;
+  double best_cost = 0;
+  csnet::IlsArgs best{};
+  for (int ns = 1; ns <= 16; ++ns) {
+    if (P.ils_force_ns > 0 && ns != P.ils_force_ns) continue;
+    if (A.GH % ns || (A.GH / ns) % 2) continue;
+    csnet::IlsArgs T = A;
+    T.ns = ns; T.gsn = A.GH / ns; T.hl = ns > 1 ? 1 : 0;
+    T.GR = T.gsn + 2 * T.hl; T.GLR = T.gsn / 2 + 2 * T.hl;
+    T.hi_warps = (T.Cho * T.gsn + 31) / 32;
+    T.lo_warps = (T.Clo * (T.gsn / 2) + 31) / 32;
+    if (T.hi_warps + T.lo_warps < 4) T.hi_warps = 4 - T.lo_warps;       // the epilogue needs one warp per TMEM lane quarter
+    const int warps = T.hi_warps + T.lo_warps;
+    if (warps * 32 > csnet::kIlsMaxThreads || T.SH > 256 || T.SL > 256 || T.GR > 256) continue;
+    const int nbh = (4 * T.GR + 15) / 16, nbl = T.Clo > 0 ? (2 * T.GLR + 15) / 16 : 0;
+    const int cols = nbh * T.NH + nbl * T.NL;                              // fp32 accumulators of a chunk: TMEM columns
+    if (cols > 512 || nbh + nbl > 16) continue;
+    T.tmem_cols = 32;
+    while (T.tmem_cols < cols) T.tmem_cols *= 2;
+    T.lo_stage_bytes = r128(2 * T.GLR * T.SL * 16);
+    T.hi_stage_bytes = r128(4 * T.GR * T.SH * 16);
+    T.off_xl = 0;
+    T.off_xh = csnet::kIlsLoStages * T.lo_stage_bytes;
+    T.off_t1l = T.off_xh + csnet::kIlsHiStages * T.hi_stage_bytes;
+    T.off_wbh = T.off_t1l + r128(2 * T.GLR * T.ST * 16);
+    T.off_wbl = T.off_wbh + r128(T.NH * T.K16 * 2);
+    T.off_bar = T.off_wbl + r128(T.NL * T.K16 * 2);
+    T.off_zero = T.off_bar + 256;
+    T.off_epi = T.off_zero + 128;                          // 4 tables of 64 floats + 512 bytes of scratch rows
+    int end = T.off_epi + 1536;
+    // the last accumulator block of a chunk reads (never uses) up to 15 pixel groups past the chunk: keep them inside
+    const int over_h = T.off_xh + T.hi_stage_bytes + nbh * 16 * T.SH * 16, over_l = T.off_xl + 2 * T.lo_stage_bytes + nbl * 16 * T.SL * 16;
+    end = over_h > end ? over_h : end;
+    end = over_l > end ? over_l : end;
+    T.smem_bytes = end + 128;
+    if (T.smem_bytes > 227 * 1024) continue;
+    // cost model: the depthwise tail (~55 % of a chunk) does not see the halo groups, everything else scales with them.
+    // (Narrow strips do NOT buy a second CTA per SM: a kernel that touches tcgen05 is resident once per SM — measured with
+    // scripts/occ_probe.cu: occupancy 1 for any kernel with tcgen05.alloc / commit, whatever its shared memory.)
+    const double cost = 0.55 + 0.45 * T.GR / T.gsn;
+    if (!found || cost < best_cost) { best = T; best_cost = cost; found = true; }
+  }
+  if (!found) return false;
+  A = best;
+  if ((int64_t)P.h_blob.size() == P.blob_floats) {       // (a geometry query before the blob exists leaves the tables zero)
     auto f = [&](int e) { return op.ext_off[e] >= 0 ? P.h_blob.data() + op.ext_off[e] : nullptr; };
     for (int c = 0; c < A.Cho; ++c) { A.bias_h[c] = f(2)[c]; A.sm1_h[c] = f(3)[c] - 1.f; }
     for (int c = 0; c < A.Clo; ++c) { A.bias_l[c] = f(4)[c]; A.sm1_l[c] = f(5)[c] - 1.f; }
@@ -675,6 +698,7 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   P->op_ils.assign(P->ops.size(), 0);
   P->ils_min_chunks = 4 * P->num_sms;
   if (const char* e1 = getenv("CSNET_ILS")) P->ils_enabled = e1[0] != '0';
+  if (const char* e3 = getenv("CSNET_ILS_NS")) P->ils_force_ns = atoi(e3);
   if (const char* e2 = getenv("CSNET_ILS_MIN_CHUNKS")) P->ils_min_chunks = atoi(e2);
   int ils_smem_max = 0;
   for (size_t i = 0; i < P->ops.size(); ++i) {
@@ -687,6 +711,9 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     // always the architectural maximum: plans created later must not lower the limit an earlier plan relies on
     e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // two CTAs of <= 113 KB share an SM only with the full shared-memory carve-out
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(il_stream): ") + cudaGetErrorString(e));
   }
   if (P->il_smem_max > 0) {
@@ -805,13 +832,13 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     A.dw1h = {f(6), f(7), f(8)};   A.dw1l = {f(9), f(10), f(11)};
     A.dw2h = {f(12), f(13), f(14)}; A.dw2l = {f(15), f(16), f(17)};
     A.N = N;
-    A.total_chunks = N * A.cpi;
+    A.total_chunks = N * A.ns * A.cpi;
     CUtensorMap tmH, tmL;
-    if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GH, 4) ||
-        !encode_group_map(&tmL, P->tensor_ptr(op.paths[1].src, N, ext_ptrs), N, A.Cli, A.H / 2, A.W / 2, A.SL, A.GL, 2))
+    if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GR, 4) ||
+        !encode_group_map(&tmL, P->tensor_ptr(op.paths[1].src, N, ext_ptrs), N, A.Cli, A.H / 2, A.W / 2, A.SL, A.GLR, 2))
       return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock)");
     int grid = A.total_chunks / 4;
-    grid = grid < 1 ? 1 : (grid > P->num_sms ? P->num_sms : grid);
+    grid = grid < 1 ? 1 : (grid > P->num_sms ? P->num_sms : grid);     // persistent: one CTA per SM
     static const bool dbg = [] { const char* e = getenv("CSNET_ILS_DBG"); return e && e[0] == '1'; }();
     static unsigned long long* dbg_buf = nullptr;
     if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(unsigned long long));
@@ -824,6 +851,9 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
       cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) m[k] += (double)h[(size_t)b * 8 + k] / grid;
+      int occ = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csnet::il_stream_kernel<__half, true>, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes);
+      fprintf(stderr, "[ils ns %d grid %d threads %d smem %d tmem %d occupancy %d] ", A.ns, grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, A.tmem_cols, occ);
       fprintf(stderr, "[ils %dx%d C %d+%d->%d+%d] cycles/CTA: load-wait %.0f resample %.0f syncA %.0f issue %.0f epilogue %.0f syncB %.0f dw %.0f tail %.0f\n",
               A.H, A.W, A.Chi, A.Cli, A.Cho, A.Clo, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
     }
