@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op time table to stderr")
+    ap.add_argument("--train-batch", type=int, default=32, help="images per GPU of the `train` sub-record's step")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the train sub-record, the eager-GPU baseline and the extra configs (profiling runs)")
     return ap.parse_args()
 
 
@@ -181,8 +184,140 @@ def op_bytes(prog, op, n):
         seen.add(key)
         t = prog.tensors[q.src]
         total += q.cin * t.H * t.W * ir.DTYPE_BYTES[t.dtype]
-    d = prog.tensors[op.dst]
-    return n * (total + d.C * d.H * d.W * ir.DTYPE_BYTES[d.dtype])
+    for t_id in (op.dst, getattr(op, "dst2", -1)):               # a fused ILBlock writes two tensors (hi and lo branch)
+        if t_id is None or t_id < 0:
+            continue
+        d = prog.tensors[t_id]
+        total += d.C * d.H * d.W * ir.DTYPE_BYTES[d.dtype]
+    return n * total
+
+
+def gpu_eager_baseline(a, dev, steps=5):
+    """eager PyTorch on the SAME B200 — the oracle's functional forward (exactly the reference module's
+    ATen calls: F.conv2d / batch_norm / prelu / pooling / interpolate -> cuDNN / ATen kernels), fp32 and torch.autocast(fp16),
+    NCHW as the reference runs.  A measured baseline, not the product: none of our kernels run here."""
+    import torch
+
+    from oracle import csnet_oracle as O
+    from sod100k_b200 import checkpoints, synth
+
+    cfg, sd = checkpoints.load_npz(a.model)
+    sd = {k: torch.from_numpy(v).to(dev) for k, v in sd.items()}
+    B, S = a.batch, a.size
+    x = torch.from_numpy(synth.randn_images(min(B, 32), S, S, 1234)).repeat((B + 31) // 32, 1, 1, 1)[:B].to(dev)
+    out = {}
+    for name, ctx in (("fp32", None), ("autocast_fp16", torch.autocast("cuda", dtype=torch.float16))):
+        try:
+            def step():
+                with torch.no_grad():
+                    if ctx is None:
+                        return O.csnet_forward(cfg, sd, x)
+                    with ctx:
+                        return O.csnet_forward(cfg, sd, x)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms}
+        except Exception as e:                                     # e.g. out of memory at an unusual batch size
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    out["what"] = (f"oracle/csnet_oracle.py functional forward (the reference module's own ATen / cuDNN calls) on this GPU, "
+                   f"{B} x {S}x{S}, eval, no_grad, device-resident input, {steps} steps after 2 warm-ups")
+    return out
+
+
+def extra_config(a, model_name, size, batch, dev, steps=5):
+    """Device-resident img/s of another inference configuration (same kernels, same timing rules), for the `configs` array."""
+    import torch
+
+    from sod100k_b200 import checkpoints, ir, roofline, synth
+
+    model, cfg, _ = checkpoints.build_from_npz(model_name)
+    model.cuda(dev.index).eval()
+    model.set_precision(a.dtype)
+    x = torch.from_numpy(synth.randn_images(min(batch, 16), size, size, 1234)).repeat((batch + 15) // 16, 1, 1, 1)[:batch].to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model(x)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model(x)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    nb = roofline.bytes_per_image(cfg, size, size, ir.DTYPE_BYTES[ir.DTYPE_NAMES[a.dtype]], "block")
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": f"{model_name} inference, {batch} x {size}x{size}, {a.dtype}", "value": batch / ms * 1e3, "unit": UNIT,
+            "ms_per_step": ms, "bytes_per_image_block_fused": nb, "achieved_gbs": batch / ms * 1e3 * nb / 1e9}
+
+
+def train_record(a, world, rank, local, dev, steps=5, warmup=3):
+    """fwd + BCE + bwd + [one NCCL all-reduce of the flat gradient bucket] + Adam, images/s over all ranks (max-over-ranks time).
+    Every rank runs it (the all-reduce is a collective); rank 0 returns the record."""
+    import torch
+    import torch.distributed as dist
+
+    from sod100k_b200 import checkpoints, roofline, synth, train_ops
+    from sod100k_b200.trainer import Trainer
+
+    model, cfg, _ = checkpoints.build_from_npz(a.model)
+    model.cuda(local)
+    tr = Trainer(model, lr=1e-4, weight_decay=5e-3)
+    B, S = a.train_batch, a.size
+    xh = torch.from_numpy(synth.randn_images(B, S, S, 1234 + rank)).pin_memory()
+    th = torch.from_numpy(synth.random_masks(B, S, S, 1236 + rank)).pin_memory()
+    xd, td = xh.to(dev), th.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(warmup):
+        tr.step(xd, td)
+    l0 = train_ops.LAUNCHES
+    ms = timed(lambda: tr.step(xd, td), steps)
+    launches = train_ops.LAUNCHES - l0
+    ms_e2e = timed(lambda: tr.step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)).item(), steps)
+    el = roofline.forward_elements(cfg, S, S)
+    train_bytes = int(2.51 * el["module"]) * 4                  # 3*sum(I) + 2*sum(O) over modules (SURVEY 8d), fp32 storage
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    ips, ips_e2e = B * world * steps / (ms * 1e-3), B * world * steps / (ms_e2e * 1e-3)
+    bucket_bytes = int(tr.flat.bucket.numel() * 4)
+    del tr, model
+    torch.cuda.empty_cache()
+    return {"metric": "images/sec CSNet fwd+BCE+bwd+allreduce+Adam 224x224", "value": ips, "unit": UNIT, "ms_per_step": ms / steps,
+            "steps": steps, "warmup": warmup, "per_gpu_batch": B, "global_batch": B * world, "ranks": world, "dtype": "fp32",
+            "collective": "one NCCL all-reduce (sum / world) of the flat fp32 gradient bucket per step" if world > 1 else
+                          "none at 1 GPU (the flat gradient bucket is all-reduced when ranks > 1)",
+            "allreduce_bytes": bucket_bytes, "gpu_launches": launches,
+            "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": int((xh.numel() + th.numel()) * 4), "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "hbm", "achieved": ips / world * train_bytes / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": ips / world * train_bytes / 1e9 / peak, "bytes_per_image_module_fused_fp32": train_bytes}}
 
 
 def run_ours(a):
@@ -249,6 +384,15 @@ def run_ours(a):
         per_op = plan.profile(B, [x_dev.data_ptr(), torch.empty_like(y_host, device=dev).data_ptr()], stream.cuda_stream)
         per_op = [min(u, v) for u, v in zip(per_op, plan.profile(B, [x_dev.data_ptr(), torch.empty_like(y_host, device=dev).data_ptr()], stream.cuda_stream))]
 
+    # train step with the gradient all-reduce: every rank takes part (the one collective of the design)
+    train = None
+    if not a.no_extras:
+        del x_dev
+        torch.cuda.empty_cache()
+        try:
+            train = train_record(a, world, rank, local, dev)
+        except Exception as e:
+            train = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -292,6 +436,20 @@ def run_ours(a):
                      "net": {"bytes_per_image_block_fused": net_bytes,
                              "achieved": ips / world * net_bytes / 1e9, "frac": ips / world * net_bytes / 1e9 / peak}},
     }
+    if not a.no_extras:
+        out["train"] = train
+        del plan, eng, model
+        torch.cuda.empty_cache()
+        out["gpu_eager_baseline"] = gpu_eager_baseline(a, dev)
+        out["configs"] = []
+        for mname, size, batch in ((a.model, 512, 64), ("csnet-L-x1" if a.model != "csnet-L-x1" else "csnet-L-x2", a.size, a.batch)):
+            try:
+                out["configs"].append(extra_config(a, mname, size, batch, dev))
+            except Exception as e:
+                out["configs"].append({"workload": f"{mname} {batch} x {size}x{size}", "unavailable": f"{type(e).__name__}: {e}"[:200]})
+        for c in out["configs"]:
+            if "achieved_gbs" in c:
+                c["roofline_net_frac"] = c["achieved_gbs"] / peak
     if not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(out))

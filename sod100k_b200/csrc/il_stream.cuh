@@ -18,6 +18,11 @@
 //              in registers: dw3x3+BN+PReLU twice with no halo recomputation in y, no shared-memory round trip for
 //              T2, 16-byte coalesced stores of the block output.  (mixed-precision FMA: fp16 x fp16 + fp32.)
 //
+// Stem form (kStem; the first block, csnet.py:60-71: both branches are 3x3 convs of the fp32 image, the lo one of its 2x2
+// max-pool): the TMA ring holds 4-row blocks of the fp32 image (4-D map, zero fill outside the image = the conv padding);
+// instead of the resample pass the threads build the im2col operand (27 slots: ci, ky, kx) of the hi chunk and of the
+// lo chunk (pooling on the fly) in the same [row][group][slot][8 px] layout; GEMM, epilogue and depthwise tail are shared.
+//
 // An image is cut into `ns` column strips of gsn 8-pixel groups (gsn even); a CTA's tile of a strip carries one halo
 // group on each side when ns > 1 (hl = 1: the TMA box starts one group early, out-of-image groups arrive as zeros).
 // Narrow strips let two CTAs share an SM (<= 113 KB shared memory, <= 256 TMEM columns each), so one CTA's waits
@@ -48,6 +53,8 @@ struct IlsArgs {
   int32_t ns, gsn, hl;                // column strips per image, hi groups per strip (even), halo groups per side (0 / 1)
   int32_t GR, GLR;                    // groups per row of a CTA's tile: gsn + 2 hl, gsn/2 + 2 hl
   int32_t tmem_cols;                  // TMEM columns to allocate (power of two >= the chunk's accumulators)
+  int32_t Ci, BW;                     // stem form: image channels; width in floats of an image block in shared memory (8 GR + 8)
+  int32_t off_xlo;                    // stem form: the lo chunk's GEMM operand buffer
   int32_t cpi, total_chunks;          // chunks per image strip (H/4), N * ns * cpi
   int32_t hi_warps, lo_warps;         // warps of the depthwise tail
   int32_t hi_stage_bytes, lo_stage_bytes;
@@ -58,6 +65,10 @@ struct IlsArgs {
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
                ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
@@ -205,7 +216,7 @@ __device__ __forceinline__ void ils_epilogue_warp(uint32_t taddr, uint32_t tile,
   }
 }
 
-template <typename T, bool kTiming = false>
+template <typename T, bool kTiming = false, bool kStem = false>
 __global__ void __launch_bounds__(kIlsMaxThreads, 1)
 il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL) {
   extern __shared__ uint8_t smem_raw[];
@@ -252,6 +263,18 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       }
     }
     if (tid < 16) reinterpret_cast<uint32_t*>(gbase + A.off_zero)[tid] = 0u;
+    if (kStem) {
+      // K-padding slots [Chi, K16) of both operand buffers: zero once (the im2col build never touches them, the in-place
+      // epilogue only writes slots < NH <= Chi)
+      // (both hi buffers: the build alternates between them so that it never overwrites the T1 the depthwise tail still reads)
+      const int per = K16 - Chi, padh = per * 4 * GR, padl = per * 2 * GLR;
+      for (int i = tid; i < 2 * padh + padl; i += nthreads) {
+        const bool hb = i < 2 * padh;
+        const int st = hb ? i / padh : 0, j = hb ? i - st * padh : i - 2 * padh, g_ = j / per, k_ = Chi + (j - g_ * per);
+        sts128((hb ? XH + (uint32_t)st * (uint32_t)A.hi_stage_bytes + (uint32_t)(g_ * SH + k_) * 16u
+                   : sbase + A.off_xlo + (uint32_t)(g_ * SL + k_) * 16u), make_uint4(0u, 0u, 0u, 0u));
+      }
+    }
     if (tid < kIlsMaxC) {
       float* ep = reinterpret_cast<float*>(gbase + A.off_epi);
       ep[tid] = A.bias_h[tid]; ep[kIlsMaxC + tid] = A.sm1_h[tid]; ep[2 * kIlsMaxC + tid] = A.bias_l[tid]; ep[3 * kIlsMaxC + tid] = A.sm1_l[tid];
@@ -295,7 +318,8 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
   const uint32_t idesc_h = (1u << 4) | (1u << 15) | ((uint32_t)(NH >> 3) << 17) | (8u << 24);   // f16 x f16 -> f32, A MN-major, M = 128
   const uint32_t idesc_l = (1u << 4) | (1u << 15) | ((uint32_t)(NL >> 3) << 17) | (8u << 24);
   const int nbh = (4 * GR + 15) >> 4, nbl = NL > 0 ? (2 * GLR + 15) >> 4 : 0;
-  const uint32_t hi_tx = (uint32_t)(64 * SH * GR), lo_tx = (uint32_t)(32 * SL * GLR);
+  const uint32_t hi_tx = (uint32_t)(64 * SH * GR), lo_tx = kStem ? (uint32_t)(A.BW * 4 * A.Ci * 4) : (uint32_t)(32 * SL * GLR);
+  const uint32_t XLO = sbase + A.off_xlo;
 
   // ---- the CTA's range of the (image, chunk) sequence ------------------------------------------------
   int ra = (int)((long long)blockIdx.x * A.total_chunks / gridDim.x);
@@ -326,12 +350,15 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
     auto issue_lo = [&](int cl) {
       const uint32_t q = lq0 + (uint32_t)(cl - cl0), bar = bar_l + 8 * (q % 3u);
       mbar_expect_tx_a(bar, lo_tx);
-      tma_load_5d(lo_stage(cl), &tmL, bar, 0, 0, (gs0 >> 1) - hl, 2 * cl, n);
+      if (kStem) tma_load_4d_a(lo_stage(cl), &tmL, bar, 8 * (gs0 - hl) - 4, 4 * cl, 0, n);     // image block: rows [4 cl, 4 cl + 4), all channels
+      else tma_load_5d(lo_stage(cl), &tmL, bar, 0, 0, (gs0 >> 1) - hl, 2 * cl, n);
     };
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      issue_hi(c0);
-      if (c0 + 1 <= c1) issue_hi(c0 + 1);
+      if (!kStem) {
+        issue_hi(c0);
+        if (c0 + 1 <= c1) issue_hi(c0 + 1);
+      }
       for (int cl = cl0; cl <= cl1 && cl <= c0 + 1; ++cl) issue_lo(cl);
     }
     int lo_waited = 0;
@@ -349,7 +376,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       // ---- 1. the chunk's inputs have landed -----------------------------------------------------------
       {
         const uint32_t q = hq0 + (uint32_t)(c - c0);
-        mbar_wait_a(bar_h + 8 * (q & 1u), (q >> 1) & 1u);
+        if (!kStem) mbar_wait_a(bar_h + 8 * (q & 1u), (q >> 1) & 1u);
         const int need = (c + 1 < cpi ? c + 1 : cpi - 1) - cl0 + 1;
         while (lo_waited < need) {
           const uint32_t ql = lq0 + (uint32_t)lo_waited;
@@ -358,9 +385,61 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
         }
       }
       ILS_MARK(0);
-      const uint32_t xh = hi_stage(c), xl = lo_stage(c);
+      const uint32_t xh = hi_stage(c), xl = kStem ? XLO : lo_stage(c);
+      if (kStem) {
+        // ---- 2s. im2col of the image chunk (hi) and of its 2x2 max-pool (lo): a task = one (row, group, ci, ky) and makes
+        //          the three kx slots from one 10-pixel window -----------------------------------------------------------
+        const int Ci = A.Ci, BW = A.BW;
+        const int n_hi = 4 * GR * Ci * 3, n_lo = Clo > 0 ? 2 * GLR * Ci * 3 : 0;
+        for (int task = tid; task < n_hi + n_lo; task += nthreads) {
+          const bool hb = task < n_hi;
+          const int t = hb ? task : task - n_hi, Gt = hb ? GR : GLR;
+          const int ck = t % (Ci * 3), rg = t / (Ci * 3);               // ck = ci * 3 + ky; rg = row * Gt + group
+          const int ci = ck / 3, ky = ck - ci * 3, r = rg / Gt, g = rg - r * Gt;
+          float f[10];
+          if (hb) {
+            const int yy = 4 * c + r + ky - 1;                           // image row of this tap row
+            if (yy >= 0 && yy < H) {
+              const uint32_t a = lo_stage(yy >> 2) + (uint32_t)(((ci * 4 + (yy & 3)) * BW + 8 * g + 3) * 4);
+              const uint4 m0 = lds128(a + 4u), m1 = lds128(a + 20u);
+              f[0] = __uint_as_float(lds32(a)); f[9] = __uint_as_float(lds32(a + 36u));
+              f[1] = __uint_as_float(m0.x); f[2] = __uint_as_float(m0.y); f[3] = __uint_as_float(m0.z); f[4] = __uint_as_float(m0.w);
+              f[5] = __uint_as_float(m1.x); f[6] = __uint_as_float(m1.y); f[7] = __uint_as_float(m1.z); f[8] = __uint_as_float(m1.w);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 10; ++j) f[j] = 0.f;
+            }
+          } else {
+            const int yl = 2 * c + r + ky - 1;                           // lo row of this tap row: max of image rows 2 yl, 2 yl + 1
+            const int col0 = 16 * g - 8 * hl + 2;                        // block column of image x = 2 (xl0 - 1)
+            if (yl >= 0 && yl < Hl) {
+              const uint32_t a = lo_stage(yl >> 1) + (uint32_t)(((ci * 4 + ((2 * yl) & 3)) * BW) * 4);
+#pragma unroll
+              for (int j = 0; j < 10; ++j) {
+                const int col = col0 + 2 * j;
+                float v = 0.f;
+                if (col >= 0 && col + 1 < BW) {                          // outside: the never-read outer half of a halo group
+                  const uint2 u0 = lds64(a + (uint32_t)col * 4u), u1 = lds64(a + (uint32_t)(col + BW) * 4u);
+                  v = fmaxf(fmaxf(__uint_as_float(u0.x), __uint_as_float(u0.y)), fmaxf(__uint_as_float(u1.x), __uint_as_float(u1.y)));
+                }
+                f[j] = v;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 10; ++j) f[j] = 0.f;
+            }
+          }
+          const uint32_t e0 = Pack<T>::from_f2(f[0], f[1]), e1 = Pack<T>::from_f2(f[2], f[3]), e2 = Pack<T>::from_f2(f[4], f[5]),
+                         e3 = Pack<T>::from_f2(f[6], f[7]), e4 = Pack<T>::from_f2(f[8], f[9]);
+          const uint32_t o0 = Pack<T>::from_f2(f[1], f[2]), o1 = Pack<T>::from_f2(f[3], f[4]), o2 = Pack<T>::from_f2(f[5], f[6]),
+                         o3 = Pack<T>::from_f2(f[7], f[8]);
+          const uint32_t dst = (hb ? xh + (uint32_t)(rg * SH) * 16u : xl + (uint32_t)(rg * SL) * 16u) + (uint32_t)(ck * 3) * 16u;
+          sts128(dst, make_uint4(e0, e1, e2, e3));                       // kx = 0: pixels x-1 .. x+6
+          sts128(dst + 16u, make_uint4(o0, o1, o2, o3));                 // kx = 1: x .. x+7
+          sts128(dst + 32u, make_uint4(e1, e2, e3, e4));                 // kx = 2: x+1 .. x+8
+        }
+      } else {
       // ---- 2. resample both ways ------------------------------------------------------------------------
-      {
         const int n_up = Cli * GR, n_pool = Clo > 0 ? Chi * GLR : 0;
         for (int task = tid; task < n_up + n_pool; task += nthreads) {
           if (task < n_up) {
@@ -436,7 +515,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       // ---- 3. next loads (one thread of the last warp); the chunk's MMAs: warp b's elected lane issues block b ----
       if (warp == nwarps - 1 && lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        if (c >= c0 + 1 && c + 1 <= c1) issue_hi(c + 1);                 // stage of chunk c-1: its T1 was consumed
+        if (!kStem && c >= c0 + 1 && c + 1 <= c1) issue_hi(c + 1);       // stage of chunk c-1: its T1 was consumed
         if (c + 2 <= cl1) issue_lo(c + 2);                               // stage of lo chunk c-1: last read by this chunk's up-sample
       }
       if (lane == 0) {

@@ -436,17 +436,33 @@ bool encode_group_map(CUtensorMap* tm, const void* base, int N, int C, int H, in
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 4-D map over the planar fp32 image [N][C][H][W]: box (bw floats, rows, C, 1) -> [c][row][bw] in shared memory, zeros outside.
+bool encode_image_map(CUtensorMap* tm, const void* base, int N, int C, int H, int W, int bw, int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)rows, (cuuint32_t)C, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Geometry of the streaming ILBlock kernel for an op; false if the op does not qualify (the tiled kernel runs it).
 // Picks the column-strip split: the fewest strips that fit the thread / shared-memory / TMEM limits.
 bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out) {
-  if (!P.ils_enabled || op.kind != CSNET_OP_ILBLOCK || op.paths[0].ksize != 1 || encode_tiled_fn() == nullptr) return false;
+  if (!P.ils_enabled || op.kind != CSNET_OP_ILBLOCK || encode_tiled_fn() == nullptr) return false;
   const csnet_tensor_desc &Xh = P.tensors[op.paths[0].src], &Xl = P.tensors[op.paths[1].src], &Yh = P.tensors[op.dst];
   if (Yh.dtype != CSNET_F16) return false;
+  const bool stem = op.paths[0].ksize == 3;                              // stem form: 3x3 convs of the fp32 image (im2col K = 9 Ci)
   csnet::IlsArgs A{};
   A.H = Yh.H; A.W = Yh.W;
-  A.Chi = Xh.C; A.Cli = Xl.C; A.Cho = Yh.C; A.Clo = op.dst2 >= 0 ? P.tensors[op.dst2].C : 0;
+  A.Chi = stem ? Xh.C * 9 : Xh.C; A.Cli = stem ? 0 : Xl.C; A.Cho = Yh.C; A.Clo = op.dst2 >= 0 ? P.tensors[op.dst2].C : 0;
+  A.Ci = stem ? Xh.C : 0;
+  if (stem && (Xh.dtype != CSNET_F32 || A.Chi > 32 || A.W % 4)) return false;
   if (A.W % 16 || A.H % 4 || A.Cho > csnet::kIlsMaxC || A.Clo > csnet::kIlsMaxC || A.Chi + A.Cli > 64) return false;
-  A.K8 = round_up(A.Chi + A.Cli, 8);
+  A.K8 = stem ? 32 : round_up(A.Chi + A.Cli, 8);                      // the compiler packs the stem's weights as [M16][32]
   A.K16 = round_up(A.Chi + A.Cli, 16);
   A.NH = round_up(A.Cho, 16);
   A.NL = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
@@ -475,7 +491,9 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
     if (cols > 512 || nbh + nbl > 16) continue;
     T.tmem_cols = 32;
     while (T.tmem_cols < cols) T.tmem_cols *= 2;
-    T.lo_stage_bytes = r128(2 * T.GLR * T.SL * 16);
+    T.BW = 8 * T.GR + 8;                                                  // stem: image block row = the tile's pixels + 4 on each side
+    if (stem && T.BW > 256) continue;
+    T.lo_stage_bytes = stem ? r128(T.BW * 4 * T.Ci * 4) : r128(2 * T.GLR * T.SL * 16);
     T.hi_stage_bytes = r128(4 * T.GR * T.SH * 16);
     T.off_xl = 0;
     T.off_xh = csnet::kIlsLoStages * T.lo_stage_bytes;
@@ -485,9 +503,11 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
     T.off_bar = T.off_wbl + r128(T.NL * T.K16 * 2);
     T.off_zero = T.off_bar + 256;
     T.off_epi = T.off_zero + 128;                          // 4 tables of 64 floats + 512 bytes of scratch rows
-    int end = T.off_epi + 1536;
+    T.off_xlo = T.off_epi + 1536;                          // stem: GEMM operand of the lo chunk (the ring holds image blocks)
+    int end = T.off_xlo + (stem ? r128(2 * T.GLR * T.SL * 16) : 0);
     // the last accumulator block of a chunk reads (never uses) up to 15 pixel groups past the chunk: keep them inside
-    const int over_h = T.off_xh + T.hi_stage_bytes + nbh * 16 * T.SH * 16, over_l = T.off_xl + 2 * T.lo_stage_bytes + nbl * 16 * T.SL * 16;
+    const int over_h = T.off_xh + T.hi_stage_bytes + nbh * 16 * T.SH * 16,
+              over_l = (stem ? T.off_xlo : T.off_xl + 2 * T.lo_stage_bytes) + nbl * 16 * T.SL * 16;
     end = over_h > end ? over_h : end;
     end = over_l > end ? over_l : end;
     T.smem_bytes = end + 128;
@@ -711,6 +731,7 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     // always the architectural maximum: plans created later must not lower the limit an earlier plan relies on
     e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     // two CTAs of <= 113 KB share an SM only with the full shared-memory carve-out
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -820,7 +841,8 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     gn_stats_kernel<<<dim3(A.groups, N), kThreads, 0, stream>>>(A);
     const int bx = (A.HW + kThreads * 4 - 1) / (kThreads * 4);
     gn_apply_kernel<<<dim3(bx < 1 ? 1 : bx, D.C, N), kThreads, 0, stream>>>(A);
-  } else if (op.kind == CSNET_OP_ILBLOCK && P->op_ils[i] && (int64_t)N * (D.H / 4) >= (int64_t)P->ils_min_chunks) {
+  } else if (op.kind == CSNET_OP_ILBLOCK && P->op_ils[i] && (int64_t)P->max_batch * (D.H / 4) >= (int64_t)P->ils_min_chunks) {
+    // (the choice depends on the plan's max_batch, not on N: every sub-batch of a plan runs the same kernels, bit for bit)
     // streaming kernel (il_stream.cuh): TMA operand tiles, tcgen05 GEMM, register-resident depthwise tail
     csnet::IlsArgs A;
     if (!make_ils(*P, op, &A)) return fail(CSNET_E_UNSUPPORTED, "ILBLOCK op no longer qualifies for the streaming kernel");
@@ -834,8 +856,13 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     A.N = N;
     A.total_chunks = N * A.ns * A.cpi;
     CUtensorMap tmH, tmL;
-    if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GR, 4) ||
-        !encode_group_map(&tmL, P->tensor_ptr(op.paths[1].src, N, ext_ptrs), N, A.Cli, A.H / 2, A.W / 2, A.SL, A.GLR, 2))
+    const bool stem = A.Ci > 0;
+    if (stem) {
+      if (!encode_image_map(&tmL, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Ci, A.H, A.W, A.BW, 4)) 
+        return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock, image)");
+      tmH = tmL;
+    } else if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GR, 4) ||
+               !encode_group_map(&tmL, P->tensor_ptr(op.paths[1].src, N, ext_ptrs), N, A.Cli, A.H / 2, A.W / 2, A.SL, A.GLR, 2))
       return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock)");
     int grid = A.total_chunks / 4;
     grid = grid < 1 ? 1 : (grid > P->num_sms ? P->num_sms : grid);     // persistent: one CTA per SM
@@ -843,9 +870,10 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     static unsigned long long* dbg_buf = nullptr;
     if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(unsigned long long));
     A.dbg = dbg ? dbg_buf : nullptr;
-    if (dbg) csnet::il_stream_kernel<__half, true><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    if (stem) csnet::il_stream_kernel<__half, false, true><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    else if (dbg) csnet::il_stream_kernel<__half, true><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     else csnet::il_stream_kernel<__half, false><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
-    if (dbg) {        // debugging aid: mean cycles per phase over the CTAs (synchronises)
+    if (dbg && !stem) {        // debugging aid: mean cycles per phase over the CTAs (synchronises)
       std::vector<unsigned long long> h((size_t)grid * 8);
       cudaStreamSynchronize(stream);
       cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
