@@ -16,6 +16,7 @@
 #include "generic_ops.cuh"
 #include "il_block.cuh"
 #include "il_stream.cuh"
+#include "mix_stream.cuh"
 #include "mix_tc.cuh"
 #include "dw_fast.cuh"
 
@@ -154,6 +155,8 @@ struct csnet_plan {
   std::vector<TcChoice> op_tc;
   std::vector<std::vector<uint16_t*>> op_w16;     // per tensor-core MIX op, per path: packed 16-bit weights (device)
   std::vector<float> h_blob;                      // host copy of the blob (epilogue tables of the streaming ILBlock kernel)
+  std::vector<char> op_ms;                        // per op: the streaming 1x1 MIX kernel (mix_stream.cuh) can run it
+  bool ms_enabled = true;                         // CSNET_MS=0 at plan creation: mix_tc / generic kernels only
   std::vector<char> op_ils;                       // per op: the streaming ILBlock kernel (il_stream.cuh) can run it
   int num_sms = 148;
   int ils_force_ns = 0;                           // CSNET_ILS_NS=k: force k column strips (0: automatic)
@@ -529,6 +532,78 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   return true;
 }
 
+// Kernel arguments of the streaming 1x1 MIX kernel for an op; false if the op does not qualify.
+bool make_ms(const csnet_plan& P, const csnet_op_desc& op, int N, const void* const* ext, csnet::MsArgs* out, CUtensorMap* maps) {
+  if (!P.ms_enabled || (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_MIXPROJ) || encode_tiled_fn() == nullptr) return false;
+  if (op.kind == CSNET_OP_MIX && op.ext_off[23] == 1) return false;      // the compiler's veto of 16-bit weights
+  const csnet_tensor_desc& D = P.tensors[op.dst];
+  csnet::MsArgs A{};
+  A.C = mix_channels(P, op);
+  A.has_proj = op.kind == CSNET_OP_MIXPROJ;
+  if (A.C > csnet::kMsMaxC || D.W % 8 || D.H % csnet::kMsRows) return false;
+  if (A.has_proj ? D.dtype != CSNET_F32 : D.dtype == CSNET_BF16) return false;
+  A.dst_f32 = D.dtype == CSNET_F32;
+  A.H = D.H; A.W = D.W; A.N = N; A.G = D.W / 8; A.NN = round_up(A.C, 16);
+  int off = 0;
+  auto r128 = [](int v) { return (v + 127) / 128 * 128; };
+  for (int p = 0; p < op.n_paths; ++p) {
+    const csnet_path_desc& q = op.paths[p];
+    const csnet_tensor_desc& S = P.tensors[q.src];
+    if (q.ksize == 0) {
+      if (A.n_rs >= csnet::kMsMaxRs || q.up < 2 || q.pool != 1 || q.pre_avg || S.H * q.up != D.H || S.W * q.up != D.W || S.dtype != CSNET_F32 || q.cout0 != 0) return false;
+      const int j = A.n_rs++;
+      A.rsrc[j] = ext || S.external < 0 ? P.tensor_ptr(q.src, N, ext) : nullptr;
+      A.r_dtype[j] = S.dtype; A.r_up[j] = q.up; A.r_H[j] = S.H; A.r_W[j] = S.W; A.r_C[j] = S.C; A.r_c0[j] = q.c0; A.r_cout0[j] = q.cout0; A.r_n[j] = q.cout;
+      continue;
+    }
+    if (A.n_in >= csnet::kMsMaxIn || q.ksize != 1 || q.stride != 1 || q.pad != 0 || q.up != 1 || q.pool != 1 || q.pre_avg || S.dtype != CSNET_F16 ||
+        S.H != D.H || S.W != D.W || q.cin > 64)
+      return false;
+    const int i = A.n_in++;
+    A.w[i] = P.blob + q.w_off;
+    A.cin[i] = q.cin; A.cout0[i] = q.cout0; A.cout[i] = q.cout;
+    A.K16[i] = round_up(q.cin, 16); A.S[i] = A.K16[i] + 1;
+    A.in_off[i] = off;
+    off += r128(csnet::kMsRows * A.G * A.S[i] * 16);
+    if (maps && !encode_group_map(&maps[i], P.tensor_ptr(q.src, N, ext), N, S.C, S.H, S.W, A.S[i], A.G, csnet::kMsRows)) return false;
+    if (q.c0 != 0) return false;                                            // (a channel-sliced source would need a c0 coordinate)
+  }
+  if (A.n_in == 0) return false;
+  A.stage_bytes = off;
+  A.tx_bytes = 0;
+  for (int i = 0; i < A.n_in; ++i) A.tx_bytes += csnet::kMsRows * A.G * A.S[i] * 16;
+  A.nb = (csnet::kMsRows * A.G + 15) / 16;
+  A.n_acc = 512 / (A.nb * A.NN);
+  A.n_acc = A.n_acc > 8 ? 8 : A.n_acc;
+  if (A.n_acc < 2) return false;
+  A.cpi = D.H / csnet::kMsRows;
+  A.total_chunks = N * A.cpi;
+  int wb = 0;
+  for (int i = 0; i < A.n_in; ++i) wb += r128(A.NN * A.K16[i] * 2);
+  const int fixed = wb + 512 + 1280 + 16 * 65 * 16 + 128;                  // weights, barriers, tables, tail slack, alignment
+  A.n_stages = (227 * 1024 - fixed) / A.stage_bytes;
+  A.n_stages = A.n_stages > 6 ? 6 : A.n_stages;
+  if (A.n_stages < 2) return false;
+  A.off_stage = 0;
+  int o = A.n_stages * A.stage_bytes + 16 * 65 * 16;
+  for (int i = 0; i < A.n_in; ++i) { A.off_wb[i] = o; o += r128(A.NN * A.K16[i] * 2); }
+  A.off_bar = o; o += 512;
+  A.off_tab = o; o += 1280;
+  A.smem_bytes = o + 128;
+  A.has_slope = op.slope_off >= 0;
+  if ((int64_t)P.h_blob.size() == P.blob_floats) {
+    for (int c = 0; c < A.C; ++c) {
+      A.bias[c] = op.bias_off >= 0 ? P.h_blob[op.bias_off + c] : 0.f;
+      A.sm1[c] = op.slope_off >= 0 ? P.h_blob[op.slope_off + c] - 1.f : 0.f;
+      A.proj[c] = A.has_proj ? P.h_blob[op.ext_off[0] + c] : 0.f;
+    }
+    A.proj_b = A.has_proj && op.ext_off[1] >= 0 ? P.h_blob[op.ext_off[1]] : 0.f;
+  }
+  A.dst = ext || D.external < 0 ? P.tensor_ptr(op.dst, N, ext) : nullptr;
+  *out = A;
+  return true;
+}
+
 template <typename T>
 void launch_il_t(const csnet::IlArgs& A, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& h, const CUtensorMap& l) {
   if (A.TH == 32) csnet::il_block_kernel<T, 32, 32><<<grid, csnet::kIlThreads, smem, st>>>(A, h, l);
@@ -715,6 +790,17 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) P->num_sms = prop.multiProcessorCount;
   }
+  if (const char* e4 = getenv("CSNET_MS")) P->ms_enabled = e4[0] != '0';
+  P->op_ms.assign(P->ops.size(), 0);
+  bool any_ms = false;
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    csnet::MsArgs M;
+    if (make_ms(*P, P->ops[i], 1, nullptr, &M, nullptr)) { P->op_ms[i] = 1; any_ms = true; }
+  }
+  if (any_ms) {
+    e = cudaFuncSetAttribute(csnet::mix_stream_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaFuncSetAttribute(mix_stream): ") + cudaGetErrorString(e));
+  }
   P->op_ils.assign(P->ops.size(), 0);
   P->ils_min_chunks = 4 * P->num_sms;
   if (const char* e1 = getenv("CSNET_ILS")) P->ils_enabled = e1[0] != '0';
@@ -794,7 +880,17 @@ static int check_run_args(csnet_plan* P, int32_t N, const void* const* ext_ptrs,
 static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_ptrs, cudaStream_t stream) {
   const csnet_op_desc& op = P->ops[i];
   const csnet_tensor_desc& D = P->tensors[op.dst];
-  if ((op.kind == CSNET_OP_MIX || op.kind == CSNET_OP_MIXPROJ) && P->op_tc[i].mt > 0) {
+  if (P->op_ms[i] && (int64_t)P->max_batch * (D.H / csnet::kMsRows) >= (int64_t)2 * P->num_sms) {
+    // streaming 1x1 MIX kernel (mix_stream.cuh): TMA operand tiles -> tcgen05 -> epilogue (resample-adds, PReLU, projection)
+    csnet::MsArgs A;
+    CUtensorMap maps[csnet::kMsMaxIn];
+    memset(maps, 0, sizeof maps);
+    if (!make_ms(*P, op, N, ext_ptrs, &A, maps)) return fail(CSNET_E_UNSUPPORTED, "MIX op no longer qualifies for the streaming kernel");
+    for (int k = A.n_in; k < csnet::kMsMaxIn; ++k) maps[k] = maps[0];
+    int grid = A.total_chunks / 2;
+    grid = grid < 1 ? 1 : (grid > P->num_sms ? P->num_sms : grid);
+    csnet::mix_stream_kernel<__half><<<grid, csnet::kMsThreads, A.smem_bytes, stream>>>(A, maps[0], maps[1], maps[2]);
+  } else if ((op.kind == CSNET_OP_MIX || op.kind == CSNET_OP_MIXPROJ) && P->op_tc[i].mt > 0) {
     csnet::MixArgs A = make_mix(*P, op, N, ext_ptrs);
     const TcChoice& tc = P->op_tc[i];
     const int Cm = A.C;
