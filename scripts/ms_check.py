@@ -24,3 +24,19 @@ for tag, h, w, nb in (("csnet-L-x2", 224, 224, 24), ("csnet-L-x1", 224, 224, 24)
         a, b = p1.read_tensor(tid, nb), p0.read_tensor(tid, nb)
         print(f"   {name:22s} rel diff {(a - b).abs().max().item() / max(1.0, b.abs().max().item()):.2e}", flush=True)
     p1.close(); p0.close()
+
+# MSBlock direct kernel (csrc/ms_direct.cuh): CSNET_MSD is read once per process -> compare against the tap values of the
+# generic program instead
+print("MSBlock taps vs the all-generic program:")
+for tag, h, w, nb in (("csnet-L-x2", 224, 224, 4), ("csnet-L-x1", 224, 224, 3), ("csnet-L-x2", 96, 160, 2)):
+    cfg, sd = checkpoints.load_npz(tag)
+    sd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    x = torch.from_numpy(synth.randn_images(nb, h, w, 5)).cuda()
+    base = compiler.compile_csnet(cfg, sd, h, w, "fp16", reuse_arena=False, fuse=False, tensor_core=False)
+    prog = compiler.compile_csnet(cfg, sd, h, w, "fp16", reuse_arena=False, fuse=False, tensor_core={"oct_fuse.ms"})
+    p0, p1 = runtime.Plan(base, max_batch=nb), runtime.Plan(prog, max_batch=nb)
+    p0.forward(x); p1.forward(x)
+    for name in ("oct_fuse.ms/0", "oct_fuse.ms/1", "oct_fuse.ms/2"):
+        if name in prog.taps:
+            a, b = p1.read_tensor(prog.taps[name], nb), p0.read_tensor(base.taps[name], nb)
+            print(f"   {tag} {h}x{w} {name}: rel diff {(a - b).abs().max().item() / max(1.0, b.abs().max().item()):.2e} finite {bool(torch.isfinite(a).all())}", flush=True)

@@ -17,6 +17,7 @@
 #include "il_block.cuh"
 #include "il_stream.cuh"
 #include "mix_stream.cuh"
+#include "ms_direct.cuh"
 #include "mix_tc.cuh"
 #include "dw_fast.cuh"
 
@@ -155,6 +156,7 @@ struct csnet_plan {
   std::vector<TcChoice> op_tc;
   std::vector<std::vector<uint16_t*>> op_w16;     // per tensor-core MIX op, per path: packed 16-bit weights (device)
   std::vector<float> h_blob;                      // host copy of the blob (epilogue tables of the streaming ILBlock kernel)
+  std::vector<char> op_msd;                       // per op: an MSBlock whose dilated paths run on ms_direct.cuh
   std::vector<char> op_ms;                        // per op: the streaming 1x1 MIX kernel (mix_stream.cuh) can run it
   bool ms_enabled = true;                         // CSNET_MS=0 at plan creation: mix_tc / generic kernels only
   std::vector<char> op_ils;                       // per op: the streaming ILBlock kernel (il_stream.cuh) can run it
@@ -532,6 +534,24 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   return true;
 }
 
+// MSBlock form of a MIX op: every path a dilated 3x3 (pad == dil in {1, 2, 4, 8, 16}, stride 1) of the SAME whole fp16 tensor,
+// at most 8 output channels per path (the concat = disjoint cout slices), fp16 destination of the same size.
+bool is_msd(const csnet_plan& P, const csnet_op_desc& op) {
+  static const bool enabled = [] { const char* e = getenv("CSNET_MSD"); return !(e && e[0] == '0'); }();
+  if (!enabled || op.kind != CSNET_OP_MIX || op.ext_off[23] == 1 || op.n_paths < 1) return false;
+  const csnet_tensor_desc& D = P.tensors[op.dst];
+  if (D.dtype != CSNET_F16 || D.W % 8) return false;
+  for (int p = 0; p < op.n_paths; ++p) {
+    const csnet_path_desc& q = op.paths[p];
+    const csnet_tensor_desc& S = P.tensors[q.src];
+    if (q.ksize != 3 || q.src != op.paths[0].src || q.c0 != 0 || q.cin != S.C || q.stride != 1 || q.pad != q.dil || q.pool != 1 || q.pre_avg ||
+        q.up != 1 || S.dtype != CSNET_F16 || S.H != D.H || S.W != D.W || q.cout > 8 || q.cin > 128)
+      return false;
+    if (q.dil != 1 && q.dil != 2 && q.dil != 4 && q.dil != 8 && q.dil != 16) return false;
+  }
+  return true;
+}
+
 // Kernel arguments of the streaming 1x1 MIX kernel for an op; false if the op does not qualify.
 bool make_ms(const csnet_plan& P, const csnet_op_desc& op, int N, const void* const* ext, csnet::MsArgs* out, CUtensorMap* maps) {
   if (!P.ms_enabled || (op.kind != CSNET_OP_MIX && op.kind != CSNET_OP_MIXPROJ) || encode_tiled_fn() == nullptr) return false;
@@ -790,6 +810,8 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) P->num_sms = prop.multiProcessorCount;
   }
+  P->op_msd.assign(P->ops.size(), 0);
+  for (size_t i = 0; i < P->ops.size(); ++i) P->op_msd[i] = is_msd(*P, P->ops[i]) ? 1 : 0;
   if (const char* e4 = getenv("CSNET_MS")) P->ms_enabled = e4[0] != '0';
   P->op_ms.assign(P->ops.size(), 0);
   bool any_ms = false;
@@ -880,7 +902,20 @@ static int check_run_args(csnet_plan* P, int32_t N, const void* const* ext_ptrs,
 static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_ptrs, cudaStream_t stream) {
   const csnet_op_desc& op = P->ops[i];
   const csnet_tensor_desc& D = P->tensors[op.dst];
-  if (P->op_ms[i] && (int64_t)P->max_batch * (D.H / csnet::kMsRows) >= (int64_t)2 * P->num_sms) {
+  if (P->op_msd[i]) {
+    // MSBlock: one launch per dilated path on the FP32 pipe (ms_direct.cuh)
+    for (int p = 0; p < op.n_paths; ++p) {
+      const csnet_path_desc& q = op.paths[p];
+      csnet::MsdArgs A{};
+      A.src = reinterpret_cast<const uint16_t*>(P->tensor_ptr(q.src, N, ext_ptrs));
+      A.dst = reinterpret_cast<uint16_t*>(P->tensor_ptr(op.dst, N, ext_ptrs));
+      A.w = P->blob + q.w_off;
+      A.bias = op.bias_off >= 0 ? P->blob + op.bias_off : nullptr;
+      A.slope = op.slope_off >= 0 ? P->blob + op.slope_off : nullptr;
+      A.N = N; A.Cin = q.cin; A.H = D.H; A.W = D.W; A.Ctot = D.C; A.cout0 = q.cout0; A.cout = q.cout;
+      csnet::msd_launch<__half>(q.dil, A, stream);
+    }
+  } else if (P->op_ms[i] && (int64_t)P->max_batch * (D.H / csnet::kMsRows) >= (int64_t)2 * P->num_sms) {
     // streaming 1x1 MIX kernel (mix_stream.cuh): TMA operand tiles -> tcgen05 -> epilogue (resample-adds, PReLU, projection)
     csnet::MsArgs A;
     CUtensorMap maps[csnet::kMsMaxIn];
@@ -1073,7 +1108,10 @@ int csnet_plan_read_tensor(csnet_plan* P, int32_t tensor, int32_t N, void* dst, 
 int32_t csnet_plan_launches(const csnet_plan* P) {
   if (!P) return 0;
   int32_t n = 0;
-  for (const auto& op : P->ops) n += op.kind == CSNET_OP_GN ? 2 : 1;
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    const auto& op = P->ops[i];
+    n += op.kind == CSNET_OP_GN ? 2 : (i < P->op_msd.size() && P->op_msd[i] ? op.n_paths : 1);
+  }
   return n;
 }
 
