@@ -39,6 +39,18 @@ int fail(int code, const std::string& msg) {
 
 size_t dtype_size(int dt) { return dt == CSNET_F32 ? 4 : 2; }
 
+// The entry points select the plan's device for their CUDA calls and put the caller's current device back on return:
+// torch (the host side's plumbing) keeps its own notion of the current device.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
@@ -749,8 +761,12 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   }
   P->arena_per_image = (P->arena_per_image + 255) / 256 * 256;
   auto cleanup = [&](int code, const std::string& m) { csnet_plan_destroy(P); return fail(code, m); };
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return cleanup(CSNET_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  DeviceGuard guard_(device);
+  cudaError_t e = cudaSuccess;
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return cleanup(CSNET_E_CUDA, "cudaSetDevice failed");
+  }
   e = cudaMalloc(&P->blob, (size_t)blob_floats * sizeof(float));
   if (e != cudaSuccess) return cleanup(CSNET_E_NOMEM, std::string("cudaMalloc(blob): ") + cudaGetErrorString(e));
   const size_t arena_bytes = (size_t)P->arena_per_image * (size_t)max_batch + 256;
@@ -856,7 +872,7 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
 
 int csnet_plan_set_blob(csnet_plan* P, const float* host_blob, int64_t n, void* stream) {
   if (!P || !host_blob || n != P->blob_floats) return fail(CSNET_E_INVALID, "csnet_plan_set_blob: size mismatch");
-  CU_CHECK(cudaSetDevice(P->device));
+  DeviceGuard guard_(P->device);
   CU_CHECK(cudaMemcpyAsync(P->blob, host_blob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   P->h_blob.assign(host_blob, host_blob + n);
   // tensor-core MIX ops read their weights as 16-bit [chunk][tap][m16_total][kc + 8] blocks: pack them here, once per
@@ -1059,7 +1075,7 @@ int csnet_plan_run(csnet_plan* P, int32_t N, const void* const* ext_ptrs, int32_
   int rc = check_run_args(P, N, ext_ptrs, n_ext);
   if (rc != CSNET_OK) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
-  CU_CHECK(cudaSetDevice(P->device));
+  DeviceGuard guard_(P->device);
   for (size_t i = 0; i < P->ops.size(); ++i) {
     rc = launch_op(P, i, N, ext_ptrs, stream);
     if (rc != CSNET_OK) return rc;
@@ -1073,7 +1089,7 @@ int csnet_plan_profile(csnet_plan* P, int32_t N, const void* const* ext_ptrs, in
   if (rc != CSNET_OK) return rc;
   if (!ms_per_op || n_ops != (int32_t)P->ops.size()) return fail(CSNET_E_INVALID, "csnet_plan_profile: n_ops mismatch");
   cudaStream_t stream = (cudaStream_t)stream_;
-  CU_CHECK(cudaSetDevice(P->device));
+  DeviceGuard guard_(P->device);
   std::vector<cudaEvent_t> ev(P->ops.size() + 1);
   for (auto& e : ev) CU_CHECK(cudaEventCreate(&e));
   CU_CHECK(cudaEventRecord(ev[0], stream));
@@ -1099,7 +1115,7 @@ int csnet_plan_read_tensor(csnet_plan* P, int32_t tensor, int32_t N, void* dst, 
   void* src = csnet_plan_tensor_ptr(P, tensor, N);
   if (!src || !dst) return fail(CSNET_E_INVALID, "csnet_plan_read_tensor: bad tensor / batch / destination");
   const csnet_tensor_desc& d = P->tensors[tensor];
-  CU_CHECK(cudaSetDevice(P->device));
+  DeviceGuard guard_(P->device);
   CU_CHECK(cudaMemcpyAsync(dst, src, (size_t)N * d.C * d.H * d.W * dtype_size(d.dtype), cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));
   return CSNET_OK;
@@ -1119,7 +1135,7 @@ int64_t csnet_plan_arena_bytes(const csnet_plan* P) { return P ? P->arena_per_im
 
 void csnet_plan_destroy(csnet_plan* P) {
   if (!P) return;
-  if (P->blob || P->arena) cudaSetDevice(P->device);
+  DeviceGuard guard_(P->device);
   if (P->blob) cudaFree(P->blob);
   if (P->arena) cudaFree(P->arena);
   if (P->gn_stats) cudaFree(P->gn_stats);
@@ -1150,7 +1166,7 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
   if (!in || !lo || in->dtype != CSNET_F32 || lo->dtype != CSNET_F32)
     return fail(CSNET_E_INVALID, "run_host: externals must be fp32");
   cudaStream_t stream = (cudaStream_t)stream_;
-  CU_CHECK(cudaSetDevice(P->device));
+  DeviceGuard guard_(P->device);
   // The batch is cut into chunks that flow through a three-stage pipeline: H2D copy (own stream) -> program
   // (caller's stream) -> D2H copy (own stream), with ping-pong device staging, so the PCIe copies of chunk i+1 / i-1
   // overlap the kernels of chunk i.  Pinned host memory is needed for the copies to be truly asynchronous.

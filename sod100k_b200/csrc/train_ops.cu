@@ -422,30 +422,39 @@ extern "C" {
 
 const char* csnet_train_last_error(void) { return t_err.c_str(); }
 
-// Workspace of the channel reductions: partials [C][parts][3] + one ticket counter per channel.  One per process, grown on
-// demand; the training entry points are meant to be issued on ONE stream (calls serialise there, so sharing is safe).
-static float* g_red_ws = nullptr;
-static unsigned* g_red_cnt = nullptr;
-static size_t g_red_ws_cap = 0, g_red_cnt_cap = 0;
+// Workspace of the channel reductions: partials [C][parts][3] + one ticket counter per channel.  One set PER DEVICE (indexed by
+// the current device, i.e. the device of the tensors the caller's torch stream belongs to), grown on demand; the training entry
+// points of one device are meant to be issued on ONE stream (calls serialise there, so sharing within a device is safe).
+constexpr int kMaxDevices = 16;
+struct RedWs { float* ws = nullptr; unsigned* cnt = nullptr; size_t ws_cap = 0, cnt_cap = 0; };
+static RedWs g_red[kMaxDevices];
+static thread_local float* g_red_ws = nullptr;          // the current call's workspace (set by reduce_workspace)
+static thread_local unsigned* g_red_cnt = nullptr;
 
 static int reduce_workspace(int C, int parts, cudaStream_t st) {
+  int dev = 0;
+  TR_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) { t_err = "device index out of range"; return CSNET_E_INVALID; }
+  RedWs& R = g_red[dev];
   const size_t need = (size_t)C * parts * 3;
-  if (need > g_red_ws_cap) {
+  if (need > R.ws_cap) {
     TR_CHECK(cudaStreamSynchronize(st));
-    if (g_red_ws) cudaFree(g_red_ws);
-    g_red_ws = nullptr; g_red_ws_cap = 0;
-    TR_CHECK(cudaMalloc(&g_red_ws, need * 2 * sizeof(float)));
-    g_red_ws_cap = need * 2;
+    if (R.ws) cudaFree(R.ws);
+    R.ws = nullptr; R.ws_cap = 0;
+    TR_CHECK(cudaMalloc(&R.ws, need * 2 * sizeof(float)));
+    R.ws_cap = need * 2;
   }
-  if ((size_t)C > g_red_cnt_cap) {
+  if ((size_t)C > R.cnt_cap) {
     TR_CHECK(cudaStreamSynchronize(st));
-    if (g_red_cnt) cudaFree(g_red_cnt);
-    g_red_cnt = nullptr; g_red_cnt_cap = 0;
+    if (R.cnt) cudaFree(R.cnt);
+    R.cnt = nullptr; R.cnt_cap = 0;
     const size_t cap = (size_t)C * 2 < 1024 ? 1024 : (size_t)C * 2;
-    TR_CHECK(cudaMalloc(&g_red_cnt, cap * sizeof(unsigned)));
-    TR_CHECK(cudaMemset(g_red_cnt, 0, cap * sizeof(unsigned)));
-    g_red_cnt_cap = cap;
+    TR_CHECK(cudaMalloc(&R.cnt, cap * sizeof(unsigned)));
+    TR_CHECK(cudaMemset(R.cnt, 0, cap * sizeof(unsigned)));
+    R.cnt_cap = cap;
   }
+  g_red_ws = R.ws;
+  g_red_cnt = R.cnt;
   return CSNET_OK;
 }
 

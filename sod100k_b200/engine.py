@@ -20,6 +20,33 @@ def _has_hooks(model) -> bool:
     return False
 
 
+_PROBES = {}
+
+
+def param_version(tensors, epoch: int = 0, owner=None) -> int:
+    """Version stamp of a parameter set: torch's in-place counters and storage addresses (cheap, catches optimizer steps,
+    load_state_dict, .to()) PLUS a value checksum computed on the device — writes through `.data` (`m.weight.data.normal_()`,
+    pruning masks `w.data.mul_(mask)`, manual BN-statistic edits) do not bump `_version`, and the reference's own callers
+    use them (weights_init, finetune).  The checksum is the dot product of all floating-point values with a fixed
+    pseudo-random probe vector: one concatenation + one dot + one scalar read per call; `freeze()` skips it."""
+    h = runtime.PARAM_EPOCH * 1000003 + epoch
+    fl = []
+    for t in tensors:
+        h = (h * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFF
+        if t.is_floating_point() and t.numel() > 0 and t.is_cuda:
+            fl.append(t.detach().reshape(-1).float())
+    if fl:
+        flat = torch.cat(fl)
+        key = (flat.numel(), flat.device)
+        probe = _PROBES.get(key)
+        if probe is None:
+            g = torch.Generator(device="cpu").manual_seed(0x5EED)
+            probe = _PROBES[key] = (torch.rand(flat.numel(), generator=g) + 0.5).to(flat.device)
+        c = torch.stack([torch.dot(flat, probe), flat.abs().sum()]).tolist()
+        h = (h * 1000003 + hash((c[0], c[1]))) & 0xFFFFFFFFFFFF
+    return h
+
+
 class ModelEngine:
     def __init__(self, model):
         self.model = model
@@ -27,6 +54,7 @@ class ModelEngine:
         self._plans: Dict[Tuple, runtime.Plan] = {}
         self._plan_version: Dict[Tuple, int] = {}
         self.frozen = False
+        self._epoch = 0
 
     def set_precision(self, dtype: str):
         if dtype not in ir.DTYPE_NAMES:
@@ -37,11 +65,12 @@ class ModelEngine:
         """Skip the per-call parameter-version scan (weights will not change; latency-critical serving)."""
         self.frozen = flag
 
+    def invalidate(self):
+        """Force the next forward to re-fold the parameters (after writes the automatic checks cannot see)."""
+        self._epoch += 1
+
     def _version(self) -> int:
-        h = runtime.PARAM_EPOCH
-        for t in list(self.model.parameters()) + list(self.model.buffers()):
-            h = (h * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFF
-        return h
+        return param_version(list(self.model.parameters()) + list(self.model.buffers()), self._epoch, self)
 
     def _state(self):
         return {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
@@ -60,7 +89,16 @@ class ModelEngine:
             self._plans[key] = plan
         elif self._plan_version.get(key) != ver:
             prog = compiler.compile_csnet(self.model.layer_config, self._state(), H, W, self.dtype)
-            plan.set_blob(prog.blob, torch.cuda.current_stream(device).cuda_stream)
+            if prog.signature() == plan.prog.signature():
+                plan.set_blob(prog.blob, torch.cuda.current_stream(device).cuda_stream)
+                plan.prog = prog
+            else:
+                # new weights changed the program itself (a 16-bit overflow veto, a fused block falling back, ...): the kernel
+                # choices frozen at plan creation no longer fit -> rebuild the plan
+                max_batch = plan.max_batch
+                plan.close()
+                plan = runtime.Plan(prog, max_batch=max_batch, device=key[3])
+                self._plans[key] = plan
         self._plan_version[key] = ver
         return plan
 

@@ -111,6 +111,17 @@ class Program:
             arr[i] = d
         return arr
 
+    def signature(self) -> bytes:
+        """Everything a plan freezes at creation: the tensor table, the op list (kinds, paths, parameter offsets, flags) and the
+        blob size.  Two programs with equal signatures differ only in parameter VALUES (csnet_plan_set_blob suffices)."""
+        import hashlib
+
+        h = hashlib.sha256()
+        h.update(bytes(self.tensor_array()))
+        h.update(bytes(self.op_array()))
+        h.update(str(0 if self.blob is None else int(self.blob.size)).encode())
+        return h.digest()
+
     @property
     def arena_bytes_per_image(self) -> int:
         return max([t.arena_offset + t.bytes_per_image for t in self.tensors if t.external < 0] + [0])

@@ -219,6 +219,28 @@ class CSNet(nn.Module):
             object.__setattr__(self, "_engine", ModelEngine(self))
         return self._engine
 
+    def invalidate(self):
+        """Tell the engine that parameters / buffers were modified in a way it cannot observe (it already notices in-place
+        torch ops, `.data` writes — by a device-side value checksum — and load_state_dict); needed only after `freeze()`."""
+        if self._engine is not None:
+            self._engine.invalidate()
+
+    # The engine holds ctypes handles (device plans): a copy / pickle of the module must not carry them.  The reference module
+    # supports copy.deepcopy (EMA / AveragedModel) and torch.save(model); so does this one — the copy builds its own plans.
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_engine"] = None
+        return d
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
+        return new
+
     def set_precision(self, dtype: str):
         """Activation storage type of the fused inference program: 'fp32' (default, 1e-3 parity gate),
         'fp16' or 'bf16' (fp32 accumulation)."""

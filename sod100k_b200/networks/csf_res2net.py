@@ -166,10 +166,25 @@ class CSFNet(nn.Module):
         self.cls_layer = nn.Conv2d(cout, num_classes, kernel_size=1)
         self.precision = "fp32"
         self._plans = {}
+        self._plan_version = {}
 
     def set_precision(self, dtype: str):
         self.precision = dtype
         return self
+
+    def __getstate__(self):                      # device plans (ctypes handles) never travel with a copy / pickle
+        d = dict(self.__dict__)
+        d["_plans"], d["_plan_version"] = {}, {}
+        return d
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k in ("_plans", "_plan_version") else copy.deepcopy(v, memo)
+        return new
 
     def head_state(self):
         return {k: v.detach().cpu() for k, v in self.state_dict().items() if not k.startswith("base.")}
@@ -190,11 +205,26 @@ class CSFNet(nn.Module):
         feats = self.backbone(x.float())
         key = (h, w, self.precision, x.device.index or 0)
         plan = self._plans.get(key)
+        # the head plan folds the head's parameters at creation: re-fold when they change (load_state_dict, weights_init,
+        # `.data` writes — same version stamp as the CSNet engine), so head and backbone never run on different weights
+        from ..engine import param_version
+
+        ver = param_version([t for k, t in list(self.named_parameters()) + list(self.named_buffers()) if not k.startswith("base.")])
         if plan is None or plan.max_batch < n:
             prog = compiler_r.compile_csf_head(self.head_state(), [tuple(f.shape[1:]) for f in feats], h, w, self.precision)
             if plan is not None:
                 plan.close()
             plan = self._plans[key] = runtime.Plan(prog, max_batch=n, device=key[3])
+        elif self._plan_version.get(key) != ver:
+            prog = compiler_r.compile_csf_head(self.head_state(), [tuple(f.shape[1:]) for f in feats], h, w, self.precision)
+            if prog.signature() == plan.prog.signature():
+                plan.set_blob(prog.blob, torch.cuda.current_stream(x.device).cuda_stream)
+                plan.prog = prog
+            else:
+                mb = plan.max_batch
+                plan.close()
+                plan = self._plans[key] = runtime.Plan(prog, max_batch=mb, device=key[3])
+        self._plan_version[key] = ver
         y = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
         plan.run(n, [f.data_ptr() for f in feats] + [y.data_ptr()], torch.cuda.current_stream(x.device).cuda_stream)
         return y

@@ -20,6 +20,8 @@ def reference_param_groups(model) -> Tuple[List[torch.nn.Parameter], List[torch.
     'conv3x3_1.bns' test (conv3x3_2's BN gammas stay in the decayed group)."""
     normal, picked = [], []
     for name, p in model.named_parameters():
+        if not p.requires_grad:                  # frozen parameters take no optimizer step (no zero grads, no weight decay)
+            continue
         if "stage" in name and ("conv1x1.bns" in name or "conv3x3_1.bns" in name or "conv3x3_1.bns" in name) and "weight" in name:
             picked.append(p)
         else:

@@ -282,3 +282,22 @@ def test_materialised_avgpool_of_stride2_entry_blocks(tag, hw, dtype):
             err = (got - ref).abs().max().item()
             assert err <= rel * max(1.0, ref.abs().max().item()), (key, err, ref.abs().max().item())
         p1.close()
+
+
+def test_data_writes_are_noticed_without_version_bumps():
+    """`p.data.op_()` does not bump torch's version counter (weights_init, pruning masks, manual BN edits use it): the engine's
+    device-side value checksum must still see the change; after freeze() an explicit invalidate() is the documented way."""
+    m, cfg, sd = _model("csnet-L-x1")
+    x = torch.from_numpy(synth.randn_images(2, 64, 64, 3)).cuda()
+    with torch.no_grad():
+        y = m(x).clone()
+        v0 = m.cls_layer.bias._version
+        m.cls_layer.bias.data.add_(1.0)
+        assert m.cls_layer.bias._version == v0
+        assert torch.allclose(m(x), y + 1.0, atol=1e-5)
+        m.engine().freeze(True)
+        m.cls_layer.bias.data.add_(1.0)
+        assert torch.allclose(m(x), y + 1.0, atol=1e-5)          # frozen: stale by contract ...
+        m.invalidate()
+        m.engine().freeze(False)
+        assert torch.allclose(m(x), y + 2.0, atol=1e-5)          # ... until invalidated

@@ -85,3 +85,50 @@ def test_streaming_kernel_is_deterministic_and_batch_independent():
     assert torch.equal(y, y2)
     assert torch.equal(y[:4], y[20:24])            # the same images at other batch positions (other CTAs, other chunk ranges)
     assert torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("tag,hw,nb", [("csnet-L-x2", (224, 224), 24), ("csnet-L-x1", (224, 224), 24), ("csnet-L-x2", (96, 160), 40)])
+def test_streaming_mix_kernel_matches_the_tensor_core_mix_kernel(tag, hw, nb):
+    """csrc/mix_stream.cuh (TMA -> tcgen05 -> epilogue with resample-adds / the cls_layer projection) on and off for the same
+    fp16 program: taps of the CSF head and the logits.  Both sides run fp16 operands with fp32 accumulation; the differences are
+    accumulation order and the 16-bit rounding of the stored taps."""
+    cfg, sd = fixtures.checkpoint(tag)
+    h, w = hw
+    x = torch.from_numpy(synth.randn_images(nb, h, w, 3)).cuda()
+    prog = compiler.compile_csnet(cfg, sd, h, w, "fp16", reuse_arena=False)
+    os.environ["CSNET_MS"] = "1"
+    p1 = runtime.Plan(prog, max_batch=nb)
+    os.environ["CSNET_MS"] = "0"
+    p0 = runtime.Plan(prog, max_batch=nb)
+    os.environ.pop("CSNET_MS")
+    y1, y0 = p1.forward(x), p0.forward(x)
+    assert torch.isfinite(y1).all()
+    assert (y1 - y0).abs().max().item() <= 2e-3 * max(1.0, y0.abs().max().item())
+    n = 0
+    for name, tid in prog.taps.items():
+        if name.startswith("oct_fuse.fuse"):
+            a, b = p1.read_tensor(tid, nb), p0.read_tensor(tid, nb)
+            assert (a - b).abs().max().item() <= 2e-3 * max(1.0, b.abs().max().item()), name
+            n += 1
+    assert n >= 2
+
+
+@pytest.mark.parametrize("tag,hw", [("csnet-L-x2", (224, 224)), ("csnet-L-x1", (224, 224)), ("csnet-L-x2", (96, 160))])
+def test_msblock_direct_kernel_matches_generic_ops(tag, hw):
+    """csrc/ms_direct.cuh: only the MSBlock ops leave the generic kernels (inputs bit-identical), taps of the three MS branches."""
+    cfg, sd = fixtures.checkpoint(tag)
+    h, w = hw
+    x = torch.from_numpy(synth.randn_images(3, h, w, 5)).cuda()
+    base = compiler.compile_csnet(cfg, sd, h, w, "fp16", reuse_arena=False, fuse=False, tensor_core=False)
+    prog = compiler.compile_csnet(cfg, sd, h, w, "fp16", reuse_arena=False, fuse=False, tensor_core={"oct_fuse.ms"})
+    p0, p1 = runtime.Plan(base, max_batch=3), runtime.Plan(prog, max_batch=3)
+    p0.forward(x)
+    p1.forward(x)
+    n = 0
+    for name in ("oct_fuse.ms/0", "oct_fuse.ms/1", "oct_fuse.ms/2"):
+        if name in prog.taps:
+            a, b = p1.read_tensor(prog.taps[name], 3), p0.read_tensor(base.taps[name], 3)
+            assert torch.isfinite(a).all()
+            assert (a - b).abs().max().item() <= 4e-3 * max(1.0, b.abs().max().item()), name
+            n += 1
+    assert n >= 2

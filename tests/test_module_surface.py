@@ -153,3 +153,57 @@ def test_lowering_choices_by_dtype():
     p = compiler.compile_csnet(cfg, sd, 224, 224, "fp16", fuse={"stage2.0.conv1x1"}, tensor_core=False)
     pooled = [o.name for o in p.ops if "pool" in o.name]
     assert len(pooled) == 3 and all(n.startswith("stage2.0.conv1x1.") for n in pooled)
+
+
+def test_module_copies_and_pickles_without_its_engine():
+    """The reference module supports copy.deepcopy (EMA) and torch.save(model); the engine's ctypes handles must not travel."""
+    import copy
+    import ctypes
+    import io
+    import pickle
+
+    cfg, sd = fixtures.checkpoint("csnet-L-x1")
+    m = csnet.CSNet(cfg)
+    m.load_state_dict(sd)
+
+    class _FakeEngine:                                   # what a used engine looks like to pickle: a raw pointer inside
+        def __init__(self):
+            self.h = ctypes.c_void_p(1234)
+
+        def invalidate(self):
+            pass
+
+    object.__setattr__(m, "_engine", _FakeEngine())
+    m2 = copy.deepcopy(m)
+    assert m2._engine is None and m._engine is not None
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    assert m3._engine is None and list(m3.state_dict().keys()) == list(m.state_dict().keys())
+    pickle.dumps(m)
+
+
+def test_frozen_parameters_take_no_optimizer_step():
+    from sod100k_b200 import trainer
+
+    cfg, sd = fixtures.checkpoint("csnet-L-x1")
+    m = csnet.CSNet(cfg)
+    n_all = sum(1 for _ in m.parameters())
+    m.cls_layer.weight.requires_grad_(False)
+    normal, picked = trainer.reference_param_groups(m)
+    assert len(normal) + len(picked) == n_all - 1
+    assert all(p.requires_grad for p in normal + picked)
+
+
+def test_program_signature_tracks_structure_not_values():
+    from sod100k_b200 import compiler
+
+    cfg, sd = fixtures.checkpoint("csnet-L-x1")
+    a = compiler.compile_csnet(cfg, sd, 64, 64, "fp16")
+    sd2 = {k: (v * 1.5 if k.endswith("prelus.0.weight") else v) for k, v in sd.items()}
+    b = compiler.compile_csnet(cfg, sd2, 64, 64, "fp16")
+    assert a.signature() == b.signature() and not np.array_equal(a.blob, b.blob)
+    c = compiler.compile_csnet(cfg, sd, 64, 64, "fp16", tensor_core=False)       # the kernel veto flags differ
+    assert c.signature() != a.signature()
