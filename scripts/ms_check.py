@@ -19,7 +19,7 @@ for tag, h, w, nb in (("csnet-L-x2", 224, 224, 24), ("csnet-L-x1", 224, 224, 24)
     torch.cuda.synchronize()
     print(f"{tag} {h}x{w} bs{nb}: logits max diff {(y1 - y0).abs().max().item():.3e} (|y| max {y0.abs().max().item():.2f}) finite {bool(torch.isfinite(y1).all())}", flush=True)
     for name, tid in prog.taps.items():
-        if not name.startswith("oct_fuse"):
+        if not (name.startswith("oct_fuse") or name.startswith("stage2.0") or name.startswith("stage3.0") or name.startswith("stage2.1")):
             continue
         a, b = p1.read_tensor(tid, nb), p0.read_tensor(tid, nb)
         print(f"   {name:22s} rel diff {(a - b).abs().max().item() / max(1.0, b.abs().max().item()):.2e}", flush=True)

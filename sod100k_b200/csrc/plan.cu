@@ -588,22 +588,26 @@ bool make_ms(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
       A.r_dtype[j] = S.dtype; A.r_up[j] = q.up; A.r_H[j] = S.H; A.r_W[j] = S.W; A.r_C[j] = S.C; A.r_c0[j] = q.c0; A.r_cout0[j] = q.cout0; A.r_n[j] = q.cout;
       continue;
     }
-    if (A.n_in >= csnet::kMsMaxIn || q.ksize != 1 || q.stride != 1 || q.pad != 0 || q.up != 1 || q.pool != 1 || q.pre_avg || S.dtype != CSNET_F16 ||
-        S.H != D.H || S.W != D.W || q.cin > 64)
+    const bool k3 = q.ksize == 3 && q.pad == 1 && q.dil == 1, k1 = q.ksize == 1 && q.pad == 0;
+    if (A.n_in >= csnet::kMsMaxIn || !(k1 || k3) || (A.n_in > 0 && (int)k3 != A.k3) || q.stride != 1 || q.up != 1 || q.pool != 1 || q.pre_avg ||
+        S.dtype != CSNET_F16 || S.H != D.H || S.W != D.W || q.cin > 64)
       return false;
+    A.k3 = k3;
+    const int trows = csnet::kMsRows + (k3 ? 2 : 0);
     const int i = A.n_in++;
     A.w[i] = P.blob + q.w_off;
     A.cin[i] = q.cin; A.cout0[i] = q.cout0; A.cout[i] = q.cout;
     A.K16[i] = round_up(q.cin, 16); A.S[i] = A.K16[i] + 1;
     A.in_off[i] = off;
-    off += r128(csnet::kMsRows * A.G * A.S[i] * 16);
-    if (maps && !encode_group_map(&maps[i], P.tensor_ptr(q.src, N, ext), N, S.C, S.H, S.W, A.S[i], A.G, csnet::kMsRows)) return false;
+    A.copy_bytes[i] = r128(trows * A.G * A.S[i] * 16);
+    off += (k3 ? 3 : 1) * A.copy_bytes[i];
+    if (maps && !encode_group_map(&maps[i], P.tensor_ptr(q.src, N, ext), N, S.C, S.H, S.W, A.S[i], A.G, trows)) return false;
     if (q.c0 != 0) return false;                                            // (a channel-sliced source would need a c0 coordinate)
   }
   if (A.n_in == 0) return false;
   A.stage_bytes = off;
   A.tx_bytes = 0;
-  for (int i = 0; i < A.n_in; ++i) A.tx_bytes += csnet::kMsRows * A.G * A.S[i] * 16;
+  for (int i = 0; i < A.n_in; ++i) A.tx_bytes += (csnet::kMsRows + (A.k3 ? 2 : 0)) * A.G * A.S[i] * 16;
   A.nb = (csnet::kMsRows * A.G + 15) / 16;
   A.n_acc = 512 / (A.nb * A.NN);
   A.n_acc = A.n_acc > 8 ? 8 : A.n_acc;
@@ -611,14 +615,15 @@ bool make_ms(const csnet_plan& P, const csnet_op_desc& op, int N, const void* co
   A.cpi = D.H / csnet::kMsRows;
   A.total_chunks = N * A.cpi;
   int wb = 0;
-  for (int i = 0; i < A.n_in; ++i) wb += r128(A.NN * A.K16[i] * 2);
+  const int taps = A.k3 ? 9 : 1;
+  for (int i = 0; i < A.n_in; ++i) wb += r128(taps * A.NN * A.K16[i] * 2);
   const int fixed = wb + 512 + 1280 + 16 * 65 * 16 + 128;                  // weights, barriers, tables, tail slack, alignment
   A.n_stages = (227 * 1024 - fixed) / A.stage_bytes;
   A.n_stages = A.n_stages > 6 ? 6 : A.n_stages;
   if (A.n_stages < 2) return false;
   A.off_stage = 0;
   int o = A.n_stages * A.stage_bytes + 16 * 65 * 16;
-  for (int i = 0; i < A.n_in; ++i) { A.off_wb[i] = o; o += r128(A.NN * A.K16[i] * 2); }
+  for (int i = 0; i < A.n_in; ++i) { A.off_wb[i] = o; o += r128(taps * A.NN * A.K16[i] * 2); }
   A.off_bar = o; o += 512;
   A.off_tab = o; o += 1280;
   A.smem_bytes = o + 128;
