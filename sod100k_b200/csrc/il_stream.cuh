@@ -56,7 +56,7 @@ struct IlsArgs {
   int32_t Ci, BW;                     // stem form: image channels; width in floats of an image block in shared memory (8 GR + 8)
   int32_t off_xlo;                    // stem form: the lo chunk's GEMM operand buffer
   int32_t cpi, total_chunks;          // chunks per image strip (H/4), N * ns * cpi
-  int32_t hi_warps, lo_warps;         // warps of the depthwise tail
+  int32_t dw_warps;                   // warps of the CTA = warps of the depthwise tail (tasks packed: hi columns, then lo)
   int32_t hi_stage_bytes, lo_stage_bytes;
   unsigned long long* dbg;             // optional: per-CTA phase cycle counters [grid][8] (CSNET_ILS_DBG=1)
   int32_t off_xl, off_xh, off_t1l, off_wbh, off_wbl, off_bar, off_zero, off_epi, smem_bytes;
@@ -287,8 +287,10 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
   const uint32_t tmem = *tmem_slot;
 
   // depthwise-tail role of this thread (fixed for the whole kernel): a channel and an 8-pixel column
-  const bool dw_hi = warp < A.hi_warps;
-  const int dwt = dw_hi ? tid : tid - A.hi_warps * 32;
+  // tail tasks are packed: threads [0, Cho * gsn) own a hi (channel, column), the next Clo * gsn / 2 a lo one
+  const int n_hi_tasks = Cho * gsn;
+  const bool dw_hi = tid < n_hi_tasks;
+  const int dwt = dw_hi ? tid : tid - n_hi_tasks;
   const int Gd = dw_hi ? gsn : gsn >> 1, Cd = dw_hi ? Cho : Clo, Sd = dw_hi ? SH : ST;   // Gd: this role's groups per strip row
   const bool dw_live = dwt < Cd * Gd;
   const int dc = dw_live ? dwt / Gd : 0, dg = dw_live ? dwt - dc * Gd : 0;

@@ -498,10 +498,9 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
     csnet::IlsArgs T = A;
     T.ns = ns; T.gsn = A.GH / ns; T.hl = ns > 1 ? 1 : 0;
     T.GR = T.gsn + 2 * T.hl; T.GLR = T.gsn / 2 + 2 * T.hl;
-    T.hi_warps = (T.Cho * T.gsn + 31) / 32;
-    T.lo_warps = (T.Clo * (T.gsn / 2) + 31) / 32;
-    if (T.hi_warps + T.lo_warps < 4) T.hi_warps = 4 - T.lo_warps;       // the epilogue needs one warp per TMEM lane quarter
-    const int warps = T.hi_warps + T.lo_warps;
+    T.dw_warps = (T.Cho * T.gsn + T.Clo * (T.gsn / 2) + 31) / 32;        // tail tasks are packed: hi (channel, column)s, then lo ones
+    if (T.dw_warps < 4) T.dw_warps = 4;                                   // the epilogue needs one warp per TMEM lane quarter
+    const int warps = T.dw_warps;
     if (warps * 32 > csnet::kIlsMaxThreads || T.SH > 256 || T.SL > 256 || T.GR > 256) continue;
     const int nbh = (4 * T.GR + 15) / 16, nbl = T.Clo > 0 ? (2 * T.GLR + 15) / 16 : 0;
     const int cols = nbh * T.NH + nbl * T.NL;                              // fp32 accumulators of a chunk: TMEM columns
@@ -1022,9 +1021,9 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     static unsigned long long* dbg_buf = nullptr;
     if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(unsigned long long));
     A.dbg = dbg ? dbg_buf : nullptr;
-    if (stem) csnet::il_stream_kernel<__half, false, true><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
-    else if (dbg) csnet::il_stream_kernel<__half, true><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
-    else csnet::il_stream_kernel<__half, false><<<grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    if (stem) csnet::il_stream_kernel<__half, false, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    else if (dbg) csnet::il_stream_kernel<__half, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    else csnet::il_stream_kernel<__half, false><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     if (dbg && !stem) {        // debugging aid: mean cycles per phase over the CTAs (synchronises)
       std::vector<unsigned long long> h((size_t)grid * 8);
       cudaStreamSynchronize(stream);
@@ -1032,8 +1031,8 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
       double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) m[k] += (double)h[(size_t)b * 8 + k] / grid;
       int occ = -1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csnet::il_stream_kernel<__half, true>, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes);
-      fprintf(stderr, "[ils ns %d grid %d threads %d smem %d tmem %d occupancy %d] ", A.ns, grid, (A.hi_warps + A.lo_warps) * 32, A.smem_bytes, A.tmem_cols, occ);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csnet::il_stream_kernel<__half, true>, A.dw_warps * 32, A.smem_bytes);
+      fprintf(stderr, "[ils ns %d grid %d threads %d smem %d tmem %d occupancy %d] ", A.ns, grid, A.dw_warps * 32, A.smem_bytes, A.tmem_cols, occ);
       fprintf(stderr, "[ils %dx%d C %d+%d->%d+%d] cycles/CTA: load-wait %.0f resample %.0f syncA %.0f issue %.0f epilogue %.0f syncB %.0f dw %.0f tail %.0f\n",
               A.H, A.W, A.Chi, A.Cli, A.Cho, A.Clo, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
     }
