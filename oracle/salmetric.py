@@ -7,8 +7,11 @@ Follows /root/reference/CSNet_training/SalMetric/src/sal_metric.cpp:
   * do_evaluation (:164-185): per-threshold means over images, F = 1.3*P*R / (0.3*P + R),
     report max-F (and its argmax P/R), mean-F, mean P/R, MAE.
 Constants: sal_metric.hpp:50-52 (THRESHOLDS 256, EPSILON 1e-4, BETA 0.3).
-The reference binary cannot run here (needs OpenCV 3.4), so this restatement is "parity unpinned"
-against the binary; it is pinned only by the hand-computed cases in tests/test_salmetric.py.
+PINNED against the reference's own code: oracle/build_ref.py compiles the UNMODIFIED sal_metric.cpp (from where it lies under
+/root/reference, with oracle/cvshim standing in for the three OpenCV headers: cv::Mat + a PGM imread) into oracle/_ref/salmetric;
+tests/golden/salmetric_ref.json holds its reports on seeded maps (tests/golden/make_salmetric_golden.py) and
+tests/test_salmetric.py compares this restatement with them (and with the live binary when present), next to the loop-for-loop
+restatement and the hand-computed cases.
 Also provides the reference's png quantisation: (sigmoid * 255).astype(uint8) (CSNet/test.py:94-96).
 """
 from __future__ import annotations

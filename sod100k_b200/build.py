@@ -20,12 +20,28 @@ def nvcc() -> str:
     return exe
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over every source the library is built from (csrc/*, the C-ABI header) and the compiler flags: the rebuild
+    decision is keyed on CONTENT, not on mtimes — a pushed .so that is newer than the sources but built from other sources
+    (the snapshot that travels to the GPU box) is rebuilt, never silently reused."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "csnet_b200.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "csnet_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(STAMP).read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -36,6 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     if verbose:
         print(res.stdout + res.stderr)
     return LIB

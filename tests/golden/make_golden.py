@@ -134,6 +134,48 @@ def main():
     print("wrote", sorted(os.listdir(HERE)))
 
 
+def main_train():
+    """Train-mode pin: the UNMODIFIED reference module in train mode with the dynamic-weight-decay hooks
+    (flops_hook(expandflop=1.0), csnet.py:332-355), mean BCE-with-logits + WEIGHT * get_flops() (train.py:209-213, WEIGHT = 3.0
+    as in configs/csnet-L-x2_train.yml), autograd.  Stored per checkpoint: loss, regulariser, for EVERY parameter the gradient's
+    L2 norm + 16 sampled elements, the updated BN running statistics (8 sampled elements each)."""
+    import torch.nn.functional as F
+
+    out = {}
+    meta = {"flops_weight": 3.0, "expandflop": 1.0, "n": 2, "hw": [64, 96], "seed": 71, "n_grad_samples": 16, "n_stat_samples": 8}
+    for tag in ("csnet-L-x2", "csnet-L-x1"):
+        model = build(predefine=f"{CK}/{tag}/{tag}.bin")
+        ck = torch.load(f"{CK}/{tag}/{tag}.pth.tar", map_location="cpu", weights_only=False)
+        model.load_state_dict(ck["state_dict"])
+        model.train()
+        model.flops_hook(expandflop=1.0)
+        x = torch.from_numpy(synth.randn_images(2, 64, 96, 71))
+        t = torch.from_numpy(synth.random_masks(2, 64, 96, 72))
+        model.clear_flops()
+        model.set_batchsize(2)
+        y = model(x)
+        loss = F.binary_cross_entropy_with_logits(y, t)
+        reg = model.get_flops()
+        total = loss + 3.0 * reg
+        model.zero_grad()
+        total.backward()
+        out[f"{tag}/loss"] = np.array([loss.item()], np.float64)
+        out[f"{tag}/reg"] = np.array([float(reg)], np.float64)
+        out[f"{tag}/logits_sample"] = y.detach().reshape(-1).numpy()[sample_idx(y.numel(), 7)]
+        for k, p_ in model.named_parameters():
+            g = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).reshape(-1).double().numpy()
+            idx = np.random.default_rng(abs(hash(k)) % (2 ** 31) if False else sum(map(ord, k))).integers(0, g.size, 16)
+            out[f"{tag}/grad/{k}"] = np.concatenate([[np.sqrt((g * g).sum())], g[idx]])
+        for k, b in model.named_buffers():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                v = b.reshape(-1).double().numpy()
+                idx = np.random.default_rng(sum(map(ord, k))).integers(0, v.size, 8)
+                out[f"{tag}/stat/{k}"] = v[idx]
+    meta["torch"] = torch.__version__
+    np.savez_compressed(os.path.join(HERE, "train.npz"), __meta__=np.array(json.dumps(meta)), **out)
+    print("wrote train.npz", {k: v.tolist() for k, v in out.items() if k.endswith("/loss") or k.endswith("/reg")})
+
+
 def main_r():
     """CSF+Res2Net (config 5): reference `networks.csf_res2net.build_model()` with seeded synthetic weights."""
     for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
@@ -167,6 +209,10 @@ def main_r():
 
 
 if __name__ == "__main__":
-    if "--r-only" not in sys.argv:
-        main()
-    main_r()
+    if "--train-only" in sys.argv:
+        main_train()
+    else:
+        if "--r-only" not in sys.argv:
+            main()
+            main_train()
+        main_r()

@@ -91,3 +91,47 @@ def test_state_shapes_and_init_config_match_reference_fixture():
         cfg, sd = fixtures.checkpoint(tag)
         assert {k: tuple(v.shape) for k, v in sd.items()} == O.state_shapes(cfg)
         assert len(sd) == meta[tag]["n_state"]
+
+
+@pytest.mark.parametrize("tag", ["csnet-L-x2", "csnet-L-x1"])
+def test_oracle_train_step_matches_reference_autograd(tag):
+    """tests/golden/train.npz: the UNMODIFIED reference module in train mode with its Oct_bn_hook regulariser (WEIGHT 3.0,
+    expandflop 1.0), BCE-with-logits and autograd, recorded by make_golden.py.  The oracle's train_step must reproduce the loss,
+    the regulariser, every parameter's gradient (L2 norm + 16 sampled elements) and the updated BN running statistics."""
+    import json
+    import os
+
+    z = np.load(os.path.join(fixtures.GOLDEN, "train.npz"))
+    meta = json.loads(str(z["__meta__"]))
+    cfg, sd = fixtures.checkpoint(tag)
+    n, (h, w) = meta["n"], meta["hw"]
+    x = torch.from_numpy(synth.randn_images(n, h, w, meta["seed"]))
+    t = torch.from_numpy(synth.random_masks(n, h, w, meta["seed"] + 1))
+    shapes = O.state_shapes(cfg)
+    params = {k: v for k, v in sd.items() if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))}
+    buffers = {k: v for k, v in sd.items() if k not in params}
+    assert set(params) | set(buffers) == set(shapes)
+    loss, grads, _, new_buffers, _ = O.train_step(cfg, params, buffers, {}, x, t, flops_weight=meta["flops_weight"],
+                                                  flops_expand=meta["expandflop"])
+    assert abs(loss.item() - float(z[f"{tag}/loss"][0])) <= 1e-6
+    # regulariser value: recompute through the forward
+    sd2 = dict(buffers)
+    sd2.update(params)
+    with torch.no_grad():
+        _, reg = O.csnet_forward(cfg, sd2, x, training=True, new_stats={}, flops_expand=meta["expandflop"])
+    assert abs(float(reg) / n - float(z[f"{tag}/reg"][0])) <= 1e-6 * max(1.0, abs(float(z[f"{tag}/reg"][0])))
+    worst = 0.0
+    for k, g in grads.items():
+        ref = z[f"{tag}/grad/{k}"]
+        gv = g.reshape(-1).double().numpy()
+        idx = np.random.default_rng(sum(map(ord, k))).integers(0, gv.size, meta["n_grad_samples"])
+        scale = max(ref[0] / np.sqrt(gv.size), 1e-12)                    # rms gradient magnitude of the tensor
+        assert abs(np.sqrt((gv * gv).sum()) - ref[0]) <= 1e-4 * max(ref[0], 1e-9), k
+        d = np.abs(gv[idx] - ref[1:]).max() / scale
+        worst = max(worst, d)
+        assert d <= 1e-3, (k, d)
+    for k in new_buffers:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            v = new_buffers[k].reshape(-1).double().numpy()
+            idx = np.random.default_rng(sum(map(ord, k))).integers(0, v.size, meta["n_stat_samples"])
+            assert np.allclose(v[idx], z[f"{tag}/stat/{k}"], rtol=1e-5, atol=1e-7), k

@@ -71,3 +71,48 @@ def test_gt_threshold_is_strictly_above_128_and_quantisation_truncates():
     assert p[0] == pytest.approx((1 + 1e-4) / (2 + 1e-4)) and r[0] == pytest.approx(1.0)
     assert p[200] == pytest.approx(1.0) and r[200] == pytest.approx(1e-4 / (1 + 1e-4), rel=1e-3)   # sal > 200 is empty
     assert sm.quantise(np.array([0.0, 0.999, 1.0, 0.5])).tolist() == [0, 254, 255, 127]
+
+
+def _golden_cases():
+    import json
+    import os
+
+    from tests import fixtures
+    return json.load(open(os.path.join(fixtures.GOLDEN, "salmetric_ref.json")))
+
+
+def _maps(args):
+    import importlib.util
+    import os
+
+    from tests import fixtures
+    spec = importlib.util.spec_from_file_location("make_salmetric_golden", os.path.join(fixtures.GOLDEN, "make_salmetric_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, mod.seeded_maps(*args)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_restatement_matches_the_reference_binary_golden(case):
+    """tests/golden/salmetric_ref.json = the report of the reference's OWN sal_metric.cpp (compiled unmodified against the
+    header shim in oracle/cvshim, oracle/build_ref.py) on seeded maps.  The binary prints 6 significant digits."""
+    g = _golden_cases()[case]
+    _, (sal, gt) = _maps(g["args"])
+    e, r = sm.evaluate(sal, gt), g["report"]
+    for mine, theirs in (("max_f", "Max_F-measre"), ("mean_f", "Mean_F-measre"), ("precision", "Precision"), ("recall", "Recall"),
+                         ("mean_precision", "Mean_Precision"), ("mean_recall", "Mean_Recall"), ("mae", "MAE")):
+        assert abs(e[mine] - r[theirs]) <= 2e-6 + 2e-6 * abs(r[theirs]), (mine, e[mine], r[theirs])
+
+
+def test_restatement_matches_the_reference_binary_live():
+    """Same comparison against the binary itself when it is present (built here by __graft_entry__.build(); it travels to the
+    GPU box with the snapshot), on maps that are not in the committed golden."""
+    import os
+
+    binary = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "salmetric")
+    if not os.path.exists(binary):
+        pytest.skip("oracle/_ref/salmetric not built (needs /root/reference at build time)")
+    mod, (sal, gt) = _maps([21, 6, 20, 28])
+    e, r = sm.evaluate(sal, gt), mod.run_reference(binary, sal, gt, threads=2)
+    for mine, theirs in (("max_f", "Max_F-measre"), ("mean_f", "Mean_F-measre"), ("mae", "MAE"), ("precision", "Precision"), ("recall", "Recall")):
+        assert abs(e[mine] - r[theirs]) <= 2e-6 + 2e-6 * abs(r[theirs]), (mine, e[mine], r[theirs])
