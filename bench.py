@@ -403,9 +403,19 @@ def run_ours(a):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     prog = plan.prog
-    top = max(range(len(per_op)), key=lambda i: per_op[i])
+    # dominant KERNEL = the kernel (family) with the largest share of the step; its roofline is aggregated over its launches:
+    # (sum of their algorithmic bytes) / (sum of their live CUDA-event durations) == mean bytes per launch / mean launch duration
+    kern = [plan.op_kernel(i) for i in range(len(per_op))]
+    share = {}
+    for k_, t_ in zip(kern, per_op):
+        share[k_] = share.get(k_, 0.0) + t_
+    dom = max(share, key=share.get)
+    dom_ops = [i for i in range(len(per_op)) if kern[i] == dom]
+    top = max(dom_ops, key=lambda i: per_op[i])                 # its slowest launch
+    dom_bytes = sum(op_bytes(prog, prog.ops[i], B) for i in dom_ops)
+    dom_ms = sum(per_op[i] for i in dom_ops)
     top_bytes = op_bytes(prog, prog.ops[top], B)
-    achieved = top_bytes / (per_op[top] * 1e-3) / 1e9
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     dbytes = ir.DTYPE_BYTES[ir.DTYPE_NAMES[a.dtype]]
     net_bytes = roofline.bytes_per_image(cfg, S, S, dbytes, "block")
     ips = B * world * a.steps / (ms * 1e-3)
@@ -422,7 +432,9 @@ def run_ours(a):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{a.model}:{prog.ops[top].name}:bs{B}:{S}x{S}:{a.dtype}")
+        tj = json.load(open(tpath))
+        per = [tj.get(f"{a.model}:{prog.ops[i].name}:bs{B}:{S}x{S}:{a.dtype}") for i in dom_ops]
+        traffic = sum(per) if all(v is not None for v in per) else None
     out = {
         "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -431,8 +443,14 @@ def run_ours(a):
                 "d2h_bytes_per_step": int(y_host.numel() * 4), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": plan.launches * a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": f"op {top} '{prog.ops[top].name}'", "kernel_ms": per_op[top],
-                     "algorithmic_bytes_per_launch": top_bytes, "peak_source": peak_src,
+                     "traffic": traffic, "kernel": dom, "kernel_share_of_step": dom_ms / sum(per_op), "kernel_launches_per_step": len(dom_ops),
+                     "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
+                     "note": "achieved = sum of the kernel's algorithmic bytes over its launches in one step / sum of their CUDA-event times; "
+                             "traffic = ncu dram bytes of the same launches (profiles/traffic.json)",
+                     "slowest_launch": {"op": prog.ops[top].name, "ms": per_op[top], "algorithmic_bytes": top_bytes,
+                                        "achieved": top_bytes / (per_op[top] * 1e-3) / 1e9, "frac": top_bytes / (per_op[top] * 1e-3) / 1e9 / peak},
+                     "by_kernel": {k_: {"ms": v_, "share": v_ / sum(per_op)} for k_, v_ in sorted(share.items(), key=lambda kv: -kv[1])},
+                     "peak_source": peak_src,
                      "net": {"bytes_per_image_block_fused": net_bytes,
                              "achieved": ips / world * net_bytes / 1e9, "frac": ips / world * net_bytes / 1e9 / peak}},
     }
@@ -447,6 +465,14 @@ def run_ours(a):
                 out["configs"].append(extra_config(a, mname, size, batch, dev))
             except Exception as e:
                 out["configs"].append({"workload": f"{mname} {batch} x {size}x{size}", "unavailable": f"{type(e).__name__}: {e}"[:200]})
+        try:                                                      # the 1e-3 parity path (fp32 activations, generic kernels), for the record
+            a32 = argparse.Namespace(**vars(a))
+            a32.dtype = "fp32"
+            c32 = extra_config(a32, a.model, a.size, 64, dev, steps=3)
+            c32["note"] = "fp32 storage: the configuration that meets the 1e-3 sigmoid gate (generic kernels)"
+            out["configs"].append(c32)
+        except Exception as e:
+            out["configs"].append({"workload": f"{a.model} fp32 64 x {a.size}x{a.size}", "unavailable": f"{type(e).__name__}: {e}"[:200]})
         for c in out["configs"]:
             if "achieved_gbs" in c:
                 c["roofline_net_frac"] = c["achieved_gbs"] / peak

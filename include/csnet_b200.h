@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CSNET_ABI_VERSION 4
+#define CSNET_ABI_VERSION 5
 
 enum { CSNET_F32 = 0, CSNET_F16 = 1, CSNET_BF16 = 2 };
 
@@ -172,6 +172,10 @@ void* csnet_plan_tensor_ptr(csnet_plan* plan, int32_t tensor, int32_t N);
 
 /* Copy an arena tensor of the last run of batch N into caller-owned DEVICE memory (same dtype, dense). */
 int csnet_plan_read_tensor(csnet_plan* plan, int32_t tensor, int32_t N, void* dst_device, void* stream);
+
+/* Name of the kernel (family) csnet_plan_run launches for op `op_index` of this plan — measurement aid: bench.py groups the per-op
+ * times of csnet_plan_profile by kernel to find the dominant one.  "" for an invalid index. */
+const char* csnet_plan_op_kernel(const csnet_plan* plan, int32_t op_index);
 
 /* Number of kernel launches one csnet_plan_run issues (bench.py reports it as gpu_launches). */
 int32_t csnet_plan_launches(const csnet_plan* plan);

@@ -1125,6 +1125,24 @@ int csnet_plan_read_tensor(csnet_plan* P, int32_t tensor, int32_t N, void* dst, 
   return CSNET_OK;
 }
 
+// Which kernel launch_op() runs for op i — the same decision chain, by name (bench.py groups per-op times by kernel).
+const char* csnet_plan_op_kernel(const csnet_plan* P, int32_t i) {
+  if (!P || i < 0 || i >= (int32_t)P->ops.size()) return "";
+  const csnet_op_desc& op = P->ops[i];
+  const csnet_tensor_desc& D = P->tensors[op.dst];
+  if (P->op_msd[i]) return "msd_kernel (ms_direct.cuh, FP32 pipe)";
+  if (P->op_ms[i] && (int64_t)P->max_batch * (D.H / csnet::kMsRows) >= (int64_t)2 * P->num_sms) return "mix_stream_kernel (TMA + tcgen05)";
+  if ((op.kind == CSNET_OP_MIX || op.kind == CSNET_OP_MIXPROJ) && P->op_tc[i].mt > 0) return "mix_tc_kernel (mma.sync)";
+  if (op.kind == CSNET_OP_MIX && op.n_paths == 1 && op.paths[0].ksize == 0 && op.paths[0].cout0 == 0 && op.paths[0].cout == D.C)
+    return "pool2 / upsample / resample kernels";
+  if (op.kind == CSNET_OP_MIX) return "mix_generic_kernel";
+  if (op.kind == CSNET_OP_GN) return "gn kernels";
+  if (op.kind == CSNET_OP_ILBLOCK && P->op_ils[i] && (int64_t)P->max_batch * (D.H / 4) >= (int64_t)P->ils_min_chunks)
+    return "il_stream_kernel (TMA + tcgen05 + TMEM)";
+  if (op.kind == CSNET_OP_ILBLOCK) return "il_block_kernel (mma.sync, tiled)";
+  return "dw kernels";
+}
+
 int32_t csnet_plan_launches(const csnet_plan* P) {
   if (!P) return 0;
   int32_t n = 0;

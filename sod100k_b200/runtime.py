@@ -13,13 +13,13 @@ from . import ir
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsnet_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 PARAM_EPOCH = 0      # bumped by in-place parameter updates that bypass torch's version counters (FusedAdam)
 _lib = None
 
 # every symbol include/csnet_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ("csnet_abi_version", "csnet_last_error", "csnet_device_count", "csnet_plan_create",
-           "csnet_plan_set_blob", "csnet_plan_run", "csnet_plan_profile", "csnet_plan_tensor_ptr", "csnet_plan_read_tensor", "csnet_plan_launches",
+           "csnet_plan_set_blob", "csnet_plan_run", "csnet_plan_profile", "csnet_plan_tensor_ptr", "csnet_plan_read_tensor", "csnet_plan_op_kernel", "csnet_plan_launches",
            "csnet_plan_arena_bytes", "csnet_plan_destroy", "csnet_plan_run_host",
            "csnet_train_last_error", "csnet_train_bn_stats", "csnet_train_bn_prelu_fwd", "csnet_train_bn_prelu_bwd",
            "csnet_train_dw_conv", "csnet_train_dw_wgrad", "csnet_train_mix_fwd", "csnet_train_mix_dgrad",
@@ -57,6 +57,8 @@ def load_library(path: Optional[str] = None):
     lib.csnet_plan_tensor_ptr.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.csnet_plan_read_tensor.restype = C.c_int
     lib.csnet_plan_read_tensor.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.csnet_plan_op_kernel.restype = C.c_char_p
+    lib.csnet_plan_op_kernel.argtypes = [C.c_void_p, C.c_int32]
     lib.csnet_plan_launches.restype = C.c_int32
     lib.csnet_plan_launches.argtypes = [C.c_void_p]
     lib.csnet_plan_arena_bytes.restype = C.c_int64
@@ -117,6 +119,10 @@ class Plan:
 
     def tensor_ptr(self, tensor: int, N: int) -> int:
         return int(self.lib.csnet_plan_tensor_ptr(self._h, tensor, N) or 0)
+
+    def op_kernel(self, i: int) -> str:
+        """Kernel (family) that runs op i of this plan."""
+        return (self.lib.csnet_plan_op_kernel(self._h, int(i)) or b"").decode()
 
     @property
     def launches(self) -> int:
