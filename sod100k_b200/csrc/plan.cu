@@ -168,6 +168,12 @@ struct csnet_plan {
   std::vector<TcChoice> op_tc;
   std::vector<std::vector<uint16_t*>> op_w16;     // per tensor-core MIX op, per path: packed 16-bit weights (device)
   std::vector<float> h_blob;                      // host copy of the blob (epilogue tables of the streaming ILBlock kernel)
+  // small-batch replay: the whole op list captured once per batch size into a CUDA graph over plan-owned input / output staging
+  // (CSNet/test.py calls the model one image at a time: ~80 launches per forward are launch-bound there)
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; void* in = nullptr; void* out = nullptr; size_t in_bytes = 0, out_bytes = 0; };
+  std::vector<GraphSlot> graphs;                  // index = batch size
+  cudaStream_t cap_stream = nullptr;
+  int graph_max_n = 8;                            // CSNET_GRAPH_MAX_N (0 disables)
   std::vector<char> op_msd;                       // per op: an MSBlock whose dilated paths run on ms_direct.cuh
   std::vector<char> op_ms;                        // per op: the streaming 1x1 MIX kernel (mix_stream.cuh) can run it
   bool ms_enabled = true;                         // CSNET_MS=0 at plan creation: mix_tc / generic kernels only
@@ -832,6 +838,7 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   }
   P->op_msd.assign(P->ops.size(), 0);
   for (size_t i = 0; i < P->ops.size(); ++i) P->op_msd[i] = is_msd(*P, P->ops[i]) ? 1 : 0;
+  if (const char* e6 = getenv("CSNET_GRAPH_MAX_N")) P->graph_max_n = atoi(e6);
   if (const char* e4 = getenv("CSNET_MS")) P->ms_enabled = e4[0] != '0';
   P->op_ms.assign(P->ops.size(), 0);
   bool any_ms = false;
@@ -874,11 +881,14 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   return CSNET_OK;
 }
 
+static void drop_graphs(csnet_plan* P);
+
 int csnet_plan_set_blob(csnet_plan* P, const float* host_blob, int64_t n, void* stream) {
   if (!P || !host_blob || n != P->blob_floats) return fail(CSNET_E_INVALID, "csnet_plan_set_blob: size mismatch");
   DeviceGuard guard_(P->device);
   CU_CHECK(cudaMemcpyAsync(P->blob, host_blob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   P->h_blob.assign(host_blob, host_blob + n);
+  drop_graphs(P);                                   // captured launches carry parameter tables of the old blob
   // tensor-core MIX ops read their weights as 16-bit [chunk][tap][m16_total][kc + 8] blocks: pack them here, once per
   // weight update, so the kernels stage them with plain 16-byte copies
   std::vector<std::vector<uint16_t>> keep;
@@ -1075,16 +1085,69 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
   return CSNET_OK;
 }
 
+static int run_ops(csnet_plan* P, int32_t N, const void* const* ext_ptrs, cudaStream_t stream) {
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    const int rc = launch_op(P, i, N, ext_ptrs, stream);
+    if (rc != CSNET_OK) return rc;
+  }
+  return CSNET_OK;
+}
+
+static void drop_graphs(csnet_plan* P) {
+  for (auto& g : P->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.in) cudaFree(g.in);
+    if (g.out) cudaFree(g.out);
+    g = csnet_plan::GraphSlot();
+  }
+}
+
+// Small batches of a two-external plan (input, logits): copy the input into the plan's staging buffer, replay the captured
+// graph, copy the logits out — three stream operations instead of one launch per op.
+static int run_graph(csnet_plan* P, int32_t N, const void* const* ext_ptrs, cudaStream_t stream) {
+  if ((int)P->graphs.size() <= N) P->graphs.resize((size_t)N + 1);
+  csnet_plan::GraphSlot& G = P->graphs[N];
+  const csnet_tensor_desc *in = nullptr, *out = nullptr;
+  for (const auto& d : P->tensors) {
+    if (d.external == 0) in = &d;
+    if (d.external == 1) out = &d;
+  }
+  if (!G.exec) {
+    G.in_bytes = (size_t)N * in->C * in->H * in->W * dtype_size(in->dtype);
+    G.out_bytes = (size_t)N * out->C * out->H * out->W * dtype_size(out->dtype);
+    CU_CHECK(cudaMalloc(&G.in, G.in_bytes));
+    CU_CHECK(cudaMalloc(&G.out, G.out_bytes));
+    const void* ext[2] = {G.in, G.out};
+    cudaGraph_t graph = nullptr;
+    // capture on a stream of our own: the caller's may be the legacy default stream, which cannot be captured
+    if (!P->cap_stream) CU_CHECK(cudaStreamCreateWithFlags(&P->cap_stream, cudaStreamNonBlocking));
+    CU_CHECK(cudaStreamBeginCapture(P->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_ops(P, N, ext, P->cap_stream);
+    const cudaError_t e = cudaStreamEndCapture(P->cap_stream, &graph);
+    if (rc != CSNET_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != CSNET_OK ? rc : fail(CSNET_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    }
+    const cudaError_t e2 = cudaGraphInstantiate(&G.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { G.exec = nullptr; return fail(CSNET_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2)); }
+  }
+  CU_CHECK(cudaMemcpyAsync(G.in, ext_ptrs[0], G.in_bytes, cudaMemcpyDeviceToDevice, stream));
+  CU_CHECK(cudaGraphLaunch(G.exec, stream));
+  CU_CHECK(cudaMemcpyAsync(const_cast<void*>(ext_ptrs[1]), G.out, G.out_bytes, cudaMemcpyDeviceToDevice, stream));
+  return CSNET_OK;
+}
+
 int csnet_plan_run(csnet_plan* P, int32_t N, const void* const* ext_ptrs, int32_t n_ext, void* stream_) {
   int rc = check_run_args(P, N, ext_ptrs, n_ext);
   if (rc != CSNET_OK) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceGuard guard_(P->device);
-  for (size_t i = 0; i < P->ops.size(); ++i) {
-    rc = launch_op(P, i, N, ext_ptrs, stream);
-    if (rc != CSNET_OK) return rc;
-  }
-  return CSNET_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (N <= P->graph_max_n && P->n_ext == 2 && cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+    return run_graph(P, N, ext_ptrs, stream);
+  return run_ops(P, N, ext_ptrs, stream);
 }
 
 int csnet_plan_profile(csnet_plan* P, int32_t N, const void* const* ext_ptrs, int32_t n_ext, void* stream_,
@@ -1157,6 +1220,8 @@ int64_t csnet_plan_arena_bytes(const csnet_plan* P) { return P ? P->arena_per_im
 
 void csnet_plan_destroy(csnet_plan* P) {
   if (!P) return;
+  drop_graphs(P);
+  if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
   DeviceGuard guard_(P->device);
   if (P->blob) cudaFree(P->blob);
   if (P->arena) cudaFree(P->arena);
@@ -1244,7 +1309,7 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
     CU_CHECK(cudaStreamWaitEvent(stream, P->ev_h2d[b], 0));
     if (it >= 2) CU_CHECK(cudaStreamWaitEvent(stream, P->ev_d2h[b], 0));         // staging output b was drained
     const void* ext[2] = {P->h_in[b], P->h_out[b]};
-    rc = csnet_plan_run(P, nb, ext, 2, stream_);
+    rc = run_ops(P, nb, ext, stream);               // (its own staging: no graph path)
     if (rc != CSNET_OK) break;
     CU_CHECK(cudaEventRecord(P->ev_comp[b], stream));
     CU_CHECK(cudaStreamWaitEvent(P->s_d2h, P->ev_comp[b], 0));
