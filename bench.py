@@ -381,6 +381,15 @@ def run_ours(a):
         for _ in range(max(1, a.warmup // 2)):
             e2e_fn()
         ms_e2e = timed(e2e_fn, a.steps)
+        # same, with the reference's pre / post-processing on the device (uint8 images in, uint8 maps out: test.py:68-98)
+        ms_u8 = None
+        if not a.no_extras:
+            xu8 = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8).pin_memory()
+            yu8 = torch.empty((B, S, S), dtype=torch.uint8).pin_memory()
+            u8_fn = lambda: eng.forward_host_u8(xu8, out=yu8, device=local)
+            for _ in range(max(1, a.warmup // 2)):
+                u8_fn()
+            ms_u8 = timed(u8_fn, a.steps)
         per_op = plan.profile(B, [x_dev.data_ptr(), torch.empty_like(y_host, device=dev).data_ptr()], stream.cuda_stream)
         per_op = [min(u, v) for u, v in zip(per_op, plan.profile(B, [x_dev.data_ptr(), torch.empty_like(y_host, device=dev).data_ptr()], stream.cuda_stream))]
 
@@ -441,6 +450,10 @@ def run_ours(a):
         "dtype": a.dtype, "data": "synthetic", "config": workload_config(a, world), "clocks": clk,
         "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(y_host.numel() * 4), "ms_per_step": ms_e2e / a.steps},
+        "e2e_u8": None if ms_u8 is None else {
+            "value": B * world * a.steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(B * S * S * 3),
+            "d2h_bytes_per_step": int(B * S * S), "ms_per_step": ms_u8 / a.steps,
+            "note": "csnet_plan_run_host_u8: uint8 HWC images in, uint8 saliency maps out; normalisation and sigmoid*255 on the device"},
         "gpu_launches": plan.launches * a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": dom, "kernel_share_of_step": dom_ms / sum(per_op), "kernel_launches_per_step": len(dom_ops),

@@ -194,6 +194,15 @@ void csnet_plan_destroy(csnet_plan* plan);
  */
 int csnet_plan_run_host(csnet_plan* plan, int32_t N, const float* x_host, float* y_host, void* stream);
 
+/*
+ * Same pipeline with the reference's pre- and post-processing moved onto the device (CSNet/test.py:68-69,86-96):
+ * x_hwc = uint8 [N][H][W][3] images as io.imread returns them (already at the network size), y_u8 = uint8 [N][H][W] saliency maps
+ * = (sigmoid(logits) * 255) truncated, exactly what test.py writes to png.  The input becomes (x / 255 - mean[c]) / std[c]
+ * (evaluated in float64, rounded to fp32, like the host code).  4x fewer bytes over PCIe in both directions.
+ */
+int csnet_plan_run_host_u8(csnet_plan* plan, int32_t N, const uint8_t* x_hwc, uint8_t* y_u8, const float* mean, const float* std,
+                           void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training primitives (fp32 planar NCHW device tensors).  The reference trains through torch autograd
  * (CSNet_training/train.py:203-216); train-mode BatchNorm makes the reference MODULE the closed unit, so the

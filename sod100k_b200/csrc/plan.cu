@@ -135,6 +135,27 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const __grid_constan
   }
 }
 
+// Device-side pre / post-processing of CSNet/test.py:68-69,86-96: uint8 HWC image -> (x / 255 - mean) / std as the
+// fp32 NCHW network input (the reference computes it in float64 on the host and rounds to fp32: same here), and
+// sigmoid(logit) * 255 -> uint8 (astype truncation) of the saliency map.
+struct PreArgs { double mean[3], std[3]; };
+__global__ void __launch_bounds__(kThreads) pre_u8_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, int64_t npix, int64_t hw, const __grid_constant__ PreArgs A) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;          // pixel over (n, h, w)
+  if (i >= npix) return;
+  const int64_t n = i / hw, p = i - n * hw;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) y[(n * 3 + c) * hw + p] = (float)(((double)x[i * 3 + c] / 255.0 - A.mean[c]) / A.std[c]);
+}
+__global__ void __launch_bounds__(kThreads) post_u8_kernel(const float* __restrict__ z, uint8_t* __restrict__ y, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+  if (i >= n) return;
+  uchar4 o;
+  const float4 v = *reinterpret_cast<const float4*>(z + i);                // n % 4 == 0 (W % 16 == 0)
+  o.x = (unsigned char)((1.f / (1.f + expf(-v.x))) * 255.f); o.y = (unsigned char)((1.f / (1.f + expf(-v.y))) * 255.f);
+  o.z = (unsigned char)((1.f / (1.f + expf(-v.z))) * 255.f); o.w = (unsigned char)((1.f / (1.f + expf(-v.w))) * 255.f);
+  *reinterpret_cast<uchar4*>(y + i) = o;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -184,6 +205,9 @@ struct csnet_plan {
   int ils_min_chunks = 592;                       // batches with fewer 4-row chunks per ILBlock run the tiled kernel
   // host-buffer pipeline (csnet_plan_run_host): copy streams, ping-pong staging, ordering events
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  void* h_in8[2] = {nullptr, nullptr};             // uint8 staging of csnet_plan_run_host_u8
+  void* h_out8[2] = {nullptr, nullptr};
+  size_t h_in8_bytes = 0;
   void* h_in[2] = {nullptr, nullptr};
   void* h_out[2] = {nullptr, nullptr};
   size_t h_in_bytes = 0, h_out_bytes = 0;
@@ -1232,6 +1256,8 @@ void csnet_plan_destroy(csnet_plan* P) {
   for (int b = 0; b < 2; ++b) {
     if (P->h_in[b]) cudaFree(P->h_in[b]);
     if (P->h_out[b]) cudaFree(P->h_out[b]);
+    if (P->h_in8[b]) cudaFree(P->h_in8[b]);
+    if (P->h_out8[b]) cudaFree(P->h_out8[b]);
     if (P->ev_h2d[b]) cudaEventDestroy(P->ev_h2d[b]);
     if (P->ev_comp[b]) cudaEventDestroy(P->ev_comp[b]);
     if (P->ev_d2h[b]) cudaEventDestroy(P->ev_d2h[b]);
@@ -1241,7 +1267,18 @@ void csnet_plan_destroy(csnet_plan* P) {
   delete P;
 }
 
+static int run_host_impl(csnet_plan* P, int32_t N, const void* x_host, void* y_host, void* stream_, bool u8, const float* mean, const float* stdv);
+
 int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_host, void* stream_) {
+  return run_host_impl(P, N, x_host, y_host, stream_, false, nullptr, nullptr);
+}
+
+int csnet_plan_run_host_u8(csnet_plan* P, int32_t N, const uint8_t* x_hwc, uint8_t* y_u8, const float* mean, const float* stdv, void* stream_) {
+  if (!mean || !stdv) return fail(CSNET_E_INVALID, "null mean / std");
+  return run_host_impl(P, N, x_hwc, y_u8, stream_, true, mean, stdv);
+}
+
+static int run_host_impl(csnet_plan* P, int32_t N, const void* x_host, void* y_host, void* stream_, bool u8, const float* mean, const float* stdv) {
   if (!P || !x_host || !y_host) return fail(CSNET_E_INVALID, "null argument");
   if (N <= 0 || N > P->max_batch) return fail(CSNET_E_INVALID, "batch size outside [1, max_batch]");
   if (P->n_ext != 2) return fail(CSNET_E_INVALID, "run_host needs a plan with externals {0: input, 1: logits}");
@@ -1269,10 +1306,14 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
     for (int n0 = 0; n0 < N; n0 += c) sizes[n_sizes++] = (N - n0) < c ? (N - n0) : c;
   } else {
     // first / last chunk in 256ths of the batch (CSNET_HOST_SPLIT="first,last", 0 = no such chunk); default 32 / 32
-    static int f256 = 32, l256 = 32;
-    static const bool parsed = [] { const char* e = getenv("CSNET_HOST_SPLIT"); if (e) sscanf(e, "%d,%d", &f256, &l256); return true; }();
+    // (uint8 form: the copies are 4x smaller, so one chunk at full-batch kernel efficiency wins; CSNET_HOST_SPLIT_U8)
+    static int f256 = 32, l256 = 32, f256u = 0, l256u = 0;    // measured (scripts/host_split.py): u8 one chunk 14.7 ms, 32/32 16.1 ms
+    static const bool parsed = [] {
+      const char* e = getenv("CSNET_HOST_SPLIT"); if (e) sscanf(e, "%d,%d", &f256, &l256);
+      e = getenv("CSNET_HOST_SPLIT_U8"); if (e) sscanf(e, "%d,%d", &f256u, &l256u);
+      return true; }();
     (void)parsed;
-    const int first = N * f256 / 256, last = N * l256 / 256;
+    const int first = N * (u8 ? f256u : f256) / 256, last = N * (u8 ? l256u : l256) / 256;
     if (first > 0 && first < N) sizes[n_sizes++] = first;
     const int mid = N - (first > 0 && first < N ? first : 0) - (last > 0 && last < N - first ? last : 0);
     sizes[n_sizes++] = mid;
@@ -1300,20 +1341,43 @@ int csnet_plan_run_host(csnet_plan* P, int32_t N, const float* x_host, float* y_
     P->h_in_bytes = (size_t)chunk * xin;
     P->h_out_bytes = (size_t)chunk * yout;
   }
+  const size_t xin8 = xin / sizeof(float), yout8 = yout / sizeof(float);      // bytes per image of the uint8 forms
+  if (u8 && P->h_in8_bytes < (size_t)chunk * xin8) {
+    for (int b = 0; b < 2; ++b) {
+      if (P->h_in8[b]) cudaFree(P->h_in8[b]);
+      if (P->h_out8[b]) cudaFree(P->h_out8[b]);
+      CU_CHECK(cudaMalloc(&P->h_in8[b], (size_t)chunk * xin8));
+      CU_CHECK(cudaMalloc(&P->h_out8[b], (size_t)chunk * yout8));
+    }
+    P->h_in8_bytes = (size_t)chunk * xin8;
+  }
+  if (u8 && in->C != 3) return fail(CSNET_E_INVALID, "run_host_u8: the network input must have 3 channels");
+  PreArgs PA{};
+  if (u8) for (int c = 0; c < 3; ++c) { PA.mean[c] = (double)mean[c]; PA.std[c] = (double)stdv[c]; }
   int rc = CSNET_OK;
   for (int it = 0, n0 = 0; it < n_sizes && rc == CSNET_OK; n0 += sizes[it], ++it) {
     const int b = it & 1, nb = sizes[it];
     if (it >= 2) CU_CHECK(cudaStreamWaitEvent(P->s_h2d, P->ev_comp[b], 0));     // staging input b was consumed
-    CU_CHECK(cudaMemcpyAsync(P->h_in[b], x_host + (size_t)n0 * (xin / sizeof(float)), (size_t)nb * xin, cudaMemcpyHostToDevice, P->s_h2d));
+    if (u8) CU_CHECK(cudaMemcpyAsync(P->h_in8[b], (const uint8_t*)x_host + (size_t)n0 * xin8, (size_t)nb * xin8, cudaMemcpyHostToDevice, P->s_h2d));
+    else CU_CHECK(cudaMemcpyAsync(P->h_in[b], (const float*)x_host + (size_t)n0 * (xin / sizeof(float)), (size_t)nb * xin, cudaMemcpyHostToDevice, P->s_h2d));
     CU_CHECK(cudaEventRecord(P->ev_h2d[b], P->s_h2d));
     CU_CHECK(cudaStreamWaitEvent(stream, P->ev_h2d[b], 0));
     if (it >= 2) CU_CHECK(cudaStreamWaitEvent(stream, P->ev_d2h[b], 0));         // staging output b was drained
+    if (u8) {
+      const int64_t npix = (int64_t)nb * in->H * in->W;
+      pre_u8_kernel<<<(unsigned)((npix + kThreads - 1) / kThreads), kThreads, 0, stream>>>((const uint8_t*)P->h_in8[b], (float*)P->h_in[b], npix, (int64_t)in->H * in->W, PA);
+    }
     const void* ext[2] = {P->h_in[b], P->h_out[b]};
     rc = run_ops(P, nb, ext, stream);               // (its own staging: no graph path)
     if (rc != CSNET_OK) break;
+    if (u8) {
+      const int64_t nel = (int64_t)nb * lo->C * lo->H * lo->W;
+      post_u8_kernel<<<(unsigned)((nel / 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>((const float*)P->h_out[b], (uint8_t*)P->h_out8[b], nel);
+    }
     CU_CHECK(cudaEventRecord(P->ev_comp[b], stream));
     CU_CHECK(cudaStreamWaitEvent(P->s_d2h, P->ev_comp[b], 0));
-    CU_CHECK(cudaMemcpyAsync(y_host + (size_t)n0 * (yout / sizeof(float)), P->h_out[b], (size_t)nb * yout, cudaMemcpyDeviceToHost, P->s_d2h));
+    if (u8) CU_CHECK(cudaMemcpyAsync((uint8_t*)y_host + (size_t)n0 * yout8, P->h_out8[b], (size_t)nb * yout8, cudaMemcpyDeviceToHost, P->s_d2h));
+    else CU_CHECK(cudaMemcpyAsync((float*)y_host + (size_t)n0 * (yout / sizeof(float)), P->h_out[b], (size_t)nb * yout, cudaMemcpyDeviceToHost, P->s_d2h));
     CU_CHECK(cudaEventRecord(P->ev_d2h[b], P->s_d2h));
   }
   cudaError_t e1 = cudaStreamSynchronize(P->s_d2h), e2 = cudaStreamSynchronize(stream), e3 = cudaStreamSynchronize(P->s_h2d);

@@ -135,3 +135,19 @@ class ModelEngine:
             out = torch.empty((N, 1, H, W), dtype=torch.float32, pin_memory=True)
         plan.run_host(N, x_host.data_ptr(), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         return out
+
+    IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)          # CSNet/test.py:68-69
+
+    def forward_host_u8(self, x_u8: torch.Tensor, out: torch.Tensor = None, device: int = 0, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+        """uint8 images in, uint8 saliency maps out, host to host (CSNet/test.py:72-98 without its resizes): x_u8 is [N,H,W,3] uint8
+        (ideally pinned) as io.imread returns it; normalisation, the network, sigmoid and the *255 quantisation run on the device."""
+        if x_u8.is_cuda or x_u8.dtype != torch.uint8 or x_u8.dim() != 4 or x_u8.shape[-1] != 3:
+            raise ValueError("forward_host_u8 takes a uint8 host tensor [N, H, W, 3]")
+        x_u8 = x_u8.contiguous()
+        N, H, W, _ = x_u8.shape
+        dev = torch.device("cuda", device)
+        plan = self.plan_for(N, H, W, dev)
+        if out is None:
+            out = torch.empty((N, H, W), dtype=torch.uint8, pin_memory=True)
+        plan.run_host_u8(N, x_u8.data_ptr(), out.data_ptr(), mean, std, torch.cuda.current_stream(dev).cuda_stream)
+        return out

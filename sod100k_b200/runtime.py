@@ -20,7 +20,7 @@ _lib = None
 # every symbol include/csnet_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ("csnet_abi_version", "csnet_last_error", "csnet_device_count", "csnet_plan_create",
            "csnet_plan_set_blob", "csnet_plan_run", "csnet_plan_profile", "csnet_plan_tensor_ptr", "csnet_plan_read_tensor", "csnet_plan_op_kernel", "csnet_plan_launches",
-           "csnet_plan_arena_bytes", "csnet_plan_destroy", "csnet_plan_run_host",
+           "csnet_plan_arena_bytes", "csnet_plan_destroy", "csnet_plan_run_host", "csnet_plan_run_host_u8",
            "csnet_train_last_error", "csnet_train_bn_stats", "csnet_train_bn_prelu_fwd", "csnet_train_bn_prelu_bwd",
            "csnet_train_dw_conv", "csnet_train_dw_wgrad", "csnet_train_mix_fwd", "csnet_train_mix_dgrad",
            "csnet_train_mix_wgrad", "csnet_train_bce", "csnet_train_adam", "csnet_salmetric_hist")
@@ -67,6 +67,8 @@ def load_library(path: Optional[str] = None):
     lib.csnet_plan_destroy.argtypes = [C.c_void_p]
     lib.csnet_plan_run_host.restype = C.c_int
     lib.csnet_plan_run_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.csnet_plan_run_host_u8.restype = C.c_int
+    lib.csnet_plan_run_host_u8.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]
     if lib.csnet_abi_version() != ABI_VERSION:
         raise EngineError(f"{path}: ABI {lib.csnet_abi_version()} != expected {ABI_VERSION}; rebuild")
     if path == LIB_PATH:
@@ -116,6 +118,10 @@ class Plan:
 
     def run_host(self, N: int, x_host_ptr: int, y_host_ptr: int, stream: int = 0):
         _check(self.lib, self.lib.csnet_plan_run_host(self._h, int(N), x_host_ptr, y_host_ptr, stream), "csnet_plan_run_host")
+
+    def run_host_u8(self, N: int, x_host_ptr: int, y_host_ptr: int, mean, std, stream: int = 0):
+        m, s_ = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        _check(self.lib, self.lib.csnet_plan_run_host_u8(self._h, int(N), x_host_ptr, y_host_ptr, m, s_, stream), "csnet_plan_run_host_u8")
 
     def tensor_ptr(self, tensor: int, N: int) -> int:
         return int(self.lib.csnet_plan_tensor_ptr(self._h, tensor, N) or 0)

@@ -159,6 +159,29 @@ def test_pipelined_host_call_equals_device_call():
     assert torch.equal(y_dev, y_host) and torch.equal(y_dev, y_host2)
 
 
+def test_uint8_host_path_matches_the_reference_pre_and_post_processing():
+    """csnet_plan_run_host_u8: the device-side (x / 255 - mean) / std and sigmoid * 255 -> uint8 against
+    the host code of CSNet/test.py:68-69,86-96 around the same network; 70 images so the chunked pipeline runs too."""
+    m, cfg, sd = _model("csnet-L-x1")
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(70, 64, 96, 3), dtype=np.uint8)
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    x_ref = torch.from_numpy((((img.astype(np.float64) / 255.0) - mean) / std).transpose(0, 3, 1, 2).copy()).float()   # test.py:68-69, 76-79
+    with torch.no_grad():
+        z = m(x_ref.cuda()).cpu()
+        y8 = m.engine().forward_host_u8(torch.from_numpy(img))
+    assert y8.dtype == torch.uint8 and tuple(y8.shape) == (70, 64, 96)
+    want = (torch.sigmoid(z.double())[:, 0] * 255.0)                        # test.py:86-96: sigmoid, * 255, astype(uint8)
+    d = (y8.double() - want.floor()).abs()
+    # the device evaluates sigmoid in fp32: a value within 1e-4 of an integer may truncate to the neighbour
+    near = (want - want.round()).abs() < 1e-3
+    assert d[~near].max().item() == 0 and d.max().item() <= 1
+    m.set_precision("fp16")
+    with torch.no_grad():
+        y8h = m.engine().forward_host_u8(torch.from_numpy(img).pin_memory())
+    assert (y8h.int() - y8.int()).abs().max().item() <= 3
+
+
 def test_large_batch_full_size_properties():
     """BASELINE config size (bs 256, 224x224, fp16): determinism + per-image independence."""
     m, cfg, sd = _model("csnet-L-x2")
@@ -170,6 +193,12 @@ def test_large_batch_full_size_properties():
     assert torch.equal(y, y2)
     assert torch.equal(y[:8], y[8 * 17:8 * 18])
     assert torch.isfinite(y).all()
+    # the 8 distinct images against the oracle: at this batch every streaming / tensor-core kernel of the bench
+    # configuration is on the path (the smaller parity tests above run the tiled kernels for some blocks)
+    ref = torch.sigmoid(_oracle(cfg, sd, x[:8].cpu().numpy()))
+    d = (torch.sigmoid(y[:8].float()).cpu() - ref).abs()
+    _record("fp16_bs256_sigmoid_maxabs", d.max().item())
+    assert d.max().item() <= SIG_TOL_FP16 and d.mean().item() <= SIG_MEAN_TOL["fp16"]
 
 
 @pytest.mark.parametrize("tag,hw,dtype", [("csnet-L-x2", (224, 224), "fp16"), ("csnet-L-x2", (96, 160), "fp16"),

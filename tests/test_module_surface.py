@@ -26,7 +26,7 @@ def lib():
 
 def test_header_symbols_are_exported(lib):
     header = open(os.path.join(ROOT, "include", "csnet_b200.h")).read()
-    declared = set(re.findall(r"\b(csnet_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(csnet_[a-z0-9_]+)\s*\(", header))
     assert declared == set(runtime.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
