@@ -251,6 +251,14 @@ int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
 /* Gradient of one conv path w.r.t. its weight, kernel layout [cin][k*k][cout]. */
 int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dw,
                           void* stream);
+/* The down-sampling a path carries, materialised once (F.avg_pool2d(2) of a stride-2 gOctaveConv, csnet.py:683-686, then F.max_pool2d(pool)
+ * of a high -> low path, :692-698): dst [N, cin, Hs/f, Ws/f] from channels [c0, c0+cin) of src [N, Cs, Hs, Ws], f = (pre_avg ? 2 : 1) * pool;
+ * idx (uint8, same shape, required when pool > 1) = position of the first maximum in the window.  _bwd routes the gradient of dst back to
+ * dsrc [N, cin, Hs, Ws] the way autograd does (max: to the recorded position; average: a quarter to each). */
+int csnet_train_pool_fwd(const float* src, int32_t N, int32_t Cs, int32_t c0, int32_t cin, int32_t Hs, int32_t Ws, int32_t pre_avg, int32_t pool,
+                         float* dst, uint8_t* idx, void* stream);
+int csnet_train_pool_bwd(const float* dpool, const uint8_t* idx, int32_t N, int32_t cin, int32_t Hs, int32_t Ws, int32_t pre_avg, int32_t pool,
+                         float* dsrc, void* stream);
 /* F.binary_cross_entropy_with_logits (mean) and its gradient * grad_scale (train.py:209). */
 int csnet_train_bce(const float* logits, const float* target, float* dlogits, float* loss, int64_t n, float grad_scale, void* stream);
 /* torch.optim.Adam step (train.py:108-123) over many tensors: `chunk_table_device` = n_chunks records

@@ -13,6 +13,7 @@
 
 #include "../../include/csnet_b200.h"
 #include "generic_ops.cuh"
+#include "train_fast.cuh"
 
 namespace {
 
@@ -426,7 +427,7 @@ const char* csnet_train_last_error(void) { return t_err.c_str(); }
 // the current device, i.e. the device of the tensors the caller's torch stream belongs to), grown on demand; the training entry
 // points of one device are meant to be issued on ONE stream (calls serialise there, so sharing within a device is safe).
 constexpr int kMaxDevices = 16;
-struct RedWs { float* ws = nullptr; unsigned* cnt = nullptr; size_t ws_cap = 0, cnt_cap = 0; };
+struct RedWs { float* ws = nullptr; unsigned* cnt = nullptr; size_t ws_cap = 0, cnt_cap = 0; float* part = nullptr; size_t part_cap = 0; };
 static RedWs g_red[kMaxDevices];
 static thread_local float* g_red_ws = nullptr;          // the current call's workspace (set by reduce_workspace)
 static thread_local unsigned* g_red_cnt = nullptr;
@@ -456,6 +457,103 @@ static int reduce_workspace(int C, int parts, cudaStream_t st) {
   g_red_ws = R.ws;
   g_red_cnt = R.cnt;
   return CSNET_OK;
+}
+
+// Block partials of the weight-gradient kernels ([blocks][elements] floats), one buffer per device, grown on demand.
+static int partial_workspace(size_t floats, cudaStream_t st, float** out) {
+  int dev = 0;
+  TR_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) { t_err = "device index out of range"; return CSNET_E_INVALID; }
+  RedWs& R = g_red[dev];
+  if (floats > R.part_cap) {
+    TR_CHECK(cudaStreamSynchronize(st));
+    if (R.part) cudaFree(R.part);
+    R.part = nullptr; R.part_cap = 0;
+    const size_t cap = floats * 2 < (1u << 20) ? (1u << 20) : floats * 2;
+    TR_CHECK(cudaMalloc(&R.part, cap * sizeof(float)));
+    R.part_cap = cap;
+  }
+  *out = R.part;
+  return CSNET_OK;
+}
+
+// ---- fast (register-tiled) dispatch: train_fast.cuh ------------------------------------------------------------------------------
+namespace tf = csnet::tf;
+constexpr size_t kFastSmem = 92 * 1024;                   // operand tiles; + kFastWsm of weights: two blocks per SM
+constexpr size_t kFastWsm = 16 * 1024;
+constexpr int kFastSmemMax = (int)(kFastSmem + kFastWsm);
+
+static bool fast_enabled() {
+  static const bool on = [] { const char* e = getenv("CSNET_TRAIN_FAST"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+static int num_sms() {
+  static int sms[kMaxDevices] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev] > 0 ? sms[dev] : 148;
+}
+
+static bool conv_tile_geometry(tf::ConvArgs& A) {
+  A.quads = (A.W + 3) / 4;
+  A.vec = (A.W % 4) == 0;
+  if (A.quads > tf::kT) return false;
+  if (A.H * A.quads * 2 <= tf::kT) { A.R = A.H; A.ipb = tf::kT / (A.H * A.quads); }
+  else { A.ipb = 1; A.R = tf::kT / A.quads; if (A.R > A.H) A.R = A.H; }
+  if (A.ipb > A.N) A.ipb = A.N;
+  return true;
+}
+
+static bool conv_path_geometry(tf::ConvPath& P, const tf::ConvArgs& A) {
+  const int kk = A.ksize * A.ksize;
+  P.halo = P.dil * (A.ksize / 2);
+  P.hp = (P.halo + 3) / 4 * 4;
+  P.Wp = (A.W + 2 * P.hp + 3) / 4 * 4;
+  P.rows = A.R + 2 * P.halo;
+  const size_t per_ci = (size_t)A.ipb * P.rows * P.Wp * sizeof(float), per_w = (size_t)kk * tf::kCoT * sizeof(float);
+  size_t chunk = kFastSmem / per_ci;
+  if (chunk > kFastWsm / per_w) chunk = kFastWsm / per_w;
+  if (chunk < 1) return false;
+  P.chunk = chunk < (size_t)P.cin ? (int)chunk : P.cin;
+  return true;
+}
+
+static int launch_conv(tf::ConvArgs& A, cudaStream_t st) {
+  const int kk = A.ksize * A.ksize;
+  size_t tile = 0, wsm = 0;
+  bool dil1 = true;
+  for (int i = 0; i < A.n_conv; ++i) {
+    const tf::ConvPath& P = A.p[i];
+    const size_t t = (size_t)P.chunk * A.ipb * P.rows * P.Wp, w = (size_t)P.chunk * kk * tf::kCoT;
+    tile = t > tile ? t : tile; wsm = w > wsm ? w : wsm;
+    dil1 = dil1 && P.dil == 1;
+  }
+  A.tile_floats = (int)tile;
+  const size_t smem = (tile + wsm) * sizeof(float);
+  const int bands = (A.H + A.R - 1) / A.R;
+  const unsigned grid = (unsigned)(((A.N + A.ipb - 1) / A.ipb) * bands);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tf::conv_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+    cudaFuncSetAttribute(tf::conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+    cudaFuncSetAttribute(tf::conv_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+    cudaFuncSetAttribute(tf::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+    cudaFuncSetAttribute(tf::conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+    attr = true;
+  }
+  if (A.n_conv == 0 || (A.ksize == 1)) tf::conv_fwd_kernel<1><<<grid, tf::kT, smem, st>>>(A);
+  else if (A.ksize == 3 && dil1) tf::conv_fwd_kernel<3><<<grid, tf::kT, smem, st>>>(A);
+  else tf::conv_fwd_kernel<0><<<grid, tf::kT, smem, st>>>(A);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+static bool dense_conv_path(const csnet::MixPath& P, int H, int W) {
+  return P.ksize >= 1 && (P.ksize & 1) && P.stride == 1 && P.pre_avg == 0 && P.pool == 1 && P.up == 1 && P.H == H && P.W == W &&
+         P.pad == P.dil * (P.ksize / 2) && P.dil >= 1;
 }
 
 // segments per image plane: enough parts to fill the GPU for narrow layers and small batches, at most 64 per plane
@@ -495,13 +593,32 @@ int csnet_train_bn_prelu_bwd(const float* z, const float* dy, float* dz, int32_t
 
 int csnet_train_dw_conv(const float* x, const float* w, float* y, int32_t N, int32_t C, int32_t H, int32_t W, float scale,
                         int32_t transposed, void* stream) {
-  dw_fwd_kernel<<<dim3((H * W + kT - 1) / kT, C, N), kT, 0, (cudaStream_t)stream>>>(x, w, y, C, H, W, scale, transposed);
+  if (fast_enabled()) {
+    const int quads = (W + 3) / 4, rows = H < 8 ? H : 8, bands = (H + rows - 1) / rows;
+    const size_t tasks = (size_t)N * C * bands * quads;
+    tf::dw3_kernel<<<(unsigned)((tasks + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(x, w, y, N, C, H, W, scale, transposed, quads, rows);
+  } else {
+    dw_fwd_kernel<<<dim3((H * W + kT - 1) / kT, C, N), kT, 0, (cudaStream_t)stream>>>(x, w, y, C, H, W, scale, transposed);
+  }
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
 
 int csnet_train_dw_wgrad(const float* x, const float* dy, float* dw, int32_t N, int32_t C, int32_t H, int32_t W, float scale, void* stream) {
-  dw_wgrad_kernel<<<dim3(C, 9), kT, 0, (cudaStream_t)stream>>>(x, dy, dw, N, C, H, W, scale);
+  if (fast_enabled()) {
+    const int quads = (W + 3) / 4, rows = H < 8 ? H : 8, bands = (H + rows - 1) / rows;
+    const size_t tasks = (size_t)N * bands * quads;
+    int bx = (int)((tasks + tf::kT - 1) / tf::kT), cap = 4 * num_sms() / C;
+    cap = cap < 1 ? 1 : cap;
+    bx = bx > cap ? cap : bx;
+    float* part = nullptr;
+    if (int rc = partial_workspace((size_t)bx * C * 9, (cudaStream_t)stream, &part)) return rc;
+    tf::dw3_wgrad_kernel<<<dim3(bx, C), tf::kT, 0, (cudaStream_t)stream>>>(x, dy, part, N, C, H, W, quads, rows);
+    TR_CHECK(cudaGetLastError());
+    tf::reduce_partials_kernel<<<(C * 9 + tf::kT - 1) / tf::kT, tf::kT, 0, (cudaStream_t)stream>>>(part, bx, C * 9, scale, dw);
+  } else {
+    dw_wgrad_kernel<<<dim3(C, 9), kT, 0, (cudaStream_t)stream>>>(x, dy, dw, N, C, H, W, scale);
+  }
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
@@ -511,6 +628,31 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
   csnet::MixArgs A{};
   A.dst = dst; A.bias = nullptr; A.slope = nullptr; A.dtype = CSNET_F32; A.C = C; A.H = H; A.W = W; A.n_paths = n_paths;
   for (int p = 0; p < n_paths; ++p) A.p[p] = to_path(paths[p]);
+  if (fast_enabled()) {
+    // every conv path dense with one kernel size, every other path a bilinear resample-add: the register-tiled kernel
+    tf::ConvArgs F{};
+    F.dst = dst; F.N = N; F.C = C; F.H = H; F.W = W; F.ksize = 1;
+    bool ok = conv_tile_geometry(F);
+    int ks = 0;
+    for (int p = 0; p < n_paths && ok; ++p) {
+      const csnet::MixPath& P = A.p[p];
+      if (P.ksize == 0) {
+        if (F.n_rs >= tf::kMaxRs || P.up < 2 || P.pre_avg || P.pool != 1 || P.H * P.up != H || P.W * P.up != W) { ok = false; break; }
+        tf::RsPath& Q = F.rs[F.n_rs++];
+        Q.src = reinterpret_cast<const float*>(P.src); Q.Cs = P.C; Q.c0 = P.c0; Q.Hs = P.H; Q.Ws = P.W; Q.up = P.up; Q.cout0 = P.cout0; Q.cout = P.cout;
+      } else {
+        if (F.n_conv >= tf::kMaxConv || !dense_conv_path(P, H, W) || (ks && ks != P.ksize)) { ok = false; break; }
+        ks = P.ksize;
+        tf::ConvPath& Q = F.p[F.n_conv++];
+        Q.src = reinterpret_cast<const float*>(P.src); Q.w = P.w; Q.Cs = P.C; Q.c0 = P.c0; Q.cin = P.cin; Q.cout0 = P.cout0; Q.cout = P.cout; Q.dil = P.dil;
+      }
+    }
+    if (ok) {
+      F.ksize = ks ? ks : 1;
+      for (int i = 0; i < F.n_conv && ok; ++i) ok = conv_path_geometry(F.p[i], F);
+    }
+    if (ok) return launch_conv(F, (cudaStream_t)stream);
+  }
   tr_mix_fwd_kernel<<<dim3((H * W + kT - 1) / kT, (C + csnet::kMixCT - 1) / csnet::kMixCT, N), kT, 0, (cudaStream_t)stream>>>(A);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
@@ -519,6 +661,13 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
 int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dsrc, void* stream) {
   const csnet::MixPath P = to_path(*path);
   if (P.pre_avg > 2 || P.up > 1 && P.ksize > 0) { t_err = "csnet_train_mix_dgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
+  if (fast_enabled() && dense_conv_path(P, H, W)) {
+    tf::ConvArgs F{};
+    F.dst = dsrc; F.N = N; F.C = P.cin; F.H = H; F.W = W; F.ksize = P.ksize; F.transposed = 1; F.n_conv = 1;
+    tf::ConvPath& Q = F.p[0];
+    Q.src = ddst; Q.w = P.w; Q.Cs = C; Q.c0 = P.cout0; Q.cin = P.cout; Q.cout0 = 0; Q.cout = P.cin; Q.dil = P.dil;
+    if (conv_tile_geometry(F) && conv_path_geometry(Q, F)) return launch_conv(F, (cudaStream_t)stream);
+  }
   tr_mix_dgrad_kernel<<<dim3((P.H * P.W + kT - 1) / kT, P.cin, N), kT, 0, (cudaStream_t)stream>>>(ddst, C, H, W, P, dsrc);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
@@ -529,9 +678,77 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
   if (P.ksize == 0) { t_err = "csnet_train_mix_wgrad: resample paths have no weights"; return CSNET_E_INVALID; }
   if (P.pre_avg > 2 || P.up > 1) { t_err = "csnet_train_mix_wgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
   const int kk = P.ksize * P.ksize;
+  if (fast_enabled() && dense_conv_path(P, H, W) && P.dil == 1 && (P.ksize == 1 || P.ksize == 3)) {
+    tf::WgradArgs G{};
+    G.in = reinterpret_cast<const float*>(P.src); G.dd = ddst; G.N = N; G.Cs = P.C; G.c0 = P.c0; G.cin = P.cin; G.Cd = C; G.cout0 = P.cout0;
+    G.cout = P.cout; G.H = H; G.W = W;
+    G.cin4 = (P.cin + 3) / 4 * 4; G.cout4 = (P.cout + 3) / 4 * 4;
+    G.Wp = (W + 8 + 3) / 4 * 4; G.quads = (W + 3) / 4; G.vec = (W % 4) == 0;
+    const int extra = P.ksize == 3 ? 2 : 0;
+    int R = 0;                                               // the largest row band whose operands fit
+    for (int r = 1; r <= H && r <= 16; ++r)
+      if (((size_t)G.cin4 * (r + extra) + (size_t)G.cout4 * r) * G.Wp * sizeof(float) <= kFastSmem) R = r;
+    if (R >= 1) {
+      G.R = R;
+      const int bands = (H + R - 1) / R;
+      G.units = N * bands;
+      G.mt = G.cin4 / 4 * (P.ksize == 3 ? 3 : 1); G.nt = G.cout4 / 4; G.tiles = G.mt * G.nt;
+      int groups = 1;
+      if (G.tiles <= tf::kT) {
+        if (G.tiles >= 32) G.tpad = (G.tiles + 31) / 32 * 32;
+        else { G.tpad = 1; while (G.tpad < G.tiles) G.tpad *= 2; }
+        G.splits = tf::kT / G.tpad;
+      } else {
+        G.tpad = tf::kT; G.splits = 1; groups = (G.tiles + tf::kT - 1) / tf::kT;
+      }
+      const size_t stage = ((size_t)G.cin4 * (R + extra) + (size_t)G.cout4 * R) * G.Wp * sizeof(float),
+                   red = (size_t)G.splits * G.tpad * (P.ksize == 3 ? 48 : 16) * sizeof(float);
+      const size_t smem = stage > red ? stage : red;
+      int gx = 2 * num_sms() / groups;
+      gx = gx < 1 ? 1 : gx;
+      gx = gx > G.units ? G.units : gx;
+      const int nel = P.cin * kk * P.cout;
+      float* part = nullptr;
+      if (int rc = partial_workspace((size_t)gx * nel, (cudaStream_t)stream, &part)) return rc;
+      G.part = part;
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(tf::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+        cudaFuncSetAttribute(tf::conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+        attr = true;
+      }
+      if (P.ksize == 1) tf::conv_wgrad_kernel<1><<<dim3(gx, groups), tf::kT, smem, (cudaStream_t)stream>>>(G);
+      else tf::conv_wgrad_kernel<3><<<dim3(gx, groups), tf::kT, smem, (cudaStream_t)stream>>>(G);
+      TR_CHECK(cudaGetLastError());
+      tf::reduce_partials_kernel<<<(nel + tf::kT - 1) / tf::kT, tf::kT, 0, (cudaStream_t)stream>>>(part, gx, nel, 1.f, dw);
+      TR_CHECK(cudaGetLastError());
+      return CSNET_OK;
+    }
+  }
   TR_CHECK(cudaMemsetAsync(dw, 0, (size_t)P.cin * kk * P.cout * sizeof(float), (cudaStream_t)stream));
   const int split = N < 32 ? N : 32;
   tr_mix_wgrad_kernel<<<dim3(P.cin, kk * ((P.cout + 7) / 8), split), kT, 0, (cudaStream_t)stream>>>(ddst, N, C, H, W, P, dw);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_pool_fwd(const float* src, int32_t N, int32_t Cs, int32_t c0, int32_t cin, int32_t Hs, int32_t Ws, int32_t pre_avg, int32_t pool,
+                         float* dst, uint8_t* idx, void* stream) {
+  if (!src || !dst || pre_avg < 0 || pre_avg > 1 || pool < 1 || pool > 8 || (pool > 1 && !idx)) { t_err = "csnet_train_pool_fwd: bad arguments"; return CSNET_E_INVALID; }
+  const int f = (pre_avg ? 2 : 1) * pool;
+  const size_t total = (size_t)N * cin * (Hs / f) * (Ws / f);
+  if (total == 0) return CSNET_OK;
+  tf::pool_fwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(src, N, Cs, c0, cin, Hs, Ws, pre_avg, pool, dst, idx);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_train_pool_bwd(const float* dpool, const uint8_t* idx, int32_t N, int32_t cin, int32_t Hs, int32_t Ws, int32_t pre_avg, int32_t pool,
+                         float* dsrc, void* stream) {
+  if (!dpool || !dsrc || pre_avg < 0 || pre_avg > 1 || pool < 1 || pool > 8 || (pool > 1 && !idx)) { t_err = "csnet_train_pool_bwd: bad arguments"; return CSNET_E_INVALID; }
+  const size_t total = (size_t)N * cin * Hs * Ws;
+  if (total == 0) return CSNET_OK;
+  tf::pool_bwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }

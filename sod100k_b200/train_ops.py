@@ -41,6 +41,8 @@ def lib():
         l.csnet_train_mix_fwd.argtypes = [f32p, i32, i32, i32, i32, C.POINTER(TrainPath), i32, vp]
         l.csnet_train_mix_dgrad.argtypes = [f32p, i32, i32, i32, i32, C.POINTER(TrainPath), f32p, vp]
         l.csnet_train_mix_wgrad.argtypes = [f32p, i32, i32, i32, i32, C.POINTER(TrainPath), f32p, vp]
+        l.csnet_train_pool_fwd.argtypes = [f32p, i32, i32, i32, i32, i32, i32, i32, i32, f32p, vp, vp]
+        l.csnet_train_pool_bwd.argtypes = [f32p, vp, i32, i32, i32, i32, i32, i32, f32p, vp]
         l.csnet_train_bce.argtypes = [f32p, f32p, f32p, f32p, i64, f, vp]
         l.csnet_train_adam.argtypes = [vp, i32, f, f, f, f, i32, f, vp]
         _lib = l
@@ -49,7 +51,7 @@ def lib():
 
 # kernels launched through this module since import (bench.py reports the count of a timed region): kernels per entry point
 LAUNCHES = 0
-_KERNELS = {"csnet_train_bn_prelu_bwd": 2}
+_KERNELS = {"csnet_train_bn_prelu_bwd": 2, "csnet_train_mix_wgrad": 2, "csnet_train_dw_wgrad": 2}
 
 
 def _ck(rc, what):
@@ -94,41 +96,75 @@ def _cpath(ps: PathSpec, tensors: Sequence[torch.Tensor]) -> TrainPath:
 
 
 class MixFn(torch.autograd.Function):
-    """dst[N, C, H, W] = sum of paths (gOctaveConv.forward for one output branch, csnet.py:664-726)."""
+    """dst[N, C, H, W] = sum of paths (gOctaveConv.forward for one output branch, csnet.py:664-726).
+
+    The down-sampling of a path (2x2 average of a stride-2 conv, max-pool of a high -> low path) is materialised once by
+    csnet_train_pool_fwd, with the arg-max; the convolution kernels then see dense stride-1 paths only, the backward routes the
+    pooled gradient with csnet_train_pool_bwd, and the full-resolution source is not kept for this Function."""
 
     @staticmethod
     def forward(ctx, spec, *tensors):
         out_c, out_h, out_w, paths = spec
         tensors = [_f32(t) for t in tensors]
         n = tensors[paths[0].src].shape[0]
-        dst = torch.empty((n, out_c, out_h, out_w), dtype=torch.float32, device=tensors[0].device)
-        arr = (TrainPath * len(paths))(*[_cpath(p, tensors) for p in paths])
-        _ck(lib().csnet_train_mix_fwd(dst.data_ptr(), n, out_c, out_h, out_w, arr, len(paths), _stream(dst)), "csnet_train_mix_fwd")
-        ctx.spec = spec
-        ctx.save_for_backward(*tensors)
+        dev = tensors[0].device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        saved = list(tensors)
+        dense, pooled = [], {}
+        for k, p in enumerate(paths):
+            if p.ksize > 0 and (p.pre_avg or p.pool > 1):
+                s = tensors[p.src]
+                f = (2 if p.pre_avg else 1) * p.pool
+                xp = torch.empty((n, p.cin, s.shape[2] // f, s.shape[3] // f), dtype=torch.float32, device=dev)
+                idx = torch.empty(xp.shape, dtype=torch.uint8, device=dev) if p.pool > 1 else None
+                _ck(lib().csnet_train_pool_fwd(s.data_ptr(), n, s.shape[1], p.c0, p.cin, s.shape[2], s.shape[3], p.pre_avg, p.pool,
+                                               xp.data_ptr(), idx.data_ptr() if idx is not None else None, st), "csnet_train_pool_fwd")
+                saved += [xp, idx]
+                pooled[k] = (len(saved) - 2, len(saved) - 1, tuple(s.shape))
+                dense.append(PathSpec(len(saved) - 2, p.w, p.cin, p.cout, cout0=p.cout0, ksize=p.ksize, dil=p.dil, stride=p.stride, pad=p.pad))
+            else:
+                dense.append(p)
+        dst = torch.empty((n, out_c, out_h, out_w), dtype=torch.float32, device=dev)
+        arr = (TrainPath * len(dense))(*[_cpath(p, saved) for p in dense])
+        _ck(lib().csnet_train_mix_fwd(dst.data_ptr(), n, out_c, out_h, out_w, arr, len(dense), st), "csnet_train_mix_fwd")
+        # a source used only through its pooled copy is not kept
+        direct = {p.src for k, p in enumerate(paths) if k not in pooled}
+        shapes = [tuple(t.shape) for t in tensors]
+        for k, p in enumerate(paths):
+            if k in pooled and p.src not in direct:
+                saved[p.src] = None
+        ctx.spec, ctx.dense, ctx.pooled, ctx.shapes, ctx.n_in = spec, dense, pooled, shapes, len(tensors)
+        ctx.save_for_backward(*saved)
         return dst
 
     @staticmethod
     def backward(ctx, ddst):
         out_c, out_h, out_w, paths = ctx.spec
-        tensors = ctx.saved_tensors
+        saved = ctx.saved_tensors
         ddst = _f32(ddst)
         n = ddst.shape[0]
-        grads: List[Optional[torch.Tensor]] = [None] * len(tensors)
+        grads: List[Optional[torch.Tensor]] = [None] * ctx.n_in
         st = _stream(ddst)
-        for p in paths:
-            cp = _cpath(p, tensors)
-            src = tensors[p.src]
+        for k, (p, q) in enumerate(zip(paths, ctx.dense)):
+            cp = _cpath(q, saved)
+            shp = ctx.shapes[p.src]
             if ctx.needs_input_grad[1 + p.src]:
-                d = torch.empty((n, p.cin, src.shape[2], src.shape[3]), dtype=torch.float32, device=ddst.device)
+                xs = saved[q.src].shape
+                d = torch.empty((n, p.cin, xs[2], xs[3]), dtype=torch.float32, device=ddst.device)
                 _ck(lib().csnet_train_mix_dgrad(ddst.data_ptr(), n, out_c, out_h, out_w, C.byref(cp), d.data_ptr(), st), "csnet_train_mix_dgrad")
-                if p.c0 != 0 or p.cin != src.shape[1]:
-                    full = torch.zeros_like(src)
+                if k in ctx.pooled:
+                    idx = saved[ctx.pooled[k][1]]
+                    full = torch.empty((n, p.cin, shp[2], shp[3]), dtype=torch.float32, device=ddst.device)
+                    _ck(lib().csnet_train_pool_bwd(d.data_ptr(), idx.data_ptr() if idx is not None else None, n, p.cin, shp[2], shp[3],
+                                                   p.pre_avg, p.pool, full.data_ptr(), st), "csnet_train_pool_bwd")
+                    d = full
+                if p.c0 != 0 or p.cin != shp[1]:
+                    full = torch.zeros(shp, dtype=torch.float32, device=ddst.device)
                     full[:, p.c0:p.c0 + p.cin] = d
                     d = full
                 grads[p.src] = d if grads[p.src] is None else grads[p.src] + d
             if p.w is not None and ctx.needs_input_grad[1 + p.w]:
-                dw = torch.empty_like(tensors[p.w])
+                dw = torch.empty_like(saved[p.w])
                 _ck(lib().csnet_train_mix_wgrad(ddst.data_ptr(), n, out_c, out_h, out_w, C.byref(cp), dw.data_ptr(), st), "csnet_train_mix_wgrad")
                 grads[p.w] = dw if grads[p.w] is None else grads[p.w] + dw
         return (None, *grads)

@@ -201,3 +201,66 @@ def test_resample_dw_bn_primitives(up):
         assert (got.detach().cpu().double() - ref.detach()).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
     assert torch.allclose(gap.cpu().double(), r.detach().mean((2, 3)), atol=1e-5)
     assert torch.allclose(var.cpu().double(), z64.detach().var((0, 2, 3), unbiased=False), rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 20, 37, 8, 224, 1, 1), (5, 7, 5, 14, 14, 3, 1), (9, 7, 5, 14, 14, 1, 1), (2, 33, 70, 28, 28, 3, 1),
+                                   (2, 66, 70, 12, 28, 3, 1), (2, 6, 3, 40, 112, 3, 16), (3, 18, 13, 10, 56, 3, 2), (2, 3, 13, 16, 64, 3, 1)])
+def test_register_tiled_conv_kernels(shape):
+    """train_fast.cuh at the shapes that pick its different geometries: several output-channel groups, channel chunks, several
+    images per block (14 x 14 planes), rows that are not 16-byte multiples, > 256 weight-gradient tiles, dilation;
+    forward, data gradient and weight gradient against torch's float64 autograd."""
+    import torch.nn.functional as F
+    n, cin, cout, h, w, k, dil = shape
+    g = torch.Generator().manual_seed(11)
+    pad = dil * (k // 2)
+    x = torch.randn(n, cin, h, w, generator=g).cuda().requires_grad_(True)
+    wt = (0.3 * torch.randn(cout, cin, k, k, generator=g)).cuda().requires_grad_(True)
+    y = T.MixFn.apply((cout, h, w, [T.PathSpec(0, 1, cin, cout, ksize=k, dil=dil, pad=pad)]), x, T.pack_conv_weight(wt))
+    gy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(gy)
+    x64, w64 = x.detach().cpu().double().requires_grad_(True), wt.detach().cpu().double().requires_grad_(True)
+    r = F.conv2d(x64, w64, None, 1, pad, dil)
+    r.backward(gy.cpu().double())
+    for got, ref in ((y, r), (x.grad, x64.grad), (wt.grad, w64.grad)):
+        assert (got.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_register_tiled_mix_of_paths():
+    """One output branch of a gOctaveConv as the modules build it (csnet.py:664-726): a same-resolution path, a max-pooled
+    high -> low path on a channel slice, a low -> high path convolved at low resolution and added through the bilinear
+    resample, disjoint output slices of an MSBlock-like concat; all gradients against float64 autograd."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(12)
+    n, h, w = 3, 24, 40
+    xa = torch.randn(n, 9, h, w, generator=g).cuda().requires_grad_(True)              # same resolution
+    xb = torch.randn(n, 11, 2 * h, 2 * w, generator=g).cuda().requires_grad_(True)     # higher resolution: max-pool 2, channels [2, 9)
+    xc = torch.randn(n, 21, h // 2, w // 2, generator=g).cuda().requires_grad_(True)   # lower resolution: conv there, then x2 bilinear
+    wa = (0.3 * torch.randn(21, 9, 1, 1, generator=g)).cuda().requires_grad_(True)
+    wb = (0.3 * torch.randn(21, 7, 1, 1, generator=g)).cuda().requires_grad_(True)
+    y = T.MixFn.apply((21, h, w, [T.PathSpec(0, 1, 9, 21, ksize=1), T.PathSpec(2, 3, 7, 21, c0=2, pool=2, ksize=1),
+                                  T.PathSpec(4, None, 21, 21, ksize=0, up=2)]),
+                      xa, T.pack_conv_weight(wa), xb, T.pack_conv_weight(wb), xc)
+    gy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(gy)
+    a64, b64, c64, wa64, wb64 = (t.detach().cpu().double().requires_grad_(True) for t in (xa, xb, xc, wa, wb))
+    r = F.conv2d(a64, wa64) + F.conv2d(F.max_pool2d(b64[:, 2:9], 2, 2), wb64) + F.interpolate(c64, scale_factor=2, mode="bilinear")
+    r.backward(gy.cpu().double())
+    for got, ref in ((y, r), (xa.grad, a64.grad), (xb.grad, b64.grad), (xc.grad, c64.grad), (wa.grad, wa64.grad), (wb.grad, wb64.grad)):
+        assert (got.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    # disjoint output slices with different dilations (MSBlock, csnet.py:141-146)
+    x = torch.randn(n, 6, h, w, generator=g).cuda().requires_grad_(True)
+    ws = [(0.3 * torch.randn(c, 6, 3, 3, generator=g)).cuda().requires_grad_(True) for c in (2, 1, 3)]
+    paths, tensors, c0 = [], [x], 0
+    for wt_, d in zip(ws, (1, 2, 8)):
+        tensors.append(T.pack_conv_weight(wt_))
+        paths.append(T.PathSpec(0, len(tensors) - 1, 6, wt_.shape[0], cout0=c0, ksize=3, dil=d, pad=d))
+        c0 += wt_.shape[0]
+    y = T.MixFn.apply((c0, h, w, paths), *tensors)
+    gy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(gy)
+    x64 = x.detach().cpu().double().requires_grad_(True)
+    w64 = [t.detach().cpu().double().requires_grad_(True) for t in ws]
+    r = torch.cat([F.conv2d(x64, w64[i], None, 1, d, d) for i, d in enumerate((1, 2, 8))], 1)
+    r.backward(gy.cpu().double())
+    for got, ref in [(y, r), (x.grad, x64.grad)] + [(ws[i].grad, w64[i].grad) for i in range(3)]:
+        assert (got.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
