@@ -62,7 +62,8 @@ __device__ __forceinline__ void bilin(int H, int W, int up, int oy, int ox, int&
   w00 = (1.f - ly) * (1.f - lx); w01 = (1.f - ly) * lx; w10 = ly * (1.f - lx); w11 = ly * lx;
 }
 
-// KS: 1 or 3 with dil == 1 (vector shared-memory reads); 0: any ksize / dilation (scalar reads; the MSBlock's dilated paths)
+// KS: 3 with dil == 1 (vector shared-memory reads); 0: any ksize / dilation (scalar reads; the MSBlock's dilated paths).  1x1 mixes run
+// on conv1x1_kernel below.
 template <int KS>
 __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__ ConvArgs A) {
   extern __shared__ __align__(16) float smem[];
@@ -79,6 +80,8 @@ __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__
   const bool ok = live && n < A.N && y < H;
   const size_t plane = (size_t)H * W;
 
+  // one path whose channels fit one stage: the input tile is staged once and reused by every output-channel group
+  const bool once = A.n_conv == 1 && A.p[0].chunk >= A.p[0].cin;
   for (int cg = 0; cg * kCoT < A.C; ++cg) {
     const int cb = cg * kCoT;
     float acc[kCoT][4];
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__
         const int nc = P.cin - ci0 < P.chunk ? P.cin - ci0 : P.chunk;
         __syncthreads();
         // ---- stage the input tile: one warp per (channel, image, row), zero outside the image -------------------------------
-        for (int rr = warp; rr < nc * trows; rr += kT / 32) {
+        for (int rr = warp; rr < ((once && cg > 0) ? 0 : nc * trows); rr += kT / 32) {
           const int c = rr / trows, ir = rr - c * trows, i = ir / P.rows, row = ir - i * P.rows;
           const int gy = r0 + row - P.halo, gn = n0 + i;
           float* d = tile + (size_t)rr * P.Wp;
@@ -128,19 +131,7 @@ __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__
         for (int c = 0; c < nc; ++c) {
           const float* tc = tb + (size_t)c * trows * P.Wp;
           const float* wc = wsm + c * kk * kCoT;
-          if (KS == 1) {
-            const float4 v = *reinterpret_cast<const float4*>(tc);
-#pragma unroll
-            for (int q = 0; q < kCoT / 4; ++q) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wc + 4 * q);
-              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                acc[4 * q + j][0] = fmaf(v.x, wv[j], acc[4 * q + j][0]); acc[4 * q + j][1] = fmaf(v.y, wv[j], acc[4 * q + j][1]);
-                acc[4 * q + j][2] = fmaf(v.z, wv[j], acc[4 * q + j][2]); acc[4 * q + j][3] = fmaf(v.w, wv[j], acc[4 * q + j][3]);
-              }
-            }
-          } else if (KS == 3) {
+          if (KS == 3) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
               const float* tr_ = tc + (ky * P.Wp) - 4;                              // halo == 1: rows y-1..y+1 are tile rows tr..tr+2
@@ -220,6 +211,110 @@ __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__
   }
 }
 
+// ---- 1x1 convolution mix, direct form ------------------------------------------------------------------------------------------------
+// A 1x1 path needs each input element in exactly one thread (the one that owns its pixel, for every output channel), so the inputs go
+// global -> registers as 16-byte loads (re-reads for a second output-channel group hit L1) and only the weights live in shared
+// memory: no tile staging, no barriers after the prologue.  Also runs a mix that has only resample-add paths (n_conv == 0).
+struct C1Path {
+  const float* src;
+  const float* w;
+  int32_t Cs, c0, cin, cout0, cout, woff;          // woff: first weight row of this path in shared memory
+};
+
+struct C1Args {
+  float* dst;
+  int32_t N, C, H, W, quads, vec, transposed, n_conv, n_rs, Cpad, wrows;
+  C1Path p[kMaxConv];
+  RsPath rs[kMaxRs];
+};
+
+template <int CT>
+__device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int cb, int n, int y, int x0) {
+  const int H = A.H, W = A.W;
+  const size_t plane = (size_t)H * W;
+  float acc[CT][4];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+  for (int pi = 0; pi < A.n_conv; ++pi) {
+    const C1Path& P = A.p[pi];
+    if (P.cout0 >= cb + CT || P.cout0 + P.cout <= cb) continue;
+    const float* s = P.src + (((size_t)n * P.Cs + P.c0) * H + y) * W + x0;
+    const float* wr = wsm + (size_t)P.woff * A.Cpad + cb;
+#pragma unroll 4
+    for (int ci = 0; ci < P.cin; ++ci) {
+      float4 v;
+      if (A.vec) v = __ldg(reinterpret_cast<const float4*>(s + (size_t)ci * plane));
+      else {
+        const float* q = s + (size_t)ci * plane;
+        v.x = __ldg(q); v.y = x0 + 1 < W ? __ldg(q + 1) : 0.f; v.z = x0 + 2 < W ? __ldg(q + 2) : 0.f; v.w = x0 + 3 < W ? __ldg(q + 3) : 0.f;
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < CT / 4; ++q4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + (size_t)ci * A.Cpad + 4 * q4);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[4 * q4 + j][0] = fmaf(v.x, wv[j], acc[4 * q4 + j][0]); acc[4 * q4 + j][1] = fmaf(v.y, wv[j], acc[4 * q4 + j][1]);
+          acc[4 * q4 + j][2] = fmaf(v.z, wv[j], acc[4 * q4 + j][2]); acc[4 * q4 + j][3] = fmaf(v.w, wv[j], acc[4 * q4 + j][3]);
+        }
+      }
+    }
+  }
+  for (int ri = 0; ri < A.n_rs; ++ri) {
+    const RsPath& Q = A.rs[ri];
+    if (Q.cout0 >= cb + CT || Q.cout0 + Q.cout <= cb) continue;
+    const size_t lp = (size_t)Q.Hs * Q.Ws;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      if (x0 + px >= W) continue;
+      int o00, o01, o10, o11;
+      float w00, w01, w10, w11;
+      bilin(Q.Hs, Q.Ws, Q.up, y, x0 + px, o00, o01, o10, o11, w00, w01, w10, w11);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int co = cb + c - Q.cout0;
+        if (co < 0 || co >= Q.cout) continue;
+        const float* sp = Q.src + ((size_t)n * Q.Cs + Q.c0 + co) * lp;
+        acc[c][px] += w00 * __ldg(sp + o00) + w01 * __ldg(sp + o01) + w10 * __ldg(sp + o10) + w11 * __ldg(sp + o11);
+      }
+    }
+  }
+  float* o = A.dst + (((size_t)n * A.C + cb) * H + y) * W + x0;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    if (cb + c >= A.C) break;
+    if (A.vec) *reinterpret_cast<float4*>(o + (size_t)c * plane) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+    else {
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+        if (x0 + px < W) o[(size_t)c * plane + px] = acc[c][px];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ C1Args A) {
+  extern __shared__ __align__(16) float wsm[];                          // [wrows][Cpad]: every path's weights, zero outside its slice
+  for (int i = threadIdx.x; i < A.wrows * A.Cpad; i += kT) {
+    const int row = i / A.Cpad, col = i - row * A.Cpad;
+    float v = 0.f;
+    for (int pi = 0; pi < A.n_conv; ++pi) {
+      const C1Path& P = A.p[pi];
+      const int ci = row - P.woff, co = col - P.cout0;
+      if (ci >= 0 && ci < P.cin && co >= 0 && co < P.cout)
+        v = A.transposed ? __ldg(P.w + (size_t)co * P.cin + ci) : __ldg(P.w + (size_t)ci * P.cout + co);
+    }
+    wsm[i] = v;
+  }
+  __syncthreads();
+  const size_t task = (size_t)blockIdx.x * kT + threadIdx.x;
+  if (task >= (size_t)A.N * A.H * A.quads) return;
+  const int q = (int)(task % A.quads), y = (int)((task / A.quads) % A.H), n = (int)(task / ((size_t)A.quads * A.H));
+  for (int cb = 0; cb < A.C;) {
+    if (A.C - cb <= 8) { c1_group<8>(A, wsm, cb, n, y, 4 * q); cb += 8; }
+    else { c1_group<16>(A, wsm, cb, n, y, 4 * q); cb += 16; }
+  }
+}
+
 // ---- weight gradient ---------------------------------------------------------------------------------------------------------
 struct WgradArgs {
   const float* in;                  // [N][Cs][H][W], channels [c0, c0 + cin)
@@ -232,15 +327,17 @@ struct WgradArgs {
   int32_t tpad;                     // tiles per block (grid.y groups of tpad tiles): a multiple of 32, or a power of two < 32
   int32_t cin4, cout4;              // channel counts rounded up to 4 (zero rows)
   int32_t vec;
+  int32_t dil, hp;                  // dilation (KS == 0 form) and the column pad of the input tile (multiple of 4, >= dil)
 };
 
-// KS == 1: thread tile 4 ci x 4 co;  KS == 3: 4 ci x 4 co x the 3 taps of one kernel row
+// KS == 1: thread tile 4 ci x 4 co;  KS == 3: 4 ci x 4 co x the 3 taps of one kernel row (dil 1);  KS == 0: 3x3 with any dilation —
+// the input tile holds the three row bands r0 + (ky - 1) dil ... of a kernel row each, scalar shared-memory reads
 template <int KS>
 __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant__ WgradArgs A) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int KX = KS == 3 ? 3 : 1, KY = KS == 3 ? 3 : 1;
+  constexpr int KX = KS == 1 ? 1 : 3, KY = KS == 1 ? 1 : 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = A.H, W = A.W, R = A.R, Wp = A.Wp, rows_in = R + (KS == 3 ? 2 : 0);
+  const int H = A.H, W = A.W, R = A.R, Wp = A.Wp, rows_in = KS == 0 ? 3 * R : R + (KS == 3 ? 2 : 0), hp = A.hp;
   float* tin = smem;                                             // [cin4][rows_in][Wp]   (image column x at x + 4)
   float* tdd = smem + (size_t)A.cin4 * rows_in * Wp;             // [cout4][R][Wp]        (column x at x; Wp >= W rounded to 4)
   const int bands = (H + R - 1) / R;
@@ -259,20 +356,21 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
     const int n = u / bands, r0 = (u % bands) * R;
     __syncthreads();
     for (int rr = warp; rr < A.cin4 * rows_in; rr += kT / 32) {
-      const int c = rr / rows_in, row = rr - c * rows_in, gy = r0 + row - (KS == 3 ? 1 : 0);
-      const bool inside = c < A.cin && gy >= 0 && gy < H;
+      const int c = rr / rows_in, row = rr - c * rows_in;
+      const int gy = KS == 0 ? r0 + row % R + (row / R - 1) * A.dil : r0 + row - (KS == 3 ? 1 : 0);
+      const bool inside = c < A.cin && gy >= 0 && gy < H && (KS != 0 || r0 + row % R < H);
       const float* s = A.in + (((size_t)n * A.Cs + A.c0 + (inside ? c : 0)) * H + (inside ? gy : 0)) * W;
       float* d = tin + (size_t)rr * Wp;
       if (A.vec) {
         for (int v = lane; v * 4 < Wp; v += 32) {
-          const int xx = v * 4 - 4;
+          const int xx = v * 4 - hp;
           float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
           if (inside && xx >= 0 && xx < W) t = __ldg(reinterpret_cast<const float4*>(s + xx));
           *reinterpret_cast<float4*>(d + v * 4) = t;
         }
       } else {
         for (int v = lane; v < Wp; v += 32) {
-          const int xx = v - 4;
+          const int xx = v - hp;
           d[v] = (inside && xx >= 0 && xx < W) ? __ldg(s + xx) : 0.f;
         }
       }
@@ -303,8 +401,16 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
       for (int j = 0; j < 4; ++j) d4[j] = *reinterpret_cast<const float4*>(tdd + ((size_t)(co_t + j) * R + row) * Wp + x0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float* ip = tin + ((size_t)(ci_t + i) * rows_in + row + ky) * Wp + x0 + 4;
-        if (KS == 1) {
+        const float* ip = tin + ((size_t)(ci_t + i) * rows_in + (KS == 0 ? ky * R + row : row + ky)) * Wp + x0 + hp;
+        if (KS == 0) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float* tp = ip + (kx - 1) * A.dil;
+            const float i0 = tp[0], i1 = tp[1], i2 = tp[2], i3 = tp[3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[kx][i][j] += i0 * d4[j].x + i1 * d4[j].y + i2 * d4[j].z + i3 * d4[j].w;
+          }
+        } else if (KS == 1) {
           const float4 v = *reinterpret_cast<const float4*>(ip);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -337,7 +443,7 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
         for (int j = 0; j < 4; ++j) o[(a * 4 + i) * 4 + j] = acc[a][i][j];
   }
   __syncthreads();
-  const int kk = KS == 3 ? 9 : 1;
+  const int kk = KS == 1 ? 1 : 9;
   float* out = A.part + (size_t)blockIdx.x * A.cin * kk * A.cout;
   for (int e = tid; e < A.tpad * TA; e += kT) {
     const int lt = e / TA, t = blockIdx.y * A.tpad + lt, r = e - lt * TA, a = r / 16, i = (r / 4) % 4, j = r % 4;
@@ -407,6 +513,75 @@ __global__ void __launch_bounds__(kT) pool_bwd_kernel(const float* __restrict__ 
     if (hit) g = dpool[j] * (pre_avg ? 0.25f : 1.f);
   }
   dsrc[i] = g;
+}
+
+// four consecutive source pixels per thread (Ws % 4 == 0)
+__global__ void __launch_bounds__(kT) pool_bwd4_kernel(const float* __restrict__ dpool, const uint8_t* __restrict__ idx, int N, int cin, int Hs, int Ws,
+                                                       int pre_avg, int pool, float* __restrict__ dsrc) {
+  const int f = pre_avg ? 2 : 1, Hc = Hs / (f * pool), Wc = Ws / (f * pool), W4 = Ws >> 2;
+  const size_t t = (size_t)blockIdx.x * kT + threadIdx.x, total = (size_t)N * cin * Hs * W4;
+  if (t >= total) return;
+  const int x4 = (int)(t % W4), ys = (int)((t / W4) % Hs);
+  const size_t nc = t / ((size_t)W4 * Hs);
+  const int ya = ys / f, yc = ya / pool;
+  float g[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int xs = 4 * x4 + j, xa = xs / f, xc = xa / pool;
+    g[j] = 0.f;
+    if (yc < Hc && xc < Wc) {
+      const size_t k = (nc * Hc + yc) * Wc + xc;
+      const bool hit = pool == 1 || (int)__ldg(idx + k) == (ya - yc * pool) * pool + (xa - xc * pool);
+      if (hit) g[j] = __ldg(dpool + k) * (pre_avg ? 0.25f : 1.f);
+    }
+  }
+  *reinterpret_cast<float4*>(dsrc + (nc * Hs + ys) * Ws + 4 * x4) = make_float4(g[0], g[1], g[2], g[3]);
+}
+
+// adjoint of the bilinear x up resample (align_corners=False, source index clamped at 0): dsrc[n][c][ys][xs] for c < cin gathers the
+// <= (2 up)^2 destination pixels it fed; the separable weights are computed once per thread.  up <= 4.
+__global__ void __launch_bounds__(kT) resample_bwd_kernel(const float* __restrict__ ddst, int N, int C, int H, int W, int cout0, int cin, int Hs, int Ws,
+                                                          int up, float* __restrict__ dsrc) {
+  const size_t t = (size_t)blockIdx.x * kT + threadIdx.x, total = (size_t)N * cin * Hs * Ws;
+  if (t >= total) return;
+  const int xs = (int)(t % Ws), ys = (int)((t / Ws) % Hs), c = (int)((t / ((size_t)Ws * Hs)) % cin), n = (int)(t / ((size_t)Ws * Hs * cin));
+  const float inv = 1.f / (float)up;
+  float wy[12], wx[12];
+  const int yb = ys * up - up, xb = xs * up - up, span = 3 * up;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    wy[k] = 0.f; wx[k] = 0.f;
+    if (k < span) {
+      const int oy = yb + k, ox = xb + k;
+      if (oy >= 0 && oy < H) {
+        float sy = ((float)oy + 0.5f) * inv - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        const int y0 = (int)sy, y1 = y0 + (y0 < Hs - 1 ? 1 : 0);
+        const float ly = sy - (float)y0;
+        wy[k] = (y0 == ys ? 1.f - ly : 0.f) + (y1 == ys ? ly : 0.f);
+      }
+      if (ox >= 0 && ox < W) {
+        float sx = ((float)ox + 0.5f) * inv - 0.5f;
+        sx = sx < 0.f ? 0.f : sx;
+        const int x0 = (int)sx, x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+        const float lx = sx - (float)x0;
+        wx[k] = (x0 == xs ? 1.f - lx : 0.f) + (x1 == xs ? lx : 0.f);
+      }
+    }
+  }
+  const float* d = ddst + ((size_t)n * C + cout0 + c) * H * W;
+  float g = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 12; ++ky) {
+    if (ky >= span || wy[ky] == 0.f) continue;
+    const float* row = d + (size_t)(yb + ky) * W + xb;
+    float r = 0.f;
+#pragma unroll
+    for (int kx = 0; kx < 12; ++kx)
+      if (kx < span && wx[kx] != 0.f) r = fmaf(wx[kx], __ldg(row + kx), r);
+    g = fmaf(wy[ky], r, g);
+  }
+  dsrc[t] = g;
 }
 
 // ---- depthwise 3x3 ------------------------------------------------------------------------------------------------------------------

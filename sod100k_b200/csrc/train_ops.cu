@@ -521,7 +521,35 @@ static bool conv_path_geometry(tf::ConvPath& P, const tf::ConvArgs& A) {
   return true;
 }
 
+constexpr int kNotHandled = 1;                            // the shape does not fit the fast kernel: the caller runs the generic one
+// 1x1 mixes (and mixes of resample-add paths only): the direct kernel
+static int launch_conv1x1(const tf::ConvArgs& F, cudaStream_t st) {
+  tf::C1Args A{};
+  A.dst = F.dst; A.N = F.N; A.C = F.C; A.H = F.H; A.W = F.W; A.quads = (F.W + 3) / 4; A.vec = (F.W % 4) == 0; A.transposed = F.transposed;
+  A.n_conv = F.n_conv; A.n_rs = F.n_rs; A.Cpad = (F.C + 15) / 16 * 16;
+  int rows = 0;
+  for (int i = 0; i < F.n_conv; ++i) {
+    const tf::ConvPath& P = F.p[i];
+    tf::C1Path& Q = A.p[i];
+    Q.src = P.src; Q.w = P.w; Q.Cs = P.Cs; Q.c0 = P.c0; Q.cin = P.cin; Q.cout0 = P.cout0; Q.cout = P.cout; Q.woff = rows;
+    rows += P.cin;
+  }
+  for (int i = 0; i < F.n_rs; ++i) A.rs[i] = F.rs[i];
+  A.wrows = rows;
+  const size_t smem = (size_t)rows * A.Cpad * sizeof(float);
+  if (smem > 96 * 1024) return kNotHandled;                // (not a CSNet shape) -> the generic kernel
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tf::conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  const size_t tasks = (size_t)A.N * A.H * A.quads;
+  tf::conv1x1_kernel<<<(unsigned)((tasks + tf::kT - 1) / tf::kT), tf::kT, smem, st>>>(A);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
 static int launch_conv(tf::ConvArgs& A, cudaStream_t st) {
+  if (A.n_conv == 0 || A.ksize == 1) {
+    return launch_conv1x1(A, st);
+  }
   const int kk = A.ksize * A.ksize;
   size_t tile = 0, wsm = 0;
   bool dil1 = true;
@@ -538,14 +566,13 @@ static int launch_conv(tf::ConvArgs& A, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(tf::conv_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
-    cudaFuncSetAttribute(tf::conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
+    cudaFuncSetAttribute(tf::conv_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
     cudaFuncSetAttribute(tf::conv_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
     cudaFuncSetAttribute(tf::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
     cudaFuncSetAttribute(tf::conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
     attr = true;
   }
-  if (A.n_conv == 0 || (A.ksize == 1)) tf::conv_fwd_kernel<1><<<grid, tf::kT, smem, st>>>(A);
-  else if (A.ksize == 3 && dil1) tf::conv_fwd_kernel<3><<<grid, tf::kT, smem, st>>>(A);
+  if (A.ksize == 3 && dil1) tf::conv_fwd_kernel<3><<<grid, tf::kT, smem, st>>>(A);
   else tf::conv_fwd_kernel<0><<<grid, tf::kT, smem, st>>>(A);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
@@ -651,7 +678,10 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
       F.ksize = ks ? ks : 1;
       for (int i = 0; i < F.n_conv && ok; ++i) ok = conv_path_geometry(F.p[i], F);
     }
-    if (ok) return launch_conv(F, (cudaStream_t)stream);
+    if (ok) {
+      const int rc = launch_conv(F, (cudaStream_t)stream);
+      if (rc != kNotHandled) return rc;
+    }
   }
   tr_mix_fwd_kernel<<<dim3((H * W + kT - 1) / kT, (C + csnet::kMixCT - 1) / csnet::kMixCT, N), kT, 0, (cudaStream_t)stream>>>(A);
   TR_CHECK(cudaGetLastError());
@@ -661,12 +691,21 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
 int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dsrc, void* stream) {
   const csnet::MixPath P = to_path(*path);
   if (P.pre_avg > 2 || P.up > 1 && P.ksize > 0) { t_err = "csnet_train_mix_dgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
+  if (fast_enabled() && P.ksize == 0 && P.up >= 2 && P.up <= 4 && !P.pre_avg && P.pool == 1 && P.H * P.up == H && P.W * P.up == W) {
+    const size_t total = (size_t)N * P.cin * P.H * P.W;
+    tf::resample_bwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(ddst, N, C, H, W, P.cout0, P.cin, P.H, P.W, P.up, dsrc);
+    TR_CHECK(cudaGetLastError());
+    return CSNET_OK;
+  }
   if (fast_enabled() && dense_conv_path(P, H, W)) {
     tf::ConvArgs F{};
     F.dst = dsrc; F.N = N; F.C = P.cin; F.H = H; F.W = W; F.ksize = P.ksize; F.transposed = 1; F.n_conv = 1;
     tf::ConvPath& Q = F.p[0];
     Q.src = ddst; Q.w = P.w; Q.Cs = C; Q.c0 = P.cout0; Q.cin = P.cout; Q.cout0 = 0; Q.cout = P.cin; Q.dil = P.dil;
-    if (conv_tile_geometry(F) && conv_path_geometry(Q, F)) return launch_conv(F, (cudaStream_t)stream);
+    if (conv_tile_geometry(F) && conv_path_geometry(Q, F)) {
+      const int rc = launch_conv(F, (cudaStream_t)stream);
+      if (rc != kNotHandled) return rc;
+    }
   }
   tr_mix_dgrad_kernel<<<dim3((P.H * P.W + kT - 1) / kT, P.cin, N), kT, 0, (cudaStream_t)stream>>>(ddst, C, H, W, P, dsrc);
   TR_CHECK(cudaGetLastError());
@@ -678,21 +717,23 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
   if (P.ksize == 0) { t_err = "csnet_train_mix_wgrad: resample paths have no weights"; return CSNET_E_INVALID; }
   if (P.pre_avg > 2 || P.up > 1) { t_err = "csnet_train_mix_wgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
   const int kk = P.ksize * P.ksize;
-  if (fast_enabled() && dense_conv_path(P, H, W) && P.dil == 1 && (P.ksize == 1 || P.ksize == 3)) {
+  if (fast_enabled() && dense_conv_path(P, H, W) && (P.ksize == 3 || (P.ksize == 1 && P.dil == 1))) {
+    const int form = P.ksize == 1 ? 1 : (P.dil == 1 ? 3 : 0);    // template argument of conv_wgrad_kernel
     tf::WgradArgs G{};
     G.in = reinterpret_cast<const float*>(P.src); G.dd = ddst; G.N = N; G.Cs = P.C; G.c0 = P.c0; G.cin = P.cin; G.Cd = C; G.cout0 = P.cout0;
-    G.cout = P.cout; G.H = H; G.W = W;
+    G.cout = P.cout; G.H = H; G.W = W; G.dil = P.dil;
     G.cin4 = (P.cin + 3) / 4 * 4; G.cout4 = (P.cout + 3) / 4 * 4;
-    G.Wp = (W + 8 + 3) / 4 * 4; G.quads = (W + 3) / 4; G.vec = (W % 4) == 0;
-    const int extra = P.ksize == 3 ? 2 : 0;
+    G.hp = form == 0 ? (P.dil + 3) / 4 * 4 : 4;
+    G.Wp = (W + 2 * G.hp + 3) / 4 * 4; G.quads = (W + 3) / 4; G.vec = (W % 4) == 0;
+    auto rows_in = [&](int r) { return form == 0 ? 3 * r : r + (form == 3 ? 2 : 0); };
     int R = 0;                                               // the largest row band whose operands fit
     for (int r = 1; r <= H && r <= 16; ++r)
-      if (((size_t)G.cin4 * (r + extra) + (size_t)G.cout4 * r) * G.Wp * sizeof(float) <= kFastSmem) R = r;
+      if (((size_t)G.cin4 * rows_in(r) + (size_t)G.cout4 * r) * G.Wp * sizeof(float) <= kFastSmem) R = r;
     if (R >= 1) {
       G.R = R;
       const int bands = (H + R - 1) / R;
       G.units = N * bands;
-      G.mt = G.cin4 / 4 * (P.ksize == 3 ? 3 : 1); G.nt = G.cout4 / 4; G.tiles = G.mt * G.nt;
+      G.mt = G.cin4 / 4 * (form == 1 ? 1 : 3); G.nt = G.cout4 / 4; G.tiles = G.mt * G.nt;
       int groups = 1;
       if (G.tiles <= tf::kT) {
         if (G.tiles >= 32) G.tpad = (G.tiles + 31) / 32 * 32;
@@ -701,8 +742,8 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
       } else {
         G.tpad = tf::kT; G.splits = 1; groups = (G.tiles + tf::kT - 1) / tf::kT;
       }
-      const size_t stage = ((size_t)G.cin4 * (R + extra) + (size_t)G.cout4 * R) * G.Wp * sizeof(float),
-                   red = (size_t)G.splits * G.tpad * (P.ksize == 3 ? 48 : 16) * sizeof(float);
+      const size_t stage = ((size_t)G.cin4 * rows_in(R) + (size_t)G.cout4 * R) * G.Wp * sizeof(float),
+                   red = (size_t)G.splits * G.tpad * (form == 1 ? 16 : 48) * sizeof(float);
       const size_t smem = stage > red ? stage : red;
       int gx = 2 * num_sms() / groups;
       gx = gx < 1 ? 1 : gx;
@@ -713,12 +754,14 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
       G.part = part;
       static bool attr = false;
       if (!attr) {
+        cudaFuncSetAttribute(tf::conv_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
         cudaFuncSetAttribute(tf::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
         cudaFuncSetAttribute(tf::conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
         attr = true;
       }
-      if (P.ksize == 1) tf::conv_wgrad_kernel<1><<<dim3(gx, groups), tf::kT, smem, (cudaStream_t)stream>>>(G);
-      else tf::conv_wgrad_kernel<3><<<dim3(gx, groups), tf::kT, smem, (cudaStream_t)stream>>>(G);
+      if (form == 1) tf::conv_wgrad_kernel<1><<<dim3(gx, groups), tf::kT, smem, (cudaStream_t)stream>>>(G);
+      else if (form == 3) tf::conv_wgrad_kernel<3><<<dim3(gx, groups), tf::kT, smem, (cudaStream_t)stream>>>(G);
+      else tf::conv_wgrad_kernel<0><<<dim3(gx, groups), tf::kT, smem, (cudaStream_t)stream>>>(G);
       TR_CHECK(cudaGetLastError());
       tf::reduce_partials_kernel<<<(nel + tf::kT - 1) / tf::kT, tf::kT, 0, (cudaStream_t)stream>>>(part, gx, nel, 1.f, dw);
       TR_CHECK(cudaGetLastError());
@@ -748,7 +791,8 @@ int csnet_train_pool_bwd(const float* dpool, const uint8_t* idx, int32_t N, int3
   if (!dpool || !dsrc || pre_avg < 0 || pre_avg > 1 || pool < 1 || pool > 8 || (pool > 1 && !idx)) { t_err = "csnet_train_pool_bwd: bad arguments"; return CSNET_E_INVALID; }
   const size_t total = (size_t)N * cin * Hs * Ws;
   if (total == 0) return CSNET_OK;
-  tf::pool_bwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
+  if (Ws % 4 == 0) tf::pool_bwd4_kernel<<<(unsigned)((total / 4 + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
+  else tf::pool_bwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
