@@ -316,6 +316,12 @@ __global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ 
 }
 
 // ---- weight gradient ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 16 : 0;                                   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
 struct WgradArgs {
   const float* in;                  // [N][Cs][H][W], channels [c0, c0 + cin)
   const float* dd;                  // [N][Cd][H][W], channels [cout0, cout0 + cout)
@@ -338,9 +344,8 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
   constexpr int KX = KS == 1 ? 1 : 3, KY = KS == 1 ? 1 : 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = A.H, W = A.W, R = A.R, Wp = A.Wp, rows_in = KS == 0 ? 3 * R : R + (KS == 3 ? 2 : 0), hp = A.hp;
-  float* tin = smem;                                             // [cin4][rows_in][Wp]   (image column x at x + 4)
-  float* tdd = smem + (size_t)A.cin4 * rows_in * Wp;             // [cout4][R][Wp]        (column x at x; Wp >= W rounded to 4)
-  const int bands = (H + R - 1) / R;
+  const int buf_floats = (A.cin4 * rows_in + A.cout4 * R) * Wp;    // one stage: input tile [cin4][rows_in][Wp] (image column x at x + hp),
+  const int bands = (H + R - 1) / R;                               //            gradient tile [cout4][R][Wp] (column x at x)
   // task of this thread: (pixel split, tile); tiles beyond A.tiles idle.  Threads of one warp share the split when tiles >= 32.
   const int ltile = tid % A.tpad, split = tid / A.tpad, tile = blockIdx.y * A.tpad + ltile;
   const bool active = tile < A.tiles && split < A.splits;
@@ -352,9 +357,12 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
 
-  for (int u = blockIdx.x; u < A.units; u += gridDim.x) {
+  // stage unit u into `base` with 16-byte cp.async (zero-filled outside the image / the channel range); rows that are not 16-byte
+  // multiples take the synchronous scalar route
+  auto stage = [&](int u, float* base) {
     const int n = u / bands, r0 = (u % bands) * R;
-    __syncthreads();
+    float* tin = base;
+    float* tdd = base + (size_t)A.cin4 * rows_in * Wp;
     for (int rr = warp; rr < A.cin4 * rows_in; rr += kT / 32) {
       const int c = rr / rows_in, row = rr - c * rows_in;
       const int gy = KS == 0 ? r0 + row % R + (row / R - 1) * A.dil : r0 + row - (KS == 3 ? 1 : 0);
@@ -364,9 +372,8 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
       if (A.vec) {
         for (int v = lane; v * 4 < Wp; v += 32) {
           const int xx = v * 4 - hp;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (inside && xx >= 0 && xx < W) t = __ldg(reinterpret_cast<const float4*>(s + xx));
-          *reinterpret_cast<float4*>(d + v * 4) = t;
+          const bool ld = inside && xx >= 0 && xx < W;
+          cp_async16(d + v * 4, ld ? s + xx : A.in, ld);
         }
       } else {
         for (int v = lane; v < Wp; v += 32) {
@@ -383,16 +390,28 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
       if (A.vec) {
         for (int v = lane; v * 4 < Wp; v += 32) {
           const int xx = v * 4;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (inside && xx < W) t = __ldg(reinterpret_cast<const float4*>(s + xx));
-          *reinterpret_cast<float4*>(d + v * 4) = t;
+          const bool ld = inside && xx < W;
+          cp_async16(d + v * 4, ld ? s + xx : A.dd, ld);
         }
       } else {
         for (int v = lane; v < Wp; v += 32) d[v] = (inside && v < W) ? __ldg(s + v) : 0.f;
       }
     }
+  };
+
+  // two stages in flight: unit u+grid is copied while unit u is consumed
+  int cur = 0;
+  if ((int)blockIdx.x < A.units) stage(blockIdx.x, smem);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  for (int u = blockIdx.x; u < A.units; u += gridDim.x, cur ^= 1) {
+    const int un = u + gridDim.x;
+    if (un < A.units) stage(un, smem + (size_t)(cur ^ 1) * buf_floats);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     __syncthreads();
-    if (!active) continue;
+    const float* tin = smem + (size_t)cur * buf_floats;
+    const float* tdd = tin + (size_t)A.cin4 * rows_in * Wp;
+    if (active) {
     const int nq = R * A.quads;
     for (int q = split; q < nq; q += A.splits) {
       const int row = q / A.quads, x0 = 4 * (q - row * A.quads);
@@ -428,7 +447,10 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
         }
       }
     }
+    }
+    __syncthreads();                                               // everyone is done with this stage before the next copy lands in it
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   // ---- merge the pixel splits of the block in split order, write the block's partial ---------------------------------------------
   __syncthreads();
   float* red = smem;                                              // [splits][tpad][KX*16]
@@ -538,47 +560,51 @@ __global__ void __launch_bounds__(kT) pool_bwd4_kernel(const float* __restrict__
   *reinterpret_cast<float4*>(dsrc + (nc * Hs + ys) * Ws + 4 * x4) = make_float4(g[0], g[1], g[2], g[3]);
 }
 
-// adjoint of the bilinear x up resample (align_corners=False, source index clamped at 0): dsrc[n][c][ys][xs] for c < cin gathers the
-// <= (2 up)^2 destination pixels it fed; the separable weights are computed once per thread.  up <= 4.
+// adjoint of the bilinear x UP resample (align_corners=False, source index clamped at 0): dsrc[n][c][ys][xs] for c < cin gathers the
+// (2 UP)^2 destination pixels that can feed it — rows UP ys - UP/2 ... UP ys + 3 UP/2 - 1, which also covers the clamped borders —
+// with separable weights computed once per thread.
+template <int UP>
 __global__ void __launch_bounds__(kT) resample_bwd_kernel(const float* __restrict__ ddst, int N, int C, int H, int W, int cout0, int cin, int Hs, int Ws,
-                                                          int up, float* __restrict__ dsrc) {
+                                                          float* __restrict__ dsrc) {
   const size_t t = (size_t)blockIdx.x * kT + threadIdx.x, total = (size_t)N * cin * Hs * Ws;
   if (t >= total) return;
   const int xs = (int)(t % Ws), ys = (int)((t / Ws) % Hs), c = (int)((t / ((size_t)Ws * Hs)) % cin), n = (int)(t / ((size_t)Ws * Hs * cin));
-  const float inv = 1.f / (float)up;
-  float wy[12], wx[12];
-  const int yb = ys * up - up, xb = xs * up - up, span = 3 * up;
+  constexpr float inv = 1.f / (float)UP;
+  constexpr int K = 2 * UP;
+  float wy[K], wx[K];
+  const int yb = ys * UP - UP / 2, xb = xs * UP - UP / 2;
 #pragma unroll
-  for (int k = 0; k < 12; ++k) {
+  for (int k = 0; k < K; ++k) {
     wy[k] = 0.f; wx[k] = 0.f;
-    if (k < span) {
-      const int oy = yb + k, ox = xb + k;
-      if (oy >= 0 && oy < H) {
-        float sy = ((float)oy + 0.5f) * inv - 0.5f;
-        sy = sy < 0.f ? 0.f : sy;
-        const int y0 = (int)sy, y1 = y0 + (y0 < Hs - 1 ? 1 : 0);
-        const float ly = sy - (float)y0;
-        wy[k] = (y0 == ys ? 1.f - ly : 0.f) + (y1 == ys ? ly : 0.f);
-      }
-      if (ox >= 0 && ox < W) {
-        float sx = ((float)ox + 0.5f) * inv - 0.5f;
-        sx = sx < 0.f ? 0.f : sx;
-        const int x0 = (int)sx, x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
-        const float lx = sx - (float)x0;
-        wx[k] = (x0 == xs ? 1.f - lx : 0.f) + (x1 == xs ? lx : 0.f);
-      }
+    const int oy = yb + k, ox = xb + k;
+    if (oy >= 0 && oy < H) {
+      float sy = ((float)oy + 0.5f) * inv - 0.5f;
+      sy = sy < 0.f ? 0.f : sy;
+      const int y0 = (int)sy, y1 = y0 + (y0 < Hs - 1 ? 1 : 0);
+      const float ly = sy - (float)y0;
+      wy[k] = (y0 == ys ? 1.f - ly : 0.f) + (y1 == ys ? ly : 0.f);
+    }
+    if (ox >= 0 && ox < W) {
+      float sx = ((float)ox + 0.5f) * inv - 0.5f;
+      sx = sx < 0.f ? 0.f : sx;
+      const int x0 = (int)sx, x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+      const float lx = sx - (float)x0;
+      wx[k] = (x0 == xs ? 1.f - lx : 0.f) + (x1 == xs ? lx : 0.f);
     }
   }
   const float* d = ddst + ((size_t)n * C + cout0 + c) * H * W;
   float g = 0.f;
 #pragma unroll
-  for (int ky = 0; ky < 12; ++ky) {
-    if (ky >= span || wy[ky] == 0.f) continue;
-    const float* row = d + (size_t)(yb + ky) * W + xb;
+  for (int ky = 0; ky < K; ++ky) {
+    const int oy = yb + ky;
+    if (oy < 0 || oy >= H) continue;
+    const float* row = d + (size_t)oy * W;
     float r = 0.f;
 #pragma unroll
-    for (int kx = 0; kx < 12; ++kx)
-      if (kx < span && wx[kx] != 0.f) r = fmaf(wx[kx], __ldg(row + kx), r);
+    for (int kx = 0; kx < K; ++kx) {
+      const int ox = xb + kx;
+      if (ox >= 0 && ox < W) r = fmaf(wx[kx], __ldg(row + ox), r);
+    }
     g = fmaf(wy[ky], r, g);
   }
   dsrc[t] = g;

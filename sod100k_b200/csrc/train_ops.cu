@@ -691,9 +691,11 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
 int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dsrc, void* stream) {
   const csnet::MixPath P = to_path(*path);
   if (P.pre_avg > 2 || P.up > 1 && P.ksize > 0) { t_err = "csnet_train_mix_dgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
-  if (fast_enabled() && P.ksize == 0 && P.up >= 2 && P.up <= 4 && !P.pre_avg && P.pool == 1 && P.H * P.up == H && P.W * P.up == W) {
+  if (fast_enabled() && P.ksize == 0 && (P.up == 2 || P.up == 4) && !P.pre_avg && P.pool == 1 && P.H * P.up == H && P.W * P.up == W) {
     const size_t total = (size_t)N * P.cin * P.H * P.W;
-    tf::resample_bwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(ddst, N, C, H, W, P.cout0, P.cin, P.H, P.W, P.up, dsrc);
+    const unsigned blocks = (unsigned)((total + tf::kT - 1) / tf::kT);
+    if (P.up == 2) tf::resample_bwd_kernel<2><<<blocks, tf::kT, 0, (cudaStream_t)stream>>>(ddst, N, C, H, W, P.cout0, P.cin, P.H, P.W, dsrc);
+    else tf::resample_bwd_kernel<4><<<blocks, tf::kT, 0, (cudaStream_t)stream>>>(ddst, N, C, H, W, P.cout0, P.cin, P.H, P.W, dsrc);
     TR_CHECK(cudaGetLastError());
     return CSNET_OK;
   }
@@ -728,7 +730,7 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
     auto rows_in = [&](int r) { return form == 0 ? 3 * r : r + (form == 3 ? 2 : 0); };
     int R = 0;                                               // the largest row band whose operands fit
     for (int r = 1; r <= H && r <= 16; ++r)
-      if (((size_t)G.cin4 * rows_in(r) + (size_t)G.cout4 * r) * G.Wp * sizeof(float) <= kFastSmem) R = r;
+      if (((size_t)G.cin4 * rows_in(r) + (size_t)G.cout4 * r) * G.Wp * sizeof(float) <= kFastSmemMax / 2) R = r;    // two stages in flight
     if (R >= 1) {
       G.R = R;
       const int bands = (H + R - 1) / R;
@@ -744,7 +746,7 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
       }
       const size_t stage = ((size_t)G.cin4 * rows_in(R) + (size_t)G.cout4 * R) * G.Wp * sizeof(float),
                    red = (size_t)G.splits * G.tpad * (form == 1 ? 16 : 48) * sizeof(float);
-      const size_t smem = stage > red ? stage : red;
+      const size_t smem = 2 * stage > red ? 2 * stage : red;
       int gx = 2 * num_sms() / groups;
       gx = gx < 1 ? 1 : gx;
       gx = gx > G.units ? G.units : gx;
