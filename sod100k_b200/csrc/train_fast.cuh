@@ -228,13 +228,15 @@ struct C1Args {
   RsPath rs[kMaxRs];
 };
 
-template <int CT>
+template <int CT, int PX>
 __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int cb, int n, int y, int x0) {
   const int H = A.H, W = A.W;
   const size_t plane = (size_t)H * W;
-  float acc[CT][4];
+  float acc[CT][PX];
 #pragma unroll
-  for (int c = 0; c < CT; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+  for (int c = 0; c < CT; ++c)
+#pragma unroll
+    for (int px = 0; px < PX; ++px) acc[c][px] = 0.f;
   for (int pi = 0; pi < A.n_conv; ++pi) {
     const C1Path& P = A.p[pi];
     if (P.cout0 >= cb + CT || P.cout0 + P.cout <= cb) continue;
@@ -242,21 +244,23 @@ __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int 
     const float* wr = wsm + (size_t)P.woff * A.Cpad + cb;
 #pragma unroll 4
     for (int ci = 0; ci < P.cin; ++ci) {
-      float4 v;
-      if (A.vec) v = __ldg(reinterpret_cast<const float4*>(s + (size_t)ci * plane));
-      else {
-        const float* q = s + (size_t)ci * plane;
-        v.x = __ldg(q); v.y = x0 + 1 < W ? __ldg(q + 1) : 0.f; v.z = x0 + 2 < W ? __ldg(q + 2) : 0.f; v.w = x0 + 3 < W ? __ldg(q + 3) : 0.f;
+      float v[PX];
+      const float* q = s + (size_t)ci * plane;
+      if (A.vec) {
+        if (PX == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(q)); v[0] = t.x; v[1] = t.y; v[PX - 2] = t.z; v[PX - 1] = t.w; }
+        else { const float2 t = __ldg(reinterpret_cast<const float2*>(q)); v[0] = t.x; v[1] = t.y; }
+      } else {
+#pragma unroll
+        for (int px = 0; px < PX; ++px) v[px] = x0 + px < W ? __ldg(q + px) : 0.f;
       }
 #pragma unroll
       for (int q4 = 0; q4 < CT / 4; ++q4) {
         const float4 w4 = *reinterpret_cast<const float4*>(wr + (size_t)ci * A.Cpad + 4 * q4);
         const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[4 * q4 + j][0] = fmaf(v.x, wv[j], acc[4 * q4 + j][0]); acc[4 * q4 + j][1] = fmaf(v.y, wv[j], acc[4 * q4 + j][1]);
-          acc[4 * q4 + j][2] = fmaf(v.z, wv[j], acc[4 * q4 + j][2]); acc[4 * q4 + j][3] = fmaf(v.w, wv[j], acc[4 * q4 + j][3]);
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int px = 0; px < PX; ++px) acc[4 * q4 + j][px] = fmaf(v[px], wv[j], acc[4 * q4 + j][px]);
       }
     }
   }
@@ -265,7 +269,7 @@ __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int 
     if (Q.cout0 >= cb + CT || Q.cout0 + Q.cout <= cb) continue;
     const size_t lp = (size_t)Q.Hs * Q.Ws;
 #pragma unroll
-    for (int px = 0; px < 4; ++px) {
+    for (int px = 0; px < PX; ++px) {
       if (x0 + px >= W) continue;
       int o00, o01, o10, o11;
       float w00, w01, w10, w11;
@@ -283,15 +287,20 @@ __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int 
 #pragma unroll
   for (int c = 0; c < CT; ++c) {
     if (cb + c >= A.C) break;
-    if (A.vec) *reinterpret_cast<float4*>(o + (size_t)c * plane) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
-    else {
+    if (A.vec) {
+      if (PX == 4) *reinterpret_cast<float4*>(o + (size_t)c * plane) = make_float4(acc[c][0], acc[c][1], acc[c][PX - 2], acc[c][PX - 1]);
+      else *reinterpret_cast<float2*>(o + (size_t)c * plane) = make_float2(acc[c][0], acc[c][1]);
+    } else {
 #pragma unroll
-      for (int px = 0; px < 4; ++px)
+      for (int px = 0; px < PX; ++px)
         if (x0 + px < W) o[(size_t)c * plane + px] = acc[c][px];
     }
   }
 }
 
+// PX == 4: 4 pixels x (16 | 8) channels per pass (<= 16 output channels: one pass over the input);  PX == 2: 2 pixels x (32 | 16 | 8)
+// channels (17..32 output channels in ONE pass).  quads = ceil(W / PX), vec = W % PX == 0.
+template <int PX>
 __global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ C1Args A) {
   extern __shared__ __align__(16) float wsm[];                          // [wrows][Cpad]: every path's weights, zero outside its slice
   for (int i = threadIdx.x; i < A.wrows * A.Cpad; i += kT) {
@@ -310,8 +319,10 @@ __global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ 
   if (task >= (size_t)A.N * A.H * A.quads) return;
   const int q = (int)(task % A.quads), y = (int)((task / A.quads) % A.H), n = (int)(task / ((size_t)A.quads * A.H));
   for (int cb = 0; cb < A.C;) {
-    if (A.C - cb <= 8) { c1_group<8>(A, wsm, cb, n, y, 4 * q); cb += 8; }
-    else { c1_group<16>(A, wsm, cb, n, y, 4 * q); cb += 16; }
+    const int left = A.C - cb;
+    if (left <= 8) { c1_group<8, PX>(A, wsm, cb, n, y, PX * q); cb += 8; }
+    else if (PX == 4 || left <= 16) { c1_group<16, PX>(A, wsm, cb, n, y, PX * q); cb += 16; }
+    else { c1_group<32, PX>(A, wsm, cb, n, y, PX * q); cb += 32; }
   }
 }
 
@@ -334,6 +345,8 @@ struct WgradArgs {
   int32_t cin4, cout4;              // channel counts rounded up to 4 (zero rows)
   int32_t vec;
   int32_t dil, hp;                  // dilation (KS == 0 form) and the column pad of the input tile (multiple of 4, >= dil)
+  int32_t cpi, cpd;                 // channel pitches of the two tiles in floats, == 4 (mod 32): the 4-channel thread tiles are interleaved
+                                    // (tile t owns channels t, t + M, t + 2M, t + 3M), so the lanes of a warp read distinct bank groups
 };
 
 // KS == 1: thread tile 4 ci x 4 co;  KS == 3: 4 ci x 4 co x the 3 taps of one kernel row (dil 1);  KS == 0: 3x3 with any dilation —
@@ -344,13 +357,13 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
   constexpr int KX = KS == 1 ? 1 : 3, KY = KS == 1 ? 1 : 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = A.H, W = A.W, R = A.R, Wp = A.Wp, rows_in = KS == 0 ? 3 * R : R + (KS == 3 ? 2 : 0), hp = A.hp;
-  const int buf_floats = (A.cin4 * rows_in + A.cout4 * R) * Wp;    // one stage: input tile [cin4][rows_in][Wp] (image column x at x + hp),
+  const int buf_floats = A.cin4 * A.cpi + A.cout4 * A.cpd;         // one stage: input tile [cin4][rows_in][Wp] (image column x at x + hp),
   const int bands = (H + R - 1) / R;                               //            gradient tile [cout4][R][Wp] (column x at x)
   // task of this thread: (pixel split, tile); tiles beyond A.tiles idle.  Threads of one warp share the split when tiles >= 32.
   const int ltile = tid % A.tpad, split = tid / A.tpad, tile = blockIdx.y * A.tpad + ltile;
   const bool active = tile < A.tiles && split < A.splits;
   const int tm = active ? tile / A.nt : 0, tn = active ? tile % A.nt : 0;
-  const int ci_t = (tm / KY) * 4, ky = tm % KY, co_t = tn * 4;
+  const int ci_t = tm / KY, ky = tm % KY, co_t = tn, Mi = A.cin4 / 4, Mo = A.nt;     // channels ci_t + i * Mi, co_t + j * Mo
   float acc[KX][4][4];
 #pragma unroll
   for (int a = 0; a < KX; ++a)
@@ -362,13 +375,13 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
   auto stage = [&](int u, float* base) {
     const int n = u / bands, r0 = (u % bands) * R;
     float* tin = base;
-    float* tdd = base + (size_t)A.cin4 * rows_in * Wp;
+    float* tdd = base + (size_t)A.cin4 * A.cpi;
     for (int rr = warp; rr < A.cin4 * rows_in; rr += kT / 32) {
       const int c = rr / rows_in, row = rr - c * rows_in;
       const int gy = KS == 0 ? r0 + row % R + (row / R - 1) * A.dil : r0 + row - (KS == 3 ? 1 : 0);
       const bool inside = c < A.cin && gy >= 0 && gy < H && (KS != 0 || r0 + row % R < H);
       const float* s = A.in + (((size_t)n * A.Cs + A.c0 + (inside ? c : 0)) * H + (inside ? gy : 0)) * W;
-      float* d = tin + (size_t)rr * Wp;
+      float* d = tin + (size_t)c * A.cpi + (size_t)row * Wp;
       if (A.vec) {
         for (int v = lane; v * 4 < Wp; v += 32) {
           const int xx = v * 4 - hp;
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
       const int c = rr / R, row = rr - c * R, gy = r0 + row;
       const bool inside = c < A.cout && gy < H;
       const float* s = A.dd + (((size_t)n * A.Cd + A.cout0 + (inside ? c : 0)) * H + (inside ? gy : 0)) * W;
-      float* d = tdd + (size_t)rr * Wp;
+      float* d = tdd + (size_t)c * A.cpd + (size_t)row * Wp;
       if (A.vec) {
         for (int v = lane; v * 4 < Wp; v += 32) {
           const int xx = v * 4;
@@ -410,17 +423,17 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
     asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     __syncthreads();
     const float* tin = smem + (size_t)cur * buf_floats;
-    const float* tdd = tin + (size_t)A.cin4 * rows_in * Wp;
+    const float* tdd = tin + (size_t)A.cin4 * A.cpi;
     if (active) {
     const int nq = R * A.quads;
     for (int q = split; q < nq; q += A.splits) {
       const int row = q / A.quads, x0 = 4 * (q - row * A.quads);
       float4 d4[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) d4[j] = *reinterpret_cast<const float4*>(tdd + ((size_t)(co_t + j) * R + row) * Wp + x0);
+      for (int j = 0; j < 4; ++j) d4[j] = *reinterpret_cast<const float4*>(tdd + (size_t)(co_t + j * Mo) * A.cpd + (size_t)row * Wp + x0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float* ip = tin + ((size_t)(ci_t + i) * rows_in + (KS == 0 ? ky * R + row : row + ky)) * Wp + x0 + hp;
+        const float* ip = tin + (size_t)(ci_t + i * Mi) * A.cpi + (size_t)(KS == 0 ? ky * R + row : row + ky) * Wp + x0 + hp;
         if (KS == 0) {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
@@ -470,7 +483,7 @@ __global__ void __launch_bounds__(kT, 2) conv_wgrad_kernel(const __grid_constant
   for (int e = tid; e < A.tpad * TA; e += kT) {
     const int lt = e / TA, t = blockIdx.y * A.tpad + lt, r = e - lt * TA, a = r / 16, i = (r / 4) % 4, j = r % 4;
     if (t >= A.tiles) continue;
-    const int tm2 = t / A.nt, tn2 = t % A.nt, ci = (tm2 / KY) * 4 + i, ky2 = tm2 % KY, co = tn2 * 4 + j;
+    const int tm2 = t / A.nt, tn2 = t % A.nt, ci = tm2 / KY + i * (A.cin4 / 4), ky2 = tm2 % KY, co = tn2 + j * A.nt;
     if (ci >= A.cin || co >= A.cout) continue;
     float s = 0.f;
     for (int sp = 0; sp < A.splits; ++sp) s += red[((size_t)sp * A.tpad + lt) * TA + r];

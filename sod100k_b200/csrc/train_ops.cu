@@ -525,8 +525,11 @@ constexpr int kNotHandled = 1;                            // the shape does not 
 // 1x1 mixes (and mixes of resample-add paths only): the direct kernel
 static int launch_conv1x1(const tf::ConvArgs& F, cudaStream_t st) {
   tf::C1Args A{};
-  A.dst = F.dst; A.N = F.N; A.C = F.C; A.H = F.H; A.W = F.W; A.quads = (F.W + 3) / 4; A.vec = (F.W % 4) == 0; A.transposed = F.transposed;
-  A.n_conv = F.n_conv; A.n_rs = F.n_rs; A.Cpad = (F.C + 15) / 16 * 16;
+  // 4 px x 16 channels per pass; rows that are only 8-byte multiples (14 wide) take 2 px x 32 channels with 8-byte loads.  (2 px x 32
+  // measured SLOWER on the wide planes — 18 -> 18 @224^2: 1.12 ms vs 0.79 ms — twice the load instructions for the same bytes.)
+  const int px = (F.W % 4 != 0 && F.W % 2 == 0) ? 2 : 4;
+  A.dst = F.dst; A.N = F.N; A.C = F.C; A.H = F.H; A.W = F.W; A.quads = (F.W + px - 1) / px; A.vec = (F.W % px) == 0; A.transposed = F.transposed;
+  A.n_conv = F.n_conv; A.n_rs = F.n_rs; A.Cpad = (F.C + 31) / 32 * 32;
   int rows = 0;
   for (int i = 0; i < F.n_conv; ++i) {
     const tf::ConvPath& P = F.p[i];
@@ -539,9 +542,14 @@ static int launch_conv1x1(const tf::ConvArgs& F, cudaStream_t st) {
   const size_t smem = (size_t)rows * A.Cpad * sizeof(float);
   if (smem > 96 * 1024) return kNotHandled;                // (not a CSNet shape) -> the generic kernel
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tf::conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(tf::conv1x1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(tf::conv1x1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
   const size_t tasks = (size_t)A.N * A.H * A.quads;
-  tf::conv1x1_kernel<<<(unsigned)((tasks + tf::kT - 1) / tf::kT), tf::kT, smem, st>>>(A);
+  if (px == 2) tf::conv1x1_kernel<2><<<(unsigned)((tasks + tf::kT - 1) / tf::kT), tf::kT, smem, st>>>(A);
+  else tf::conv1x1_kernel<4><<<(unsigned)((tasks + tf::kT - 1) / tf::kT), tf::kT, smem, st>>>(A);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
@@ -728,11 +736,14 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
     G.hp = form == 0 ? (P.dil + 3) / 4 * 4 : 4;
     G.Wp = (W + 2 * G.hp + 3) / 4 * 4; G.quads = (W + 3) / 4; G.vec = (W % 4) == 0;
     auto rows_in = [&](int r) { return form == 0 ? 3 * r : r + (form == 3 ? 2 : 0); };
+    auto pitch = [](int floats) { return floats + ((4 - floats % 32) + 32) % 32; };          // == 4 (mod 32); floats is a multiple of 4
+    auto stage_bytes = [&](int r) { return ((size_t)G.cin4 * pitch(rows_in(r) * G.Wp) + (size_t)G.cout4 * pitch(r * G.Wp)) * sizeof(float); };
     int R = 0;                                               // the largest row band whose operands fit
     for (int r = 1; r <= H && r <= 16; ++r)
-      if (((size_t)G.cin4 * rows_in(r) + (size_t)G.cout4 * r) * G.Wp * sizeof(float) <= kFastSmemMax / 2) R = r;    // two stages in flight
+      if (stage_bytes(r) <= kFastSmemMax / 2) R = r;        // two stages in flight
     if (R >= 1) {
       G.R = R;
+      G.cpi = pitch(rows_in(R) * G.Wp); G.cpd = pitch(R * G.Wp);
       const int bands = (H + R - 1) / R;
       G.units = N * bands;
       G.mt = G.cin4 / 4 * (form == 1 ? 1 : 3); G.nt = G.cout4 / 4; G.tiles = G.mt * G.nt;
@@ -744,7 +755,7 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
       } else {
         G.tpad = tf::kT; G.splits = 1; groups = (G.tiles + tf::kT - 1) / tf::kT;
       }
-      const size_t stage = ((size_t)G.cin4 * rows_in(R) + (size_t)G.cout4 * R) * G.Wp * sizeof(float),
+      const size_t stage = stage_bytes(R),
                    red = (size_t)G.splits * G.tpad * (form == 1 ? 16 : 48) * sizeof(float);
       const size_t smem = 2 * stage > red ? 2 * stage : red;
       int gx = 2 * num_sms() / groups;
