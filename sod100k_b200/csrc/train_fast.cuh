@@ -532,6 +532,30 @@ __global__ void __launch_bounds__(kT) pool_fwd_kernel(const float* __restrict__ 
   if (idx) idx[i] = (uint8_t)bi;
 }
 
+// pool == 2 without the average, Ws % 4 == 0: two outputs per thread from two 16-byte loads
+__global__ void __launch_bounds__(kT) pool2_fwd_kernel(const float* __restrict__ src, int N, int Cs, int c0, int cin, int Hs, int Ws,
+                                                       float* __restrict__ dst, uint8_t* __restrict__ idx) {
+  const int Hc = Hs >> 1, Wc = Ws >> 1, W2 = Wc >> 1;
+  const unsigned t = blockIdx.x * kT + threadIdx.x, total = (unsigned)N * cin * Hc * W2;        // < 2^32: checked by the host
+  if (t >= total) return;
+  const int x2 = (int)(t % (unsigned)W2), yc = (int)((t / (unsigned)W2) % (unsigned)Hc);
+  const unsigned nc = t / ((unsigned)W2 * (unsigned)Hc);
+  const int c = (int)(nc % (unsigned)cin), n = (int)(nc / (unsigned)cin);
+  const float* s = src + (((size_t)n * Cs + c0 + c) * Hs + 2 * yc) * Ws + 4 * x2;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s + Ws));
+  float m0 = a.x; int i0 = 0;
+  if (a.y > m0) { m0 = a.y; i0 = 1; }
+  if (b.x > m0) { m0 = b.x; i0 = 2; }
+  if (b.y > m0) { m0 = b.y; i0 = 3; }
+  float m1 = a.z; int i1 = 0;
+  if (a.w > m1) { m1 = a.w; i1 = 1; }
+  if (b.z > m1) { m1 = b.z; i1 = 2; }
+  if (b.w > m1) { m1 = b.w; i1 = 3; }
+  const size_t o = ((size_t)nc * Hc + yc) * Wc + 2 * x2;
+  *reinterpret_cast<float2*>(dst + o) = make_float2(m0, m1);
+  *reinterpret_cast<uchar2*>(idx + o) = make_uchar2((unsigned char)i0, (unsigned char)i1);
+}
+
 // dsrc[n][ci][ys][xs] (exactly cin channels) from the gradient of the pooled tensor
 __global__ void __launch_bounds__(kT) pool_bwd_kernel(const float* __restrict__ dpool, const uint8_t* __restrict__ idx, int N, int cin, int Hs, int Ws,
                                                       int pre_avg, int pool, float* __restrict__ dsrc) {
@@ -554,10 +578,10 @@ __global__ void __launch_bounds__(kT) pool_bwd_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(kT) pool_bwd4_kernel(const float* __restrict__ dpool, const uint8_t* __restrict__ idx, int N, int cin, int Hs, int Ws,
                                                        int pre_avg, int pool, float* __restrict__ dsrc) {
   const int f = pre_avg ? 2 : 1, Hc = Hs / (f * pool), Wc = Ws / (f * pool), W4 = Ws >> 2;
-  const size_t t = (size_t)blockIdx.x * kT + threadIdx.x, total = (size_t)N * cin * Hs * W4;
+  const unsigned t = blockIdx.x * kT + threadIdx.x, total = (unsigned)N * cin * Hs * W4;     // < 2^32: checked by the host
   if (t >= total) return;
-  const int x4 = (int)(t % W4), ys = (int)((t / W4) % Hs);
-  const size_t nc = t / ((size_t)W4 * Hs);
+  const int x4 = (int)(t % (unsigned)W4), ys = (int)((t / (unsigned)W4) % (unsigned)Hs);
+  const size_t nc = t / ((unsigned)W4 * (unsigned)Hs);
   const int ya = ys / f, yc = ya / pool;
   float g[4];
 #pragma unroll
@@ -579,9 +603,11 @@ __global__ void __launch_bounds__(kT) pool_bwd4_kernel(const float* __restrict__
 template <int UP>
 __global__ void __launch_bounds__(kT) resample_bwd_kernel(const float* __restrict__ ddst, int N, int C, int H, int W, int cout0, int cin, int Hs, int Ws,
                                                           float* __restrict__ dsrc) {
-  const size_t t = (size_t)blockIdx.x * kT + threadIdx.x, total = (size_t)N * cin * Hs * Ws;
+  const unsigned t = blockIdx.x * kT + threadIdx.x, total = (unsigned)N * cin * Hs * Ws;         // < 2^32: checked by the host
   if (t >= total) return;
-  const int xs = (int)(t % Ws), ys = (int)((t / Ws) % Hs), c = (int)((t / ((size_t)Ws * Hs)) % cin), n = (int)(t / ((size_t)Ws * Hs * cin));
+  const int xs = (int)(t % (unsigned)Ws), ys = (int)((t / (unsigned)Ws) % (unsigned)Hs);
+  const unsigned ncq = t / ((unsigned)Ws * (unsigned)Hs);
+  const int c = (int)(ncq % (unsigned)cin), n = (int)(ncq / (unsigned)cin);
   constexpr float inv = 1.f / (float)UP;
   constexpr int K = 2 * UP;
   float wy[K], wx[K];

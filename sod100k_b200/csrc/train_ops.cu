@@ -61,9 +61,54 @@ __device__ __forceinline__ bool last_block_of(unsigned* counter, unsigned parts)
   return is_last;
 }
 
+// stats: per channel mean and biased variance in ONE pass over z: sums of (z - K) and (z - K)^2 with the shift K = the mean of 32 fixed
+// samples spread over the channel's images and planes (every block of the channel computes the same K), so (mean - K)^2 ~ var / 32
+// and the subtraction S2 - S1^2 / M loses no more than a few ulps.  (A single sample is not enough: the corner pixel of a zero-padded
+// conv sits many sigma from the mean and cost 6e-3 on one weight gradient.)  Block partials in fp32 over <= a few hundred elements per
+// thread, merged in part order in double by the last block.
+__global__ void __launch_bounds__(kT) bn_stats_kernel(const float* __restrict__ z, int N, int C, int HW, int S, float* mean,
+                                                      float* var, float* ws, unsigned* cnt) {
+  const int c = blockIdx.x, part = blockIdx.y, parts = gridDim.y, n = part / S, sg = part - n * S;
+  const int seg = (HW + S - 1) / S, i0 = sg * seg, i1 = (i0 + seg) < HW ? (i0 + seg) : HW;
+  const float* p = z + ((size_t)n * C + c) * HW;
+  __shared__ float Ks;
+  if (threadIdx.x < 32) {
+    const int l = threadIdx.x, img = l % N, off = (int)(((long long)l * HW) / 32 + 17) % HW;
+    const float v = warp_sum(__ldg(z + ((size_t)img * C + c) * HW + off)) * (1.f / 32.f);
+    if (l == 0) Ks = v;
+  }
+  __syncthreads();
+  const float K = Ks;
+  float s = 0.f, q = 0.f, d1 = 0.f;
+  if (((HW | i0) & 3) == 0 && ((i1 - i0) & 3) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(p + i0);
+    for (int i = threadIdx.x; i < (i1 - i0) / 4; i += kT) {
+      const float4 v = __ldg(p4 + i);
+      const float a = v.x - K, b = v.y - K, cc = v.z - K, d = v.w - K;
+      s += (a + b) + (cc + d);
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  } else {
+    for (int i = i0 + threadIdx.x; i < i1; i += kT) { const float d = p[i] - K; s += d; q += d * d; }
+  }
+  block_sum3(s, q, d1);
+  float* w = ws + ((size_t)c * parts + part) * 3;
+  if (threadIdx.x == 0) { w[0] = s; w[1] = q; w[2] = (float)(i1 > i0 ? i1 - i0 : 0); }
+  if (!last_block_of(cnt + c, parts)) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* v = ws + (size_t)c * parts * 3;
+    double S1 = 0.0, S2 = 0.0, M = 0.0;
+    for (int k = 0; k < parts; ++k) { S1 += (double)v[3 * k]; S2 += (double)v[3 * k + 1]; M += (double)v[3 * k + 2]; }
+    const double m1 = S1 / M, vv = (S2 - S1 * m1) / M;
+    mean[c] = (float)((double)K + m1); var[c] = (float)(vv > 0.0 ? vv : 0.0);
+    cnt[c] = 0u;                                            // ready for the next call on this stream
+  }
+}
+
 // stats: per channel mean and biased variance.  Each part is reduced two-pass (its own mean first), parts are merged with
 // Chan's formula: M2 = sum M2_p + sum m_p (mean_p - mean)^2.
-__global__ void __launch_bounds__(kT) bn_stats_kernel(const float* __restrict__ z, int N, int C, int HW, int S, float* mean,
+__global__ void __launch_bounds__(kT) bn_stats2_kernel(const float* __restrict__ z, int N, int C, int HW, int S, float* mean,
                                                       float* var, float* ws, unsigned* cnt) {
   const int c = blockIdx.x, part = blockIdx.y, parts = gridDim.y, n = part / S, sg = part - n * S;
   const int seg = (HW + S - 1) / S, i0 = sg * seg, i1 = (i0 + seg) < HW ? (i0 + seg) : HW;
@@ -601,7 +646,9 @@ static int reduce_segments(int N, int C, int HW) {
 int csnet_train_bn_stats(const float* z, int32_t N, int32_t C, int32_t HW, float* mean, float* var, void* stream) {
   const int S = reduce_segments(N, C, HW);
   if (int rc = reduce_workspace(C, N * S, (cudaStream_t)stream)) return rc;
-  bn_stats_kernel<<<dim3(C, N * S), kT, 0, (cudaStream_t)stream>>>(z, N, C, HW, S, mean, var, g_red_ws, g_red_cnt);
+  static const bool two_pass = [] { const char* e = getenv("CSNET_BN_TWO_PASS"); return e && e[0] == '1'; }();
+  if (two_pass) bn_stats2_kernel<<<dim3(C, N * S), kT, 0, (cudaStream_t)stream>>>(z, N, C, HW, S, mean, var, g_red_ws, g_red_cnt);
+  else bn_stats_kernel<<<dim3(C, N * S), kT, 0, (cudaStream_t)stream>>>(z, N, C, HW, S, mean, var, g_red_ws, g_red_cnt);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
@@ -699,7 +746,7 @@ int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, 
 int csnet_train_mix_dgrad(const float* ddst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* path, float* dsrc, void* stream) {
   const csnet::MixPath P = to_path(*path);
   if (P.pre_avg > 2 || P.up > 1 && P.ksize > 0) { t_err = "csnet_train_mix_dgrad: down-sample factors > 2 / input-side up-sampling are inference-only"; return CSNET_E_UNSUPPORTED; }
-  if (fast_enabled() && P.ksize == 0 && (P.up == 2 || P.up == 4) && !P.pre_avg && P.pool == 1 && P.H * P.up == H && P.W * P.up == W) {
+  if (fast_enabled() && (size_t)N * P.cin * P.H * P.W < (1ull << 32) && P.ksize == 0 && (P.up == 2 || P.up == 4) && !P.pre_avg && P.pool == 1 && P.H * P.up == H && P.W * P.up == W) {
     const size_t total = (size_t)N * P.cin * P.H * P.W;
     const unsigned blocks = (unsigned)((total + tf::kT - 1) / tf::kT);
     if (P.up == 2) tf::resample_bwd_kernel<2><<<blocks, tf::kT, 0, (cudaStream_t)stream>>>(ddst, N, C, H, W, P.cout0, P.cin, P.H, P.W, dsrc);
@@ -794,7 +841,11 @@ int csnet_train_pool_fwd(const float* src, int32_t N, int32_t Cs, int32_t c0, in
   const int f = (pre_avg ? 2 : 1) * pool;
   const size_t total = (size_t)N * cin * (Hs / f) * (Ws / f);
   if (total == 0) return CSNET_OK;
-  tf::pool_fwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(src, N, Cs, c0, cin, Hs, Ws, pre_avg, pool, dst, idx);
+  static const bool pool2 = [] { const char* e = getenv("CSNET_POOL2"); return !(e && e[0] == '0'); }();
+  if (pool2 && !pre_avg && pool == 2 && Ws % 4 == 0 && Hs % 2 == 0 && total < (1ull << 31))
+    tf::pool2_fwd_kernel<<<(unsigned)((total / 2 + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(src, N, Cs, c0, cin, Hs, Ws, dst, idx);
+  else
+    tf::pool_fwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(src, N, Cs, c0, cin, Hs, Ws, pre_avg, pool, dst, idx);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
@@ -804,7 +855,7 @@ int csnet_train_pool_bwd(const float* dpool, const uint8_t* idx, int32_t N, int3
   if (!dpool || !dsrc || pre_avg < 0 || pre_avg > 1 || pool < 1 || pool > 8 || (pool > 1 && !idx)) { t_err = "csnet_train_pool_bwd: bad arguments"; return CSNET_E_INVALID; }
   const size_t total = (size_t)N * cin * Hs * Ws;
   if (total == 0) return CSNET_OK;
-  if (Ws % 4 == 0) tf::pool_bwd4_kernel<<<(unsigned)((total / 4 + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
+  if (Ws % 4 == 0 && total < (1ull << 32)) tf::pool_bwd4_kernel<<<(unsigned)((total / 4 + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
   else tf::pool_bwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
