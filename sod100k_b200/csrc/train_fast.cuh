@@ -228,8 +228,9 @@ struct C1Args {
   RsPath rs[kMaxRs];
 };
 
-template <int CT, int PX>
+template <int CT, int PX, bool VEC>
 __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int cb, int n, int y, int x0) {
+  constexpr int U = 6;                                   // input channels loaded ahead of their FMAs (memory-level parallelism)
   const int H = A.H, W = A.W;
   const size_t plane = (size_t)H * W;
   float acc[CT][PX];
@@ -242,25 +243,39 @@ __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int 
     if (P.cout0 >= cb + CT || P.cout0 + P.cout <= cb) continue;
     const float* s = P.src + (((size_t)n * P.Cs + P.c0) * H + y) * W + x0;
     const float* wr = wsm + (size_t)P.woff * A.Cpad + cb;
-#pragma unroll 4
-    for (int ci = 0; ci < P.cin; ++ci) {
-      float v[PX];
-      const float* q = s + (size_t)ci * plane;
-      if (A.vec) {
-        if (PX == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(q)); v[0] = t.x; v[1] = t.y; v[PX - 2] = t.z; v[PX - 1] = t.w; }
-        else { const float2 t = __ldg(reinterpret_cast<const float2*>(q)); v[0] = t.x; v[1] = t.y; }
-      } else {
+    for (int ci0 = 0; ci0 < P.cin; ci0 += U) {
+      float v[U][PX];
 #pragma unroll
-        for (int px = 0; px < PX; ++px) v[px] = x0 + px < W ? __ldg(q + px) : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const float* q = s + (size_t)(ci0 + u) * plane;
+        const bool on = ci0 + u < P.cin;
+        if (VEC) {
+          if (PX == 4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on) t = __ldg(reinterpret_cast<const float4*>(q));
+            v[u][0] = t.x; v[u][1] = t.y; v[u][PX - 2] = t.z; v[u][PX - 1] = t.w;
+          } else {
+            float2 t = make_float2(0.f, 0.f);
+            if (on) t = __ldg(reinterpret_cast<const float2*>(q));
+            v[u][0] = t.x; v[u][1] = t.y;
+          }
+        } else {
+#pragma unroll
+          for (int px = 0; px < PX; ++px) v[u][px] = (on && x0 + px < W) ? __ldg(q + px) : 0.f;
+        }
       }
 #pragma unroll
-      for (int q4 = 0; q4 < CT / 4; ++q4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wr + (size_t)ci * A.Cpad + 4 * q4);
-        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+      for (int u = 0; u < U; ++u) {
+        if (ci0 + u >= P.cin) break;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int q4 = 0; q4 < CT / 4; ++q4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wr + (size_t)(ci0 + u) * A.Cpad + 4 * q4);
+          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-          for (int px = 0; px < PX; ++px) acc[4 * q4 + j][px] = fmaf(v[px], wv[j], acc[4 * q4 + j][px]);
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int px = 0; px < PX; ++px) acc[4 * q4 + j][px] = fmaf(v[u][px], wv[j], acc[4 * q4 + j][px]);
+        }
       }
     }
   }
@@ -287,7 +302,7 @@ __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int 
 #pragma unroll
   for (int c = 0; c < CT; ++c) {
     if (cb + c >= A.C) break;
-    if (A.vec) {
+    if (VEC) {
       if (PX == 4) *reinterpret_cast<float4*>(o + (size_t)c * plane) = make_float4(acc[c][0], acc[c][1], acc[c][PX - 2], acc[c][PX - 1]);
       else *reinterpret_cast<float2*>(o + (size_t)c * plane) = make_float2(acc[c][0], acc[c][1]);
     } else {
@@ -300,7 +315,7 @@ __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int 
 
 // PX == 4: 4 pixels x (16 | 8) channels per pass (<= 16 output channels: one pass over the input);  PX == 2: 2 pixels x (32 | 16 | 8)
 // channels (17..32 output channels in ONE pass).  quads = ceil(W / PX), vec = W % PX == 0.
-template <int PX>
+template <int PX, bool VEC>
 __global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ C1Args A) {
   extern __shared__ __align__(16) float wsm[];                          // [wrows][Cpad]: every path's weights, zero outside its slice
   for (int i = threadIdx.x; i < A.wrows * A.Cpad; i += kT) {
@@ -320,9 +335,9 @@ __global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ 
   const int q = (int)(task % A.quads), y = (int)((task / A.quads) % A.H), n = (int)(task / ((size_t)A.quads * A.H));
   for (int cb = 0; cb < A.C;) {
     const int left = A.C - cb;
-    if (left <= 8) { c1_group<8, PX>(A, wsm, cb, n, y, PX * q); cb += 8; }
-    else if (PX == 4 || left <= 16) { c1_group<16, PX>(A, wsm, cb, n, y, PX * q); cb += 16; }
-    else { c1_group<32, PX>(A, wsm, cb, n, y, PX * q); cb += 32; }
+    if (left <= 8) { c1_group<8, PX, VEC>(A, wsm, cb, n, y, PX * q); cb += 8; }
+    else if (PX == 4 || left <= 16) { c1_group<16, PX, VEC>(A, wsm, cb, n, y, PX * q); cb += 16; }
+    else { c1_group<32, PX, VEC>(A, wsm, cb, n, y, PX * q); cb += 32; }
   }
 }
 

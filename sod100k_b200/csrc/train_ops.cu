@@ -588,13 +588,16 @@ static int launch_conv1x1(const tf::ConvArgs& F, cudaStream_t st) {
   if (smem > 96 * 1024) return kNotHandled;                // (not a CSNet shape) -> the generic kernel
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(tf::conv1x1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(tf::conv1x1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(tf::conv1x1_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(tf::conv1x1_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(tf::conv1x1_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
   const size_t tasks = (size_t)A.N * A.H * A.quads;
-  if (px == 2) tf::conv1x1_kernel<2><<<(unsigned)((tasks + tf::kT - 1) / tf::kT), tf::kT, smem, st>>>(A);
-  else tf::conv1x1_kernel<4><<<(unsigned)((tasks + tf::kT - 1) / tf::kT), tf::kT, smem, st>>>(A);
+  const unsigned blocks = (unsigned)((tasks + tf::kT - 1) / tf::kT);
+  if (px == 2) tf::conv1x1_kernel<2, true><<<blocks, tf::kT, smem, st>>>(A);
+  else if (A.vec) tf::conv1x1_kernel<4, true><<<blocks, tf::kT, smem, st>>>(A);
+  else tf::conv1x1_kernel<4, false><<<blocks, tf::kT, smem, st>>>(A);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }
