@@ -51,6 +51,12 @@ struct ConvArgs {
   RsPath rs[kMaxRs];
 };
 
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 16 : 0;                                   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
 __device__ __forceinline__ void bilin(int H, int W, int up, int oy, int ox, int& o00, int& o01, int& o10, int& o11, float& w00,
                                       float& w01, float& w10, float& w11) {
   const float inv = 1.f / (float)up;
@@ -104,9 +110,8 @@ __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__
           if (A.vec) {
             for (int v = lane; v * 4 < P.Wp; v += 32) {
               const int xx = v * 4 - P.hp;
-              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (inside && xx >= 0 && xx < W) t = __ldg(reinterpret_cast<const float4*>(s + xx));
-              *reinterpret_cast<float4*>(d + v * 4) = t;
+              const bool ld = inside && xx >= 0 && xx < W;
+              cp_async16(d + v * 4, ld ? s + xx : P.src, ld);             // asynchronous: every row of the stage is in flight at once
             }
           } else {
             for (int v = lane; v < P.Wp; v += 32) {
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__
             }
           }
         }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
         // ---- stage the weights of this (channel chunk, output-channel group); zero outside the path's slice ------------------
         for (int i = tid; i < nc * kk * kCoT; i += kT) {
           const int c = i / (kk * kCoT), t = (i / kCoT) % kk, co = cb + (i % kCoT) - P.cout0;
@@ -124,6 +130,7 @@ __global__ void __launch_bounds__(kT, 2) conv_fwd_kernel(const __grid_constant__
                              : __ldg(P.w + ((size_t)(ci0 + c) * kk + t) * P.cout + co);
           wsm[i] = v;
         }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
         if (!live) continue;
         // ---- accumulate ---------------------------------------------------------------------------------------------------
@@ -342,12 +349,6 @@ __global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ 
 }
 
 // ---- weight gradient ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-  const int sz = valid ? 16 : 0;                                   // src-size 0: the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-
 struct WgradArgs {
   const float* in;                  // [N][Cs][H][W], channels [c0, c0 + cin)
   const float* dd;                  // [N][Cd][H][W], channels [cout0, cout0 + cout)
