@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op time table to stderr")
-    ap.add_argument("--train-batch", type=int, default=32, help="images per GPU of the `train` sub-record's step")
+    ap.add_argument("--train-batch", type=int, default=256, help="images per GPU of the `train` sub-record's step")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the train sub-record, the eager-GPU baseline and the extra configs (profiling runs)")
     return ap.parse_args()
