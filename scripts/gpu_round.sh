@@ -14,6 +14,6 @@ tail -c 3000 gpurun_out/bench.json; tail -40 gpurun_out/bench.err
 if [ "${NCU:-1}" = "1" ]; then
   echo "== ncu launch list"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench.log 2>&1
   tail -3 gpurun_out/ncu_bench.log
 fi

@@ -14,16 +14,19 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     eng = m.engine()
     res = {}
     for name, fn in (("f32", lambda: eng.forward_host(x, out=y)), ("u8", lambda: eng.forward_host_u8(x8, out=y8))):
-        for _ in range(3): fn()
+        for _ in range(6): fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10): fn()
+        for _ in range(20): fn()
         e1.record(); torch.cuda.synchronize()
-        res[name] = e0.elapsed_time(e1) / 10
+        res[name] = e0.elapsed_time(e1) / 20
     print(json.dumps(res))
 else:
-    for split in ("32,32", "0,0", "16,16", "8,8", "16,0", "0,16", "24,16"):
-        env = dict(os.environ, CSNET_HOST_SPLIT=split, CSNET_HOST_SPLIT_U8=split)
+    settings = [{}, {"CSNET_HOST_SCHED": "16,32,64,112,32"}, {"CSNET_HOST_SCHED": "16,48,160,32"}, {"CSNET_HOST_SCHED": "8,16,32,64,112,24"},
+                {"CSNET_HOST_SCHED": "24,72,136,24"}, {"CSNET_HOST_SCHED": "32,64,128,32"}, {"CSNET_HOST_SCHED": "16,32,64,128,16"},
+                {"CSNET_HOST_SCHED_U8": "64,192"}, {"CSNET_HOST_SCHED_U8": "32,192,32"}, {"CSNET_HOST_SCHED_U8": "32,224"}, {"CSNET_HOST_SCHED_U8": "224,32"}]
+    for st in settings:
+        env = dict(os.environ, **st)
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print(split, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:], flush=True)
+        print(st, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:], flush=True)

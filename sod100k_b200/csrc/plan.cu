@@ -1298,9 +1298,37 @@ static int run_host_impl(csnet_plan* P, int32_t N, const void* x_host, void* y_h
   // the only ones nothing overlaps — and one large middle chunk keeps the kernels at large-batch efficiency (measured at
   // bs 256: 4 equal chunks 25.2 ms, 2 equal 24.5 ms).  CSNET_HOST_CHUNKS=k forces k equal chunks.
   static const int n_equal = [] { const char* e = getenv("CSNET_HOST_CHUNKS"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
+  static int sched[2][16], sched_n[2] = {0, 0};
+  static const bool sched_parsed = [] {
+    const char* names[2] = {"CSNET_HOST_SCHED", "CSNET_HOST_SCHED_U8"};
+    for (int k = 0; k < 2; ++k) {
+      const char* e = getenv(names[k]);
+      int tot = 0;
+      while (e && *e && sched_n[k] < 16) {
+        const int v = atoi(e);
+        if (v <= 0) { sched_n[k] = 0; break; }
+        sched[k][sched_n[k]++] = v; tot += v;
+        e = strchr(e, ',');
+        if (e) ++e;
+      }
+      if (tot != 256) sched_n[k] = 0;
+    }
+    return true; }();
+  (void)sched_parsed;
   int sizes[16], n_sizes = 0;
   if (N < 64) {
     sizes[n_sizes++] = N;
+  } else if (sched_n[u8 ? 1 : 0] > 0) {
+    // explicit schedule in 256ths of the batch (CSNET_HOST_SCHED / CSNET_HOST_SCHED_U8 = "16,32,64,112,32"); the rounding remainder
+    // goes to the largest chunk.  Measured (scripts/host_split.py, bs 256): every ramp with 4-6 chunks is SLOWER than the default
+    // 32 / 192 / 32 (17.3-20.0 ms vs 16.5 ms) — each extra chunk pays the 81 launches again at a small batch.
+    const int* v = sched[u8 ? 1 : 0];
+    int tot = 0, big = 0;
+    for (int i = 0; i < sched_n[u8 ? 1 : 0]; ++i) { sizes[n_sizes] = N * v[i] / 256; tot += sizes[n_sizes]; if (sizes[n_sizes] > sizes[big]) big = n_sizes; ++n_sizes; }
+    sizes[big] += N - tot;
+    int k = 0;
+    for (int i = 0; i < n_sizes; ++i) if (sizes[i] > 0) sizes[k++] = sizes[i];
+    n_sizes = k;
   } else if (n_equal > 0) {
     const int c = (N + n_equal - 1) / n_equal;
     for (int n0 = 0; n0 < N; n0 += c) sizes[n_sizes++] = (N - n0) < c ? (N - n0) : c;
