@@ -74,6 +74,34 @@ class Trainer:
         normal, picked = reference_param_groups(model)
         self.opt = T.FusedAdam([(normal, weight_decay), (picked, 0.0)], lr=lr, betas=betas, eps=eps)
 
+    def step_host(self, x_host: torch.Tensor, target_host: torch.Tensor) -> torch.Tensor:
+        """`step` fed from (pinned) host tensors: the batch is copied into one of two device staging slots on a copy stream, so —
+        as nothing in the step syncs with the host — the copy of call k+1 runs under the kernels of call k (what a DataLoader with
+        pin_memory and non_blocking copies gives `train.py:197-203`).  Returns the loss as a device tensor; read it a step late
+        (or not every step) to keep the overlap."""
+        dev = next(self.model.parameters()).device
+        if not hasattr(self, "_feed"):
+            self._feed = {"stream": torch.cuda.Stream(dev), "slots": [None, None], "free": [None, None], "k": 0}
+        f = self._feed
+        k = f["k"] = f["k"] ^ 1
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(f["stream"]):
+            if f["free"][k] is not None:
+                f["stream"].wait_event(f["free"][k])          # the step that last read this slot has finished
+            slot = f["slots"][k]
+            if slot is None or slot[0].shape != x_host.shape or slot[1].shape != target_host.shape:
+                slot = f["slots"][k] = (torch.empty(x_host.shape, dtype=torch.float32, device=dev),
+                                        torch.empty(target_host.shape, dtype=torch.float32, device=dev))
+            slot[0].copy_(x_host, non_blocking=True)
+            slot[1].copy_(target_host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(f["stream"])
+        main.wait_event(ready)
+        loss = self.step(slot[0], slot[1])
+        f["free"][k] = torch.cuda.Event()
+        f["free"][k].record(main)
+        return loss
+
     def step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Returns the BCE loss (without the regulariser), like `losses.update(loss.item())` at train.py:211 —
         as a device tensor: no host sync inside the step."""

@@ -264,3 +264,23 @@ def test_register_tiled_mix_of_paths():
     r.backward(gy.cpu().double())
     for got, ref in [(y, r), (x.grad, x64.grad)] + [(ws[i].grad, w64[i].grad) for i in range(3)]:
         assert (got.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_host_fed_step_equals_device_step():
+    """Trainer.step_host (copy stream + two staging slots) against Trainer.step on device tensors: same losses and bit-identical
+    parameters after three steps with three different batches (every gradient kernel merges its partial sums in a fixed order)."""
+    outs = []
+    for host in (False, True):
+        m, cfg, params, buffers, _, _ = _setup("csnet-L-x2", 2, (64, 64), 21)
+        tr = Trainer(m, lr=1e-3, weight_decay=5e-3)
+        losses = []
+        for k in range(3):
+            x = torch.from_numpy(synth.randn_images(4, 64, 96, 30 + k))
+            t = torch.from_numpy(synth.random_masks(4, 64, 96, 40 + k))
+            losses.append(tr.step_host(x.pin_memory(), t.pin_memory()) if host else tr.step(x.cuda(), t.cuda()))
+        torch.cuda.synchronize()
+        outs.append(([float(l) for l in losses], {k: v.detach().clone() for k, v in m.state_dict().items()}))
+    # (the loss value itself is an atomicAdd over blocks: equal to the last ulp or two; its gradient is element-wise)
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(outs[0][0], outs[1][0]))
+    for k, v in outs[0][1].items():
+        assert torch.equal(v, outs[1][1][k]), k
