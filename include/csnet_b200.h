@@ -241,6 +241,9 @@ int csnet_train_dw_conv(const float* x, const float* w, float* y, int32_t N, int
                         int32_t transposed, void* stream);
 int csnet_train_dw_wgrad(const float* x, const float* dy, float* dw, int32_t N, int32_t C, int32_t H, int32_t W, float scale,
                          void* stream);
+/* Both gradients of the depthwise conv in one pass over dy (autograd of F.conv2d(x, 100 * w, groups=C), conv2d.py:104): dx [N,C,H,W], dw [C][9]. */
+int csnet_train_dw_bwd(const float* x, const float* dy, const float* w, float* dx, float* dw, int32_t N, int32_t C, int32_t H, int32_t W,
+                       float scale, void* stream);
 /* Raw conv mix (gOctaveConv.forward csnet.py:664-726 for one output branch; MSBlock :141-146): dst = sum of paths. */
 int csnet_train_mix_fwd(float* dst, int32_t N, int32_t C, int32_t H, int32_t W, const csnet_train_path* paths, int32_t n_paths,
                         void* stream);

@@ -235,9 +235,8 @@ struct C1Args {
   RsPath rs[kMaxRs];
 };
 
-template <int CT, int PX, bool VEC>
+template <int CT, int PX, bool VEC, int U = 6>           // U: input channels loaded ahead of their FMAs (memory-level parallelism)
 __device__ __forceinline__ void c1_group(const C1Args& A, const float* wsm, int cb, int n, int y, int x0) {
-  constexpr int U = 6;                                   // input channels loaded ahead of their FMAs (memory-level parallelism)
   const int H = A.H, W = A.W;
   const size_t plane = (size_t)H * W;
   float acc[CT][PX];
@@ -346,6 +345,27 @@ __global__ void __launch_bounds__(kT, 2) conv1x1_kernel(const __grid_constant__ 
     else if (PX == 4 || left <= 16) { c1_group<16, PX, VEC>(A, wsm, cb, n, y, PX * q); cb += 16; }
     else { c1_group<32, PX, VEC>(A, wsm, cb, n, y, PX * q); cb += 32; }
   }
+}
+
+// narrow form: 8 output channels per pass and 8 channels of loads in flight, <= 85 registers so three CTAs fit an SM
+__global__ void __launch_bounds__(kT, 3) conv1x1_narrow_kernel(const __grid_constant__ C1Args A) {
+  extern __shared__ __align__(16) float wsm[];
+  for (int i = threadIdx.x; i < A.wrows * A.Cpad; i += kT) {
+    const int row = i / A.Cpad, col = i - row * A.Cpad;
+    float v = 0.f;
+    for (int pi = 0; pi < A.n_conv; ++pi) {
+      const C1Path& P = A.p[pi];
+      const int ci = row - P.woff, co = col - P.cout0;
+      if (ci >= 0 && ci < P.cin && co >= 0 && co < P.cout)
+        v = A.transposed ? __ldg(P.w + (size_t)co * P.cin + ci) : __ldg(P.w + (size_t)ci * P.cout + co);
+    }
+    wsm[i] = v;
+  }
+  __syncthreads();
+  const size_t task = (size_t)blockIdx.x * kT + threadIdx.x;
+  if (task >= (size_t)A.N * A.H * A.quads) return;
+  const int q = (int)(task % A.quads), y = (int)((task / A.quads) % A.H), n = (int)(task / ((size_t)A.quads * A.H));
+  for (int cb = 0; cb < A.C; cb += 8) c1_group<8, 4, true, 8>(A, wsm, cb, n, y, 4 * q);
 }
 
 // ---- weight gradient ---------------------------------------------------------------------------------------------------------
@@ -774,6 +794,87 @@ __global__ void __launch_bounds__(kT) dw3_wgrad_kernel(const float* __restrict__
     }
   }
   // block reduction in a fixed order: warp shuffles, then the 8 warp results
+  __shared__ float sh[kT / 32][9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kT / 32; ++wv) s += sh[wv][threadIdx.x];
+    part[((size_t)blockIdx.x * C + c) * 9 + threadIdx.x] = s;
+  }
+}
+
+// backward of the depthwise 3x3 in ONE pass over dy: dx = scale * conv3x3(dy, flipped w) and the block partials of
+// dw[c][tap] = sum dy[y][x] * x[y+ky-1][x+kx-1]; grid = (blocks per channel, C) as dw3_wgrad_kernel.
+__global__ void __launch_bounds__(kT) dw3_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ w,
+                                                     float* __restrict__ dx, float* __restrict__ part, int N, int C, int H, int W, float scale,
+                                                     int quads, int rows) {
+  const int c = blockIdx.y, bands = (H + rows - 1) / rows;
+  const size_t tasks = (size_t)N * bands * quads;
+  const bool vec = (W & 3) == 0;
+  float k[9], acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { k[i] = __ldg(w + c * 9 + 8 - i) * scale; acc[i] = 0.f; }
+  for (size_t t = (size_t)blockIdx.x * kT + threadIdx.x; t < tasks; t += (size_t)gridDim.x * kT) {
+    const int q = (int)(t % quads), b = (int)((t / quads) % bands), n = (int)(t / ((size_t)quads * bands));
+    const int x0 = 4 * q, r0 = b * rows, r1 = r0 + rows < H ? r0 + rows : H;
+    const size_t plane = ((size_t)n * C + c) * H * W;
+    const float* p = x + plane;
+    const float* g = dy + plane;
+    float* o = dx + plane;
+    float wx[3][6], wg[3][6];                                     // 3-row windows of x and dy, columns x0 - 1 ... x0 + 4
+    auto load_row = [&](const float* base, int r, float* d) {
+      if (r < 0 || r >= H) { d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = 0.f; return; }
+      const float* s = base + (size_t)r * W + x0;
+      if (vec) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(s));
+        d[1] = m.x; d[2] = m.y; d[3] = m.z; d[4] = m.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[1 + j] = x0 + j < W ? __ldg(s + j) : 0.f;
+      }
+      d[0] = x0 > 0 ? __ldg(s - 1) : 0.f;
+      d[5] = x0 + 4 < W ? __ldg(s + 4) : 0.f;
+    };
+    load_row(p, r0 - 1, wx[0]); load_row(p, r0, wx[1]);
+    load_row(g, r0 - 1, wg[0]); load_row(g, r0, wg[1]);
+    for (int r = r0; r < r1; ++r) {
+      load_row(p, r + 1, wx[2]);
+      load_row(g, r + 1, wg[2]);
+      float a[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) s = fmaf(wg[ky][j + kx], k[ky * 3 + kx], s);
+        a[j] = s;
+      }
+      float* d = o + (size_t)r * W + x0;
+      if (vec) *reinterpret_cast<float4*>(d) = make_float4(a[0], a[1], a[2], a[3]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (x0 + j < W) d[j] = a[j];
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[ky * 3 + kx] = fmaf(wg[1][1 + j], wx[ky][j + kx], acc[ky * 3 + kx]);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { wx[0][j] = wx[1][j]; wx[1][j] = wx[2][j]; wg[0][j] = wg[1][j]; wg[1][j] = wg[2][j]; }
+    }
+  }
   __shared__ float sh[kT / 32][9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {

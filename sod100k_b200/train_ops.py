@@ -38,6 +38,7 @@ def lib():
         l.csnet_train_bn_prelu_bwd.argtypes = [f32p, f32p, f32p, i32, i32, i32, f32p, f32p, f32p, f32p, f32p, f, f32p, f32p, f32p, i32, vp]
         l.csnet_train_dw_conv.argtypes = [f32p, f32p, f32p, i32, i32, i32, i32, f, i32, vp]
         l.csnet_train_dw_wgrad.argtypes = [f32p, f32p, f32p, i32, i32, i32, i32, f, vp]
+        l.csnet_train_dw_bwd.argtypes = [f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, f, vp]
         l.csnet_train_mix_fwd.argtypes = [f32p, i32, i32, i32, i32, C.POINTER(TrainPath), i32, vp]
         l.csnet_train_mix_dgrad.argtypes = [f32p, i32, i32, i32, i32, C.POINTER(TrainPath), f32p, vp]
         l.csnet_train_mix_wgrad.argtypes = [f32p, i32, i32, i32, i32, C.POINTER(TrainPath), f32p, vp]
@@ -51,7 +52,7 @@ def lib():
 
 # kernels launched through this module since import (bench.py reports the count of a timed region): kernels per entry point
 LAUNCHES = 0
-_KERNELS = {"csnet_train_bn_prelu_bwd": 2, "csnet_train_mix_wgrad": 2, "csnet_train_dw_wgrad": 2}
+_KERNELS = {"csnet_train_bn_prelu_bwd": 2, "csnet_train_mix_wgrad": 2, "csnet_train_dw_wgrad": 2, "csnet_train_dw_bwd": 2}
 
 
 def _ck(rc, what):
@@ -250,6 +251,11 @@ class DwFn(torch.autograd.Function):
         dy = _f32(dy)
         n, c, h, ww = x.shape
         dx = dw = None
+        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:          # the usual case: one pass over dy for both gradients
+            dx, dw = torch.empty_like(x), torch.empty_like(wf)
+            _ck(lib().csnet_train_dw_bwd(x.data_ptr(), dy.data_ptr(), wf.data_ptr(), dx.data_ptr(), dw.data_ptr(), n, c, h, ww, ctx.scale,
+                                         _stream(x)), "csnet_train_dw_bwd")
+            return dx, dw.reshape(ctx.wshape), None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _ck(lib().csnet_train_dw_conv(dy.data_ptr(), wf.data_ptr(), dx.data_ptr(), n, c, h, ww, ctx.scale, 1, _stream(x)), "csnet_train_dw_conv(T)")
