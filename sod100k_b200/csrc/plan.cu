@@ -508,12 +508,14 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   A.Chi = stem ? Xh.C * 9 : Xh.C; A.Cli = stem ? 0 : Xl.C; A.Cho = Yh.C; A.Clo = op.dst2 >= 0 ? P.tensors[op.dst2].C : 0;
   A.Ci = stem ? Xh.C : 0;
   if (stem && (Xh.dtype != CSNET_F32 || A.Chi > 32 || A.W % 4)) return false;
-  if (A.W % 16 || A.H % 4 || A.Cho > csnet::kIlsMaxC || A.Clo > csnet::kIlsMaxC || A.Chi + A.Cli > 64) return false;
+  // odd-width form (il_stream.cuh, kOddW): W = 8 (mod 16), e.g. the 56-wide stage 3 at 224 x 224 — one strip, the tile one group wider than the image
+  const bool oddw = !stem && A.W % 16 == 8 && A.Cli > 0;
+  if ((A.W % 16 && !oddw) || A.H % 4 || A.Cho > csnet::kIlsMaxC || A.Clo > csnet::kIlsMaxC || A.Chi + A.Cli > 64) return false;
   A.K8 = stem ? 32 : round_up(A.Chi + A.Cli, 8);                      // the compiler packs the stem's weights as [M16][32]
   A.K16 = round_up(A.Chi + A.Cli, 16);
   A.NH = round_up(A.Cho, 16);
   A.NL = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
-  A.GH = A.W / 8; A.GL = A.W / 16;
+  A.GH = A.W / 8; A.GL = (A.W / 2 + 7) / 8;
   A.SH = (A.K16 > A.NH ? A.K16 : A.NH) + 1;            // odd: consecutive pixel groups start in different bank groups
   A.SL = A.Clo > 0 ? A.K16 + 1 : (A.Cli | 1);
   A.ST = A.NL + 1;
@@ -524,11 +526,12 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   csnet::IlsArgs best{};
   for (int ns = 1; ns <= 16; ++ns) {
     if (P.ils_force_ns > 0 && ns != P.ils_force_ns) continue;
-    if (A.GH % ns || (A.GH / ns) % 2) continue;
+    if (oddw ? ns != 1 : (A.GH % ns || (A.GH / ns) % 2)) continue;
     csnet::IlsArgs T = A;
-    T.ns = ns; T.gsn = A.GH / ns; T.hl = ns > 1 ? 1 : 0;
+    T.ns = ns; T.gsn = oddw ? A.GH + 1 : A.GH / ns; T.hl = ns > 1 ? 1 : 0;
     T.GR = T.gsn + 2 * T.hl; T.GLR = T.gsn / 2 + 2 * T.hl;
-    T.dw_warps = (T.Cho * T.gsn + T.Clo * (T.gsn / 2) + 31) / 32;        // tail tasks are packed: hi (channel, column)s, then lo ones
+    T.tgh = oddw ? A.GH : T.gsn; T.tgl = oddw ? A.GL : T.gsn / 2;
+    T.dw_warps = (T.Cho * T.tgh + T.Clo * T.tgl + 31) / 32;              // tail tasks are packed: hi (channel, column)s, then lo ones
     if (T.dw_warps < 4) T.dw_warps = 4;                                   // the epilogue needs one warp per TMEM lane quarter
     const int warps = T.dw_warps;
     if (warps * 32 > csnet::kIlsMaxThreads || T.SH > 256 || T.SL > 256 || T.GR > 256) continue;
@@ -891,6 +894,7 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     // two CTAs of <= 113 KB share an SM only with the full shared-memory carve-out
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1046,6 +1050,11 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
       if (!encode_image_map(&tmL, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Ci, A.H, A.W, A.BW, 4)) 
         return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock, image)");
       tmH = tmL;
+    } else if (A.W % 16) {                                   // odd-width form: the lo rows are not 16-byte multiples -> cp.async, no map
+      if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GR, 4))
+        return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock, odd width)");
+      tmL = tmH;
+      A.xl_in = reinterpret_cast<const uint16_t*>(P->tensor_ptr(op.paths[1].src, N, ext_ptrs));
     } else if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GR, 4) ||
                !encode_group_map(&tmL, P->tensor_ptr(op.paths[1].src, N, ext_ptrs), N, A.Cli, A.H / 2, A.W / 2, A.SL, A.GLR, 2))
       return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock)");
@@ -1055,7 +1064,8 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     static unsigned long long* dbg_buf = nullptr;
     if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(unsigned long long));
     A.dbg = dbg ? dbg_buf : nullptr;
-    if (stem) csnet::il_stream_kernel<__half, false, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    if (A.W % 16) csnet::il_stream_kernel<__half, false, false, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    else if (stem) csnet::il_stream_kernel<__half, false, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     else if (dbg) csnet::il_stream_kernel<__half, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     else csnet::il_stream_kernel<__half, false><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     if (dbg && !stem) {        // debugging aid: mean cycles per phase over the CTAs (synchronises)
