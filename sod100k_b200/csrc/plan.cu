@@ -194,6 +194,7 @@ struct csnet_plan {
   struct GraphSlot { cudaGraphExec_t exec = nullptr; void* in = nullptr; void* out = nullptr; size_t in_bytes = 0, out_bytes = 0; };
   std::vector<GraphSlot> graphs;                  // index = batch size
   cudaStream_t cap_stream = nullptr;
+  bool ils_odd = false;                           // CSNET_ILS_ODD=1: the odd-width form of il_stream (W = 8 mod 16)
   int graph_max_n = 8;                            // CSNET_GRAPH_MAX_N (0 disables)
   std::vector<char> op_msd;                       // per op: an MSBlock whose dilated paths run on ms_direct.cuh
   std::vector<char> op_ms;                        // per op: the streaming 1x1 MIX kernel (mix_stream.cuh) can run it
@@ -509,7 +510,9 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   A.Ci = stem ? Xh.C : 0;
   if (stem && (Xh.dtype != CSNET_F32 || A.Chi > 32 || A.W % 4)) return false;
   // odd-width form (il_stream.cuh, kOddW): W = 8 (mod 16), e.g. the 56-wide stage 3 at 224 x 224 — one strip, the tile one group wider than the image
-  const bool oddw = !stem && A.W % 16 == 8 && A.Cli > 0;
+  // Opt-in (CSNET_ILS_ODD=1): correct (tests/test_gpu_il_stream.py) but its 4-row x 56-px chunks are too small for the kernel's phase structure —
+  // the five stage-3 blocks take 0.93 ms instead of 1.10 ms per-op and the bs-256 step does not move (11.00 vs 10.98 ms).
+  const bool oddw = P.ils_odd && !stem && A.W % 16 == 8 && A.Cli > 0;
   if ((A.W % 16 && !oddw) || A.H % 4 || A.Cho > csnet::kIlsMaxC || A.Clo > csnet::kIlsMaxC || A.Chi + A.Cli > 64) return false;
   A.K8 = stem ? 32 : round_up(A.Chi + A.Cli, 8);                      // the compiler packs the stem's weights as [M16][32]
   A.K16 = round_up(A.Chi + A.Cli, 16);
@@ -882,6 +885,7 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   if (const char* e1 = getenv("CSNET_ILS")) P->ils_enabled = e1[0] != '0';
   if (const char* e3 = getenv("CSNET_ILS_NS")) P->ils_force_ns = atoi(e3);
   if (const char* e2 = getenv("CSNET_ILS_MIN_CHUNKS")) P->ils_min_chunks = atoi(e2);
+  if (const char* e7 = getenv("CSNET_ILS_ODD")) P->ils_odd = e7[0] == '1';
   int ils_smem_max = 0;
   for (size_t i = 0; i < P->ops.size(); ++i) {
     csnet::IlsArgs S;
