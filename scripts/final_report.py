@@ -1,0 +1,69 @@
+"""Write profiles/r02_g_final.md from the bench JSON lines (1 GPU: argv[1], 2 GPUs: argv[2]) and the ncu launch list
+profiles/r02_g_launches.csv; the ncu / sanitizer paragraphs are the summaries of the committed captures."""
+import collections, csv, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+d2 = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r02_g_launches.csv"))))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+h = rows[hi]; ki = h.index("Kernel Name"); vi = h.index("Metric Value")
+agg = collections.OrderedDict()
+for r in rows[hi + 2:]:
+    if len(r) <= vi:
+        continue
+    name = r[ki].split("(")[0].replace("void ", "").replace("csnet::", "").replace("(anonymous namespace)::", "")
+    try:
+        v = float(r[vi].replace(",", ""))
+    except ValueError:
+        continue
+    a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v
+tot = sum(v for _, v in agg.values())
+lines = [f"| `{k}` | {n} | {v / 1e3:.1f} | {100 * v / tot:.1f} % |" for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]]
+r = d["roofline"]
+md = f'''# r02-g — final state of round 2 (one B200, csnet-L-x2, 224x224)
+
+`python bench.py --steps 10 --warmup 3` (gpurun, fresh box; clocks {d["clocks"]["sm_mhz"]:.0f} / {d["clocks"]["sm_max_mhz"]:.0f} MHz, no throttle reasons), then the 2-GPU torchrun form.
+
+| record | value |
+|---|---|
+| `value` — inference, 256 img resident in HBM, fp16 storage / fp32 accumulate | **{d["value"]:.0f} img/s**, {d["ms_per_step"]:.2f} ms per step, {d["gpu_launches"] // d["steps"]} launches per step |
+| `e2e` — `csnet_plan_run_host`, pinned fp32 in / out ({d["e2e"]["h2d_bytes_per_step"] / 1e6:.0f} MB H2D + {d["e2e"]["d2h_bytes_per_step"] / 1e6:.0f} MB D2H per step) | {d["e2e"]["value"]:.0f} img/s, {d["e2e"]["ms_per_step"]:.2f} ms |
+| `e2e_u8` — `csnet_plan_run_host_u8`, uint8 HWC in, uint8 maps out ({d["e2e_u8"]["h2d_bytes_per_step"] / 1e6:.0f} + {d["e2e_u8"]["d2h_bytes_per_step"] / 1e6:.0f} MB) | {d["e2e_u8"]["value"]:.0f} img/s, {d["e2e_u8"]["ms_per_step"]:.2f} ms |
+| `roofline` (dominant kernel `{r["kernel"]}`, {r["kernel_launches_per_step"]} launches, {100 * r["kernel_share_of_step"]:.0f} % of the step) | {r["achieved"]:.0f} GB/s of {r["peak"]:.0f} = **{100 * r["frac"]:.1f} %**; algorithmic {r["algorithmic_bytes"] / 1e9:.2f} GB vs ncu DRAM traffic {(r["traffic"] or float("nan")) / 1e9:.2f} GB |
+| whole net against SURVEY 8d's 31.5 MB / image | {r["net"]["achieved"]:.0f} GB/s = {100 * r["net"]["frac"]:.1f} % |
+| `gpu_eager_baseline` (the reference's ATen / cuDNN calls, same GPU, bs 256) | fp32 {d["gpu_eager_baseline"]["fp32"]["value"]:.0f} img/s, autocast fp16 {d["gpu_eager_baseline"]["autocast_fp16"]["value"]:.0f} img/s |
+| `cpu_baseline` (oracle port, {d["cpu_baseline"]["cores"]} host cores) | {d["cpu_baseline"]["value"]:.1f} img/s |
+| `train` — fwd + BCE + bwd + Adam, fp32, bs {d["train"]["per_gpu_batch"]} | **{d["train"]["value"]:.0f} img/s** ({d["train"]["ms_per_step"]:.1f} ms, {d["train"]["gpu_launches"] // d["train"]["steps"]} launches / step), e2e from pinned host batches {d["train"]["e2e"]["value"]:.0f}; {100 * d["train"]["roofline"]["frac"]:.1f} % of the module-fused fp32 roofline (426 MB / image) |
+| 2 GPUs (`torchrun`, weak scaling) | inference {d2["value"]:.0f} img/s, e2e {d2["e2e"]["value"]:.0f}; train {d2["train"]["value"]:.0f} img/s with the NCCL all-reduce of the 563 576-byte bucket |
+'''
+for c in d["configs"]:
+    md += f'| config: {c["workload"]} | {c.get("value", 0):.0f} img/s, {c.get("ms_per_step", 0):.2f} ms' + (f', {100 * c["roofline_net_frac"]:.1f} % of the net roofline' if "roofline_net_frac" in c else "") + " |\n"
+md += '''
+Round 1 ended at 13.4 k img/s (19.07 ms), e2e 10.2 k, train 0.26 k img/s.
+
+## Launch list of one forward (`profiles/r02_g_launches.csv`, ncu `gpu__time_duration.sum`, cold-cache and serialised: shares, not absolutes)
+
+| kernel | launches | total us | share |
+|---|---|---|---|
+''' + "\n".join(lines) + '''
+
+The bench's own CUDA-event shares (`roofline.by_kernel`): ''' + ", ".join(f"{k.split(' (')[0]} {100 * v['share']:.0f} %" for k, v in r["by_kernel"].items()) + '''.
+
+## ncu `--set full` of the final build (`gpurun_out/r02g_*.ncu-rep`, one launch each)
+
+| kernel | time | DRAM read + write | issue slots busy | FMA pipe active | warps active | long-scoreboard stalls / issue | note |
+|---|---|---|---|---|---|---|---|
+| `il_stream_kernel<__half,0,0>` stage1.2, bs 256 | 792 us (cold; 784 us in the bench) | 546 + 500 MB (algorithmic 1 072 MB) | 67.6 % | 35.4 % | 32.8 % (21 warps, one CTA / SM: tcgen05 kernels are resident once) | 0.64 | issue-bound on the depthwise tail (FHFMA with three distinct registers runs at 2.3-2.5 of 3.47 warp-instr/clk/SM, `scripts/fma_rate.cu`); traffic == algorithmic: nothing is re-read |
+| `conv1x1_kernel<4,true>` (training, 18 -> 18 class, bs 64) | 349 us | 225 + 188 MB | 44.6 % | 21.0 % | 23.8 % (2 CTAs x 8 warps, 122 registers) | 3.3 | latency-bound on the 16-byte global loads; L1 hit 74 % (the second output-channel pass re-reads from L1); at bs 256 it reaches 3.7 TB/s (`scripts/train_prims.py`) |
+| `conv_wgrad_kernel<0>` (MSBlock dilated weight gradient, bs 64) | 54 us | 6.7 MB (L2 hit 68 %) | 62.7 % | 28.3 % | 22.9 % | 0.02 | shared-memory-bandwidth bound (8 LDS.128 per 64 FMA); bank conflicts 1.5 M after the interleaved tiles (5-way before) |
+
+`profiles/r02_j_traffic_ils.csv`: DRAM bytes of the il_stream launches of one forward (source of `profiles/traffic.json`, `scripts/traffic_il_stream.py`).
+
+## Sanitizer
+
+`profiles/r02_h_sanitizer_memcheck.log`, `profiles/r02_h_sanitizer_racecheck.log`: compute-sanitizer memcheck and racecheck over `scripts/small_forward.py`
+(generic fp32, tiled fp16 / bf16, the streaming TMA / tcgen05 kernels at 12 x 224 x 224, the pipelined host calls incl. uint8, SalMetric) and
+`scripts/small_train.py` (two Trainer steps with the regulariser): 0 errors, 0 hazards.
+'''
+open(os.path.join(ROOT, "profiles", "r02_g_final.md"), "w").write(md)
+print(md[:1800])
