@@ -23,10 +23,11 @@ launches = [per[k] for k in sorted(per)]
 cfg, sd = checkpoints.load_npz(model)
 import torch
 prog = compiler.compile_csnet(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, S, S, "fp16")
-# the streaming kernel takes the 1x1-kind ILBlock ops whose width is 0 or 8 (mod 16) (plan.cu make_ils)
-ops = [o.name for o in prog.ops if o.kind == 3 and prog.tensors[o.dst].W % 16 in (0, 8)]
+# the streaming kernel takes the ILBlock ops whose width is a multiple of 16 (plan.cu make_ils)
+ops = [o.name for o in prog.ops if o.kind == 3 and prog.tensors[o.dst].W % 16 == 0]
 print(len(launches), "il_stream launches;", len(ops), "ops:", ops)
 assert len(launches) >= len(ops), "capture at least one whole forward"
+launches = launches[:len(ops)]
 tj_path = os.path.join(ROOT, "profiles", "traffic.json")
 tj = json.load(open(tj_path))
 for name, b in zip(ops, launches[:len(ops)]):

@@ -28,8 +28,7 @@
 // Narrow strips let two CTAs share an SM (<= 113 KB shared memory, <= 256 TMEM columns each), so one CTA's waits
 // (TMA, MMA, barriers) are filled by the other's depthwise phase.  No row halo is ever re-read from HBM (except one
 // warm-up chunk where a CTA's range starts inside an image); the work split is a flat division of the
-// N * ns * H/4 chunks over the CTAs.  Needs W % 16 == 0 (or W % 16 == 8 in the odd-width form, see IlsArgs::tgh), H % 4 == 0,
-// K = Chi + Cli <= 64.  Other shapes: il_block.cuh.
+// N * ns * H/4 chunks over the CTAs.  Needs W % 16 == 0, H % 4 == 0, K = Chi + Cli <= 64.  Other shapes: il_block.cuh.
 #pragma once
 #include "il_block.cuh"
 
@@ -59,10 +58,6 @@ struct IlsArgs {
   int32_t cpi, total_chunks;          // chunks per image strip (H/4), N * ns * cpi
   int32_t dw_warps;                   // warps of the CTA = warps of the depthwise tail (tasks packed: hi columns, then lo)
   int32_t hi_stage_bytes, lo_stage_bytes;
-  // odd-width form (kOddW: W % 16 == 8, e.g. 56): the tile is one group wider than the image (gsn = GH + 1: the extra hi group arrives
-  // zero-filled from the TMA unit, the last lo group is half outside), lo rows are not 16-byte multiples so they are copied by cp.async
-  int32_t tgh, tgl;                    // depthwise-tail tasks per tile row: hi / lo groups that hold image pixels
-  const uint16_t* xl_in;               // odd-width form: the lo input tensor [N][Cli][H/2][W/2]
   unsigned long long* dbg;             // optional: per-CTA phase cycle counters [grid][8] (CSNET_ILS_DBG=1)
   int32_t off_xl, off_xh, off_t1l, off_wbh, off_wbl, off_bar, off_zero, off_epi, smem_bytes;
 };
@@ -124,12 +119,10 @@ __device__ __forceinline__ uint16_t h16(const uint32_t* row, int j) { return (j 
 
 // One step of the depthwise tail: T1 row r arrives (n1: pixels x0-2 .. x0+9 of this thread's channel), T2 row r-1 is
 // made from T1 rows r-2, r-1, r (10 pixels: x0-1 .. x0+8), the block output row r-2 from T2 rows r-3, r-2, r-1.
-// kOdd: halfR = the group's pixels 4..7 lie outside the image (T2 there is conv padding, only 4 pixels are stored); st8 = rows are
-// only 8-byte aligned (two 8-byte stores).
-template <typename T, bool kOdd = false>
+template <typename T>
 __device__ __forceinline__ void ils_dw_push(uint32_t (&t1)[2][6], uint32_t (&t2)[2][5], const uint32_t (&n1)[6],
                                             const uint32_t (&w1)[5], float b1, float s1, const uint32_t (&w2)[5], float b2, float s2,
-                                            bool make_t2, float mL, float mR, bool make_out, uint16_t* out, bool halfR = false, bool st8 = false) {
+                                            bool make_t2, float mL, float mR, bool make_out, uint16_t* out) {
   uint32_t q[5];
   if (make_t2) {
 #pragma unroll
@@ -151,7 +144,6 @@ __device__ __forceinline__ void ils_dw_push(uint32_t (&t1)[2][6], uint32_t (&t2)
       if (i == 8) v1 *= mR;          // T2 at x0+8 likewise on the right
       q[i >> 1] = Pack<T>::from_f2(v0, v1);
     }
-    if (kOdd && halfR) { q[2] &= 0x0000FFFFu; q[3] = 0u; q[4] = 0u; }      // T2 at pixels x0+4 .. x0+8: outside the image
   } else {
 #pragma unroll
     for (int i = 0; i < 5; ++i) q[i] = 0u;
@@ -173,12 +165,7 @@ __device__ __forceinline__ void ils_dw_push(uint32_t (&t1)[2][6], uint32_t (&t2)
       }
       o[k >> 1] = Pack<T>::from_f2(prelu_m1(v0, s2), prelu_m1(v1, s2));
     }
-    if (kOdd && st8) {
-      *reinterpret_cast<uint2*>(out) = make_uint2(o[0], o[1]);
-      if (!halfR) *reinterpret_cast<uint2*>(out + 4) = make_uint2(o[2], o[3]);
-    } else {
-      *reinterpret_cast<uint4*>(out) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
+    *reinterpret_cast<uint4*>(out) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) { t1[0][i] = t1[1][i]; t1[1][i] = n1[i]; }
@@ -229,7 +216,7 @@ __device__ __forceinline__ void ils_epilogue_warp(uint32_t taddr, uint32_t tile,
   }
 }
 
-template <typename T, bool kTiming = false, bool kStem = false, bool kOddW = false>
+template <typename T, bool kTiming = false, bool kStem = false>
 __global__ void __launch_bounds__(kIlsMaxThreads, 1)
 il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL) {
   extern __shared__ uint8_t smem_raw[];
@@ -251,8 +238,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
 
   // ---- one-time setup -----------------------------------------------------------------------------------
   if (tid == 0) {
-    // (odd-width form: the three lo barriers count the 32 lanes of the loader warp, see issue_lo_cp)
-    for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(BAR + 8 * i), "r"((kOddW && i >= 2 && i < 5) ? 32 : 1) : "memory");
+    for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(BAR + 8 * i) : "memory");
     for (int i = 0; i < 16; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_m + 8 * i) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -277,10 +263,6 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       }
     }
     if (tid < 16) reinterpret_cast<uint32_t*>(gbase + A.off_zero)[tid] = 0u;
-    if (kOddW) {
-      // the lo ring is filled by 8-byte cp.async copies of image pixels only: the K-padding slots and the half group past the image stay zero
-      for (int i = tid; i < kIlsLoStages * A.lo_stage_bytes / 16; i += nthreads) sts128(XL + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 0u));
-    }
     if (kStem) {
       // K-padding slots [Chi, K16) of both operand buffers: zero once (the im2col build never touches them, the in-place
       // epilogue only writes slots < NH <= Chi)
@@ -306,10 +288,10 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
 
   // depthwise-tail role of this thread (fixed for the whole kernel): a channel and an 8-pixel column
   // tail tasks are packed: threads [0, Cho * gsn) own a hi (channel, column), the next Clo * gsn / 2 a lo one
-  const int n_hi_tasks = Cho * A.tgh;
+  const int n_hi_tasks = Cho * gsn;
   const bool dw_hi = tid < n_hi_tasks;
   const int dwt = dw_hi ? tid : tid - n_hi_tasks;
-  const int Gd = dw_hi ? A.tgh : A.tgl, Cd = dw_hi ? Cho : Clo, Sd = dw_hi ? SH : ST;   // Gd: this role's groups per strip row
+  const int Gd = dw_hi ? gsn : gsn >> 1, Cd = dw_hi ? Cho : Clo, Sd = dw_hi ? SH : ST;   // Gd: this role's groups per strip row
   const bool dw_live = dwt < Cd * Gd;
   const int dc = dw_live ? dwt / Gd : 0, dg = dw_live ? dwt - dc * Gd : 0;
   uint32_t w1[5], w2[5];
@@ -373,30 +355,14 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       if (kStem) tma_load_4d_a(lo_stage(cl), &tmL, bar, 8 * (gs0 - hl) - 4, 4 * cl, 0, n);     // image block: rows [4 cl, 4 cl + 4), all channels
       else tma_load_5d(lo_stage(cl), &tmL, bar, 0, 0, (gs0 >> 1) - hl, 2 * cl, n);
     };
-    // odd-width form: lo chunk cl = rows 2 cl, 2 cl + 1 of every lo channel, 8 bytes (4 pixels) per copy, by the 32 lanes of the last warp;
-    // each lane's copies arrive on the stage's barrier (cp.async.mbarrier.arrive.noinc: the barrier was initialised with count 32)
-    auto issue_lo_cp = [&](int cl) {
-      const uint32_t q = lq0 + (uint32_t)(cl - cl0), bar = bar_l + 8 * (q % 3u), st = lo_stage(cl);
-      const int per_row = Wl >> 2, units = 2 * Cli * per_row;
-      const uint16_t* src = A.xl_in + ((size_t)n * Cli * Hl + 2 * cl) * Wl;
-      for (int u = lane; u < units; u += 32) {
-        const int row = u / (Cli * per_row), r2 = u - row * (Cli * per_row), ch = r2 / per_row, k = r2 - ch * per_row;
-        const uint32_t dst = st + (uint32_t)(((row * GLR + (k >> 1)) * SL + ch) * 16 + (k & 1) * 8);
-        const uint16_t* g = src + ((size_t)ch * Hl + row) * Wl + 4 * k;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(g) : "memory");
-      }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
-    };
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       if (!kStem) {
         issue_hi(c0);
         if (c0 + 1 <= c1) issue_hi(c0 + 1);
       }
-      if (!kOddW) for (int cl = cl0; cl <= cl1 && cl <= c0 + 1; ++cl) issue_lo(cl);
+      for (int cl = cl0; cl <= cl1 && cl <= c0 + 1; ++cl) issue_lo(cl);
     }
-    if (kOddW && warp == nwarps - 1)
-      for (int cl = cl0; cl <= cl1 && cl <= c0 + 1; ++cl) issue_lo_cp(cl);
     int lo_waited = 0;
     uint32_t t1w[2][6], t2w[2][5];
 #pragma unroll
@@ -406,7 +372,6 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
     const int gimg = (dw_hi ? gs0 : gs0 >> 1) + dg;                                // this thread's group in the image row
     const bool edgeL = gimg == 0, edgeR = gimg == Gimg - 1;
     const float mL = edgeL ? 0.f : 1.f, mR = edgeR ? 0.f : 1.f;
-    const bool halfR = kOddW && !dw_hi && edgeR;                                   // the lo row's last group: 4 image pixels
     uint16_t* ybase = reinterpret_cast<uint16_t*>(dw_hi ? A.yh : A.yl) + ((size_t)n * Cd + dc) * dHd * dWd + 8 * gimg;
 
     for (int c = c0; c <= c1; ++c) {
@@ -487,8 +452,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
             const int glr = (g >> 1) - (gs0 >> 1) + hl, hf = g & 1;               // lo group in the lo tile row
             const uint32_t offM = (uint32_t)(glr * SL + cl_) * 16u + 8u * hf;
             const uint32_t offL = hf ? offM - 2u : (g == 0 ? offM : offM - (uint32_t)SL * 16u + 14u);
-            // (g == GH - 1 with hf == 0: an odd group count — the image's last lo pixel is this half's last, clamp there)
-            const uint32_t offR = hf ? (g == GH - 1 ? offM + 6u : offM + (uint32_t)SL * 16u - 8u) : (g == GH - 1 ? offM + 6u : offM + 8u);
+            const uint32_t offR = hf ? (g == GH - 1 ? offM + 6u : offM + (uint32_t)SL * 16u - 8u) : offM + 8u;
             float hrow[4][8];
             const uint16_t w25 = Pack<T>::bits(0.25f), w75 = Pack<T>::bits(0.75f);
 #pragma unroll
@@ -554,9 +518,8 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       if (warp == nwarps - 1 && lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         if (!kStem && c >= c0 + 1 && c + 1 <= c1) issue_hi(c + 1);       // stage of chunk c-1: its T1 was consumed
-        if (!kOddW && c + 2 <= cl1) issue_lo(c + 2);                     // stage of lo chunk c-1: last read by this chunk's up-sample
+        if (c + 2 <= cl1) issue_lo(c + 2);                               // stage of lo chunk c-1: last read by this chunk's up-sample
       }
-      if (kOddW && warp == nwarps - 1 && c + 2 <= cl1) issue_lo_cp(c + 2);
       if (lane == 0) {
         for (int b = warp; b < nbh + nbl; b += nwarps) {
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -601,11 +564,10 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
           n1[0] = lds32(edgeL ? ZERO : p - (uint32_t)Sd * 16u + 12u);
           n1[1] = m.x; n1[2] = m.y; n1[3] = m.z; n1[4] = m.w;
           n1[5] = lds32(edgeR ? ZERO : p + (uint32_t)Sd * 16u);
-          if (kOddW && halfR) { n1[3] = 0u; n1[4] = 0u; }               // T1 at pixels 4..7 of the half group: outside the image
           const int tr = r - 1, orow = r - 2;
           const bool make_t2 = tr >= 0 && tr >= out_lo - 1 && tr <= out_hi;
           const bool make_out = orow >= out_lo && orow < out_hi;
-          ils_dw_push<T, kOddW>(t1w, t2w, n1, w1, b1, s1, w2, b2, s2, make_t2, mL, mR, make_out, ybase + (size_t)orow * dWd, halfR, !dw_hi);
+          ils_dw_push<T>(t1w, t2w, n1, w1, b1, s1, w2, b2, s2, make_t2, mL, mR, make_out, ybase + (size_t)orow * dWd);
         }
       }
       ILS_MARK(6);
@@ -615,7 +577,7 @@ il_stream_kernel(const __grid_constant__ IlsArgs A, const __grid_constant__ CUte
       const uint32_t z[6] = {0u, 0u, 0u, 0u, 0u, 0u};
       for (int rr = 0; rr < 2; ++rr) {
         const int r = dHd + rr, tr = r - 1, orow = r - 2;
-        ils_dw_push<T, kOddW>(t1w, t2w, z, w1, b1, s1, w2, b2, s2, tr < dHd, mL, mR, orow >= out_lo, ybase + (size_t)orow * dWd, halfR, !dw_hi);
+        ils_dw_push<T>(t1w, t2w, z, w1, b1, s1, w2, b2, s2, tr < dHd, mL, mR, orow >= out_lo, ybase + (size_t)orow * dWd);
       }
     }
     __syncthreads();          // every shared-memory read of this piece is done before the next piece's loads overwrite it

@@ -194,7 +194,6 @@ struct csnet_plan {
   struct GraphSlot { cudaGraphExec_t exec = nullptr; void* in = nullptr; void* out = nullptr; size_t in_bytes = 0, out_bytes = 0; };
   std::vector<GraphSlot> graphs;                  // index = batch size
   cudaStream_t cap_stream = nullptr;
-  bool ils_odd = false;                           // CSNET_ILS_ODD=1: the odd-width form of il_stream (W = 8 mod 16)
   int graph_max_n = 8;                            // CSNET_GRAPH_MAX_N (0 disables)
   std::vector<char> op_msd;                       // per op: an MSBlock whose dilated paths run on ms_direct.cuh
   std::vector<char> op_ms;                        // per op: the streaming 1x1 MIX kernel (mix_stream.cuh) can run it
@@ -509,16 +508,12 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   A.Chi = stem ? Xh.C * 9 : Xh.C; A.Cli = stem ? 0 : Xl.C; A.Cho = Yh.C; A.Clo = op.dst2 >= 0 ? P.tensors[op.dst2].C : 0;
   A.Ci = stem ? Xh.C : 0;
   if (stem && (Xh.dtype != CSNET_F32 || A.Chi > 32 || A.W % 4)) return false;
-  // odd-width form (il_stream.cuh, kOddW): W = 8 (mod 16), e.g. the 56-wide stage 3 at 224 x 224 — one strip, the tile one group wider than the image
-  // Opt-in (CSNET_ILS_ODD=1): correct (tests/test_gpu_il_stream.py) but its 4-row x 56-px chunks are too small for the kernel's phase structure —
-  // the five stage-3 blocks take 0.93 ms instead of 1.10 ms per-op and the bs-256 step does not move (11.00 vs 10.98 ms).
-  const bool oddw = P.ils_odd && !stem && A.W % 16 == 8 && A.Cli > 0;
-  if ((A.W % 16 && !oddw) || A.H % 4 || A.Cho > csnet::kIlsMaxC || A.Clo > csnet::kIlsMaxC || A.Chi + A.Cli > 64) return false;
+  if (A.W % 16 || A.H % 4 || A.Cho > csnet::kIlsMaxC || A.Clo > csnet::kIlsMaxC || A.Chi + A.Cli > 64) return false;
   A.K8 = stem ? 32 : round_up(A.Chi + A.Cli, 8);                      // the compiler packs the stem's weights as [M16][32]
   A.K16 = round_up(A.Chi + A.Cli, 16);
   A.NH = round_up(A.Cho, 16);
   A.NL = A.Clo > 0 ? round_up(A.Clo, 16) : 0;
-  A.GH = A.W / 8; A.GL = (A.W / 2 + 7) / 8;
+  A.GH = A.W / 8; A.GL = A.W / 16;
   A.SH = (A.K16 > A.NH ? A.K16 : A.NH) + 1;            // odd: consecutive pixel groups start in different bank groups
   A.SL = A.Clo > 0 ? A.K16 + 1 : (A.Cli | 1);
   A.ST = A.NL + 1;
@@ -529,12 +524,11 @@ bool make_ils(const csnet_plan& P, const csnet_op_desc& op, csnet::IlsArgs* out)
   csnet::IlsArgs best{};
   for (int ns = 1; ns <= 16; ++ns) {
     if (P.ils_force_ns > 0 && ns != P.ils_force_ns) continue;
-    if (oddw ? ns != 1 : (A.GH % ns || (A.GH / ns) % 2)) continue;
+    if (A.GH % ns || (A.GH / ns) % 2) continue;
     csnet::IlsArgs T = A;
-    T.ns = ns; T.gsn = oddw ? A.GH + 1 : A.GH / ns; T.hl = ns > 1 ? 1 : 0;
+    T.ns = ns; T.gsn = A.GH / ns; T.hl = ns > 1 ? 1 : 0;
     T.GR = T.gsn + 2 * T.hl; T.GLR = T.gsn / 2 + 2 * T.hl;
-    T.tgh = oddw ? A.GH : T.gsn; T.tgl = oddw ? A.GL : T.gsn / 2;
-    T.dw_warps = (T.Cho * T.tgh + T.Clo * T.tgl + 31) / 32;              // tail tasks are packed: hi (channel, column)s, then lo ones
+    T.dw_warps = (T.Cho * T.gsn + T.Clo * (T.gsn / 2) + 31) / 32;        // tail tasks are packed: hi (channel, column)s, then lo ones
     if (T.dw_warps < 4) T.dw_warps = 4;                                   // the epilogue needs one warp per TMEM lane quarter
     const int warps = T.dw_warps;
     if (warps * 32 > csnet::kIlsMaxThreads || T.SH > 256 || T.SL > 256 || T.GR > 256) continue;
@@ -885,7 +879,6 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
   if (const char* e1 = getenv("CSNET_ILS")) P->ils_enabled = e1[0] != '0';
   if (const char* e3 = getenv("CSNET_ILS_NS")) P->ils_force_ns = atoi(e3);
   if (const char* e2 = getenv("CSNET_ILS_MIN_CHUNKS")) P->ils_min_chunks = atoi(e2);
-  if (const char* e7 = getenv("CSNET_ILS_ODD")) P->ils_odd = e7[0] == '1';
   int ils_smem_max = 0;
   for (size_t i = 0; i < P->ops.size(); ++i) {
     csnet::IlsArgs S;
@@ -898,7 +891,6 @@ int csnet_plan_create(csnet_plan** out, const csnet_tensor_desc* tensors, int32_
     e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     // two CTAs of <= 113 KB share an SM only with the full shared-memory carve-out
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(csnet::il_stream_kernel<__half, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1054,11 +1046,6 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
       if (!encode_image_map(&tmL, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Ci, A.H, A.W, A.BW, 4)) 
         return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock, image)");
       tmH = tmL;
-    } else if (A.W % 16) {                                   // odd-width form: the lo rows are not 16-byte multiples -> cp.async, no map
-      if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GR, 4))
-        return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock, odd width)");
-      tmL = tmH;
-      A.xl_in = reinterpret_cast<const uint16_t*>(P->tensor_ptr(op.paths[1].src, N, ext_ptrs));
     } else if (!encode_group_map(&tmH, P->tensor_ptr(op.paths[0].src, N, ext_ptrs), N, A.Chi, A.H, A.W, A.SH, A.GR, 4) ||
                !encode_group_map(&tmL, P->tensor_ptr(op.paths[1].src, N, ext_ptrs), N, A.Cli, A.H / 2, A.W / 2, A.SL, A.GLR, 2))
       return fail(CSNET_E_CUDA, "cuTensorMapEncodeTiled failed (streaming ILBlock)");
@@ -1068,8 +1055,7 @@ static int launch_op(csnet_plan* P, size_t i, int32_t N, const void* const* ext_
     static unsigned long long* dbg_buf = nullptr;
     if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(unsigned long long));
     A.dbg = dbg ? dbg_buf : nullptr;
-    if (A.W % 16) csnet::il_stream_kernel<__half, false, false, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
-    else if (stem) csnet::il_stream_kernel<__half, false, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
+    if (stem) csnet::il_stream_kernel<__half, false, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     else if (dbg) csnet::il_stream_kernel<__half, true><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     else csnet::il_stream_kernel<__half, false><<<grid, A.dw_warps * 32, A.smem_bytes, stream>>>(A, tmH, tmL);
     if (dbg && !stem) {        // debugging aid: mean cycles per phase over the CTAs (synchronises)

@@ -60,38 +60,6 @@ def test_streaming_kernel_one_block_at_a_time(tag, hw, nb, ns):
     assert ran >= 6
 
 
-@pytest.mark.parametrize("tag,hw,nb", [("csnet-L-x2", (224, 224), 3), ("csnet-L-x1", (224, 224), 2), ("csnet-L-x1", (128, 64), 2)])
-def test_streaming_kernel_odd_width_form(tag, hw, nb, monkeypatch):
-    """CSNET_ILS_ODD=1: the stage-3 blocks (56 wide at 224 x 224: seven pixel groups, a 28-wide lo branch copied by cp.async; 8 wide at
-    128 x 64: one group, half a lo group) one at a time on the streaming kernel against the generic ops."""
-    monkeypatch.setenv("CSNET_ILS_ODD", "1")
-    cfg, sd = fixtures.checkpoint(tag)
-    h, w = hw
-    x = torch.from_numpy(synth.randn_images(nb, h, w, 33)).cuda()
-    base = compiler.compile_csnet(cfg, sd, h, w, "fp16", reuse_arena=False, fuse=False, tensor_core=False)
-    p0 = _plan(base, nb, False)
-    p0.forward(x)
-    full = compiler.compile_csnet(cfg, sd, h, w, "fp16", fuse=True)
-    names = [o.name for o in full.ops if o.kind == 3 and o.name.startswith("stage3.")]
-    assert len(names) == 5
-    for name in names:
-        prog = compiler.compile_csnet(cfg, sd, h, w, "fp16", reuse_arena=False, fuse={name}, tensor_core=False)
-        p1 = _plan(prog, nb, True, 0, 0)
-        (i,) = [k for k, o in enumerate(prog.ops) if o.name == name]
-        assert "il_stream" in p1.op_kernel(i), p1.op_kernel(i)
-        p1.forward(x)
-        for b in (0, 1):
-            key = f"{name}/{b}"
-            if key not in prog.taps:
-                continue
-            ref, got = p0.read_tensor(base.taps[key], nb), p1.read_tensor(prog.taps[key], nb)
-            assert torch.isfinite(got).all(), key
-            err = (got - ref).abs().max().item()
-            assert err <= 4e-3 * max(1.0, ref.abs().max().item()), (key, err, ref.abs().max().item())
-        p1.close()
-    p0.close()
-
-
 def test_streaming_and_tiled_kernels_agree_on_the_whole_network():
     """Full fp16 program, batch 16 at 224x224: streaming kernel on (every qualifying block) vs off, and vs the oracle."""
     cfg, sd = fixtures.checkpoint("csnet-L-x2")
