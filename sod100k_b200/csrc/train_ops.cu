@@ -533,6 +533,12 @@ static bool fast_enabled() {
   return on;
 }
 
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+
 static int num_sms() {
   static int sms[kMaxDevices] = {0};
   int dev = 0;
@@ -586,7 +592,8 @@ static int launch_conv1x1(const tf::ConvArgs& F, cudaStream_t st) {
   A.wrows = rows;
   const size_t smem = (size_t)rows * A.Cpad * sizeof(float);
   if (smem > 96 * 1024) return kNotHandled;                // (not a CSNet shape) -> the generic kernel
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {false};                // function attributes are per device
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(tf::conv1x1_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(tf::conv1x1_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -599,7 +606,8 @@ static int launch_conv1x1(const tf::ConvArgs& F, cudaStream_t st) {
   // (18 -> 18 @224^2 0.494 -> 0.472 ms, 13 -> 18 0.415 -> 0.357 ms; 34 -> 31 @112^2 is 8 % slower with it).  CSNET_C1_NARROW=0 / 1 forces.
   static const int narrow_env = [] { const char* e = getenv("CSNET_C1_NARROW"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
   const bool narrow = narrow_env >= 0 ? narrow_env == 1 : A.C <= 24;
-  static bool attr_n = false;
+  static bool attr_n_dev[kMaxDevices] = {false};
+  bool& attr_n = attr_n_dev[current_device()];
   if (narrow && !attr_n) { cudaFuncSetAttribute(tf::conv1x1_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024); attr_n = true; }
   if (narrow && px == 4 && A.vec && smem <= 72 * 1024) tf::conv1x1_narrow_kernel<<<blocks, tf::kT, smem, st>>>(A);
   else if (px == 2) tf::conv1x1_kernel<2, true><<<blocks, tf::kT, smem, st>>>(A);
@@ -626,7 +634,8 @@ static int launch_conv(tf::ConvArgs& A, cudaStream_t st) {
   const size_t smem = (tile + wsm) * sizeof(float);
   const int bands = (A.H + A.R - 1) / A.R;
   const unsigned grid = (unsigned)(((A.N + A.ipb - 1) / A.ipb) * bands);
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {false};
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     cudaFuncSetAttribute(tf::conv_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
     cudaFuncSetAttribute(tf::conv_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
@@ -839,7 +848,8 @@ int csnet_train_mix_wgrad(const float* ddst, int32_t N, int32_t C, int32_t H, in
       float* part = nullptr;
       if (int rc = partial_workspace((size_t)gx * nel, (cudaStream_t)stream, &part)) return rc;
       G.part = part;
-      static bool attr = false;
+      static bool attr_dev[kMaxDevices] = {false};
+      bool& attr = attr_dev[current_device()];
       if (!attr) {
         cudaFuncSetAttribute(tf::conv_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
         cudaFuncSetAttribute(tf::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemMax);
