@@ -262,6 +262,11 @@ int csnet_train_pool_fwd(const float* src, int32_t N, int32_t Cs, int32_t c0, in
                          float* dst, uint8_t* idx, void* stream);
 int csnet_train_pool_bwd(const float* dpool, const uint8_t* idx, int32_t N, int32_t cin, int32_t Hs, int32_t Ws, int32_t pre_avg, int32_t pool,
                          float* dsrc, void* stream);
+/* Channel slimming on the device (build_model_with_weight and its loaders, CSNet_training/model/csnet.py:571-818):
+ * dst[i][j][:] = src[out_idx[i]][in_idx[j]][:] for i < n_out, j < n_in; src is [Co][Ci][kk] fp32, dst [dCo][dCi][kk] (the caller zeroes it:
+ * the reference fills torch.zeros), the index lists are device int64 (torch.nonzero of the BatchNorm-gamma masks). */
+int csnet_slim_gather(const float* src, int32_t Co, int32_t Ci, int32_t kk, const int64_t* out_idx, int32_t n_out, const int64_t* in_idx, int32_t n_in,
+                      float* dst, int32_t dCo, int32_t dCi, void* stream);
 /* F.binary_cross_entropy_with_logits (mean) and its gradient * grad_scale (train.py:209). */
 int csnet_train_bce(const float* logits, const float* target, float* dlogits, float* loss, int64_t n, float grad_scale, void* stream);
 /* torch.optim.Adam step (train.py:108-123) over many tensors: `chunk_table_device` = n_chunks records

@@ -423,6 +423,18 @@ __global__ void __launch_bounds__(kT) adam_kernel(const AdamChunk* chunks, float
   }
 }
 
+// Channel slimming (CSNet_training/model/csnet.py:571-760): dst[i][j][:] = src[out_idx[i]][in_idx[j]][:] for the surviving channels,
+// dst [dCo][dCi][kk] (zero elsewhere, set by the caller), src [Co][Ci][kk]; indices outside the source are skipped.
+__global__ void __launch_bounds__(kT) slim_gather_kernel(const float* __restrict__ src, int Co, int Ci, int kk, const long long* __restrict__ oi, int no,
+                                                         const long long* __restrict__ ii, int ni, float* __restrict__ dst, int dCi) {
+  const long long e = (long long)blockIdx.x * kT + threadIdx.x, total = (long long)no * ni * kk;
+  if (e >= total) return;
+  const int t = (int)(e % kk), j = (int)((e / kk) % ni), i = (int)(e / ((long long)kk * ni));
+  const long long so = oi[i], si = ii[j];
+  if (so < 0 || so >= Co || si < 0 || si >= Ci) return;
+  dst[((long long)i * dCi + j) * kk + t] = src[(so * Ci + si) * kk + t];
+}
+
 thread_local std::string t_err;
 int tfail(int code, const char* what, cudaError_t e) {
   t_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -894,6 +906,20 @@ int csnet_train_pool_bwd(const float* dpool, const uint8_t* idx, int32_t N, int3
   if (total == 0) return CSNET_OK;
   if (Ws % 4 == 0 && total < (1ull << 32)) tf::pool_bwd4_kernel<<<(unsigned)((total / 4 + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
   else tf::pool_bwd_kernel<<<(unsigned)((total + tf::kT - 1) / tf::kT), tf::kT, 0, (cudaStream_t)stream>>>(dpool, idx, N, cin, Hs, Ws, pre_avg, pool, dsrc);
+  TR_CHECK(cudaGetLastError());
+  return CSNET_OK;
+}
+
+int csnet_slim_gather(const float* src, int32_t Co, int32_t Ci, int32_t kk, const int64_t* out_idx, int32_t n_out, const int64_t* in_idx, int32_t n_in,
+                      float* dst, int32_t dCo, int32_t dCi, void* stream) {
+  if (!src || !dst || Co <= 0 || Ci <= 0 || kk <= 0 || n_out < 0 || n_in < 0 || n_out > dCo || n_in > dCi || (n_out > 0 && !out_idx) || (n_in > 0 && !in_idx)) {
+    t_err = "csnet_slim_gather: bad arguments";
+    return CSNET_E_INVALID;
+  }
+  const long long total = (long long)n_out * n_in * kk;
+  if (total == 0) return CSNET_OK;
+  slim_gather_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, (cudaStream_t)stream>>>(src, Co, Ci, kk, reinterpret_cast<const long long*>(out_idx), n_out,
+                                                                                      reinterpret_cast<const long long*>(in_idx), n_in, dst, dCi);
   TR_CHECK(cudaGetLastError());
   return CSNET_OK;
 }

@@ -330,12 +330,32 @@ def save_layer_config(layer_config, save_path, epoch, latest=False, finetune=Fal
     print("Saved in:", os.path.join(save_path, name))
 
 
-def build_model(epoch=0, predefine="", basic_split=(1,), save_path="tmp", expand=1.0, **_unused):
-    """Reference build_model (csnet.py:571-597): load the pruned layer_config pickle if `predefine` exists,
-    else the un-pruned config of base width 20 (x expand when > 1)."""
+def build_model(epoch=0, predefine="", basic_split=(1,), save_path="tmp", model=None, expand=1.0, load_weight="NO",
+                finetune_thres="1e-20", finetune=False):
+    """Reference build_model (CSNet/model/csnet.py:571-597; the training variant CSNet_training/model/csnet.py:885-948 adds the
+    slimming arguments): load the pruned layer_config pickle if `predefine` exists, else the un-pruned config of base width 20
+    (x expand when > 1).  finetune=True slims `model` against the config in `predefine`: BatchNorm channels with
+    |gamma| < finetune_thres are dropped (`slim.finetune_config`, on the model's device), the new config is saved like the reference
+    saves it, and with load_weight='FINETUNE' (epoch != 0) the surviving weights are gather-copied into the new model
+    (`slim.build_model_with_weight`); otherwise the new model is freshly initialised."""
     width = int(round(20 * expand)) if expand > 1 else 20
-    if os.path.isfile(predefine):
+    masks = None
+    if finetune:
+        from .. import slim
+
+        layer_config, masks = slim.finetune_config(model, load_layer_config(predefine), finetune_thres)
+        save_layer_config(layer_config, save_path, epoch, finetune=True)
+    elif os.path.isfile(predefine):
         layer_config = load_layer_config(predefine)
-    else:
+    elif epoch == 0:
         layer_config = init_layers(width, basic_split)
-    return CSNet(layer_config=layer_config)
+    else:
+        raise NotImplementedError("redefine_model (re-growing a pruned model towards a target width, CSNet_training/model/csnet.py:414-517) is "
+                                  "outside the accelerated path; pass predefine= or finetune=True")
+    if masks is None or load_weight == "NO":
+        return CSNet(layer_config=layer_config)
+    if load_weight == "FINETUNE" and epoch != 0:
+        from .. import slim
+
+        return slim.build_model_with_weight(layer_config, model, masks)
+    raise ValueError(f"load_weight={load_weight!r} with epoch={epoch}: the reference leaves the new model undefined here")
