@@ -350,8 +350,8 @@ def build_model(epoch=0, predefine="", basic_split=(1,), save_path="tmp", model=
     elif epoch == 0:
         layer_config = init_layers(width, basic_split)
     else:
-        raise NotImplementedError("redefine_model (re-growing a pruned model towards a target width, CSNet_training/model/csnet.py:414-517) is "
-                                  "outside the accelerated path; pass predefine= or finetune=True")
+        raise NotImplementedError("epoch != 0 without predefine / finetune: the reference calls redefine_model here (CSNet_training/model/csnet.py:918), "
+                                  "a function it defines nowhere; pass predefine= or finetune=True")
     if masks is None or load_weight == "NO":
         return CSNet(layer_config=layer_config)
     if load_weight == "FINETUNE" and epoch != 0:
