@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op time table to stderr")
     ap.add_argument("--train-batch", type=int, default=256, help="images per GPU of the `train` sub-record's step")
+    ap.add_argument("--train-recompute", action="store_true",
+                    help="train sub-record with ILBlock-granular recompute (Trainer(recompute=True)): ~3x less activation memory, one extra forward")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the train sub-record, the eager-GPU baseline and the extra configs (profiling runs)")
     return ap.parse_args()
@@ -272,7 +274,7 @@ def train_record(a, world, rank, local, dev, steps=5, warmup=3):
 
     model, cfg, _ = checkpoints.build_from_npz(a.model)
     model.cuda(local)
-    tr = Trainer(model, lr=1e-4, weight_decay=5e-3)
+    tr = Trainer(model, lr=1e-4, weight_decay=5e-3, recompute=a.train_recompute)
     B, S = a.train_batch, a.size
     xh = torch.from_numpy(synth.randn_images(B, S, S, 1234 + rank)).pin_memory()
     th = torch.from_numpy(synth.random_masks(B, S, S, 1236 + rank)).pin_memory()
@@ -320,10 +322,12 @@ def train_record(a, world, rank, local, dev, steps=5, warmup=3):
     peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
     ips, ips_e2e = B * world * steps / (ms * 1e-3), B * world * steps / (ms_e2e * 1e-3)
     bucket_bytes = int(tr.flat.bucket.numel() * 4)
+    peak_gib = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     del tr, model
     torch.cuda.empty_cache()
     return {"metric": "images/sec CSNet fwd+BCE+bwd+allreduce+Adam 224x224", "value": ips, "unit": UNIT, "ms_per_step": ms / steps,
             "steps": steps, "warmup": warmup, "per_gpu_batch": B, "global_batch": B * world, "ranks": world, "dtype": "fp32",
+            "recompute": bool(a.train_recompute), "peak_memory_GiB": round(peak_gib, 2),
             "collective": "one NCCL all-reduce (sum / world) of the flat fp32 gradient bucket per step" if world > 1 else
                           "none at 1 GPU (the flat gradient bucket is all-reduced when ranks > 1)",
             "allreduce_bytes": bucket_bytes, "gpu_launches": launches,
@@ -406,7 +410,7 @@ def run_ours(a):
         per_op = [min(u, v) for u, v in zip(per_op, plan.profile(B, [x_dev.data_ptr(), torch.empty_like(y_host, device=dev).data_ptr()], stream.cuda_stream))]
 
     # train step with the gradient all-reduce: every rank takes part (the one collective of the design)
-    train = None
+    train = train_c3 = None
     if not a.no_extras:
         del x_dev
         torch.cuda.empty_cache()
@@ -414,6 +418,16 @@ def run_ours(a):
             train = train_record(a, world, rank, local, dev)
         except Exception as e:
             train = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        # SURVEY config c3's batch (1024 / GPU) on one GPU: ILBlock-granular recompute, fp32 storage (bf16 storage is not built)
+        try:
+            import copy
+            a3 = copy.copy(a)
+            a3.train_batch, a3.train_recompute = 1024, True
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+            train_c3 = train_record(a3, world, rank, local, dev, steps=3, warmup=2)
+        except Exception as e:
+            train_c3 = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -481,6 +495,7 @@ def run_ours(a):
     }
     if not a.no_extras:
         out["train"] = train
+        out["train_c3_batch"] = train_c3
         del plan, eng, model
         torch.cuda.empty_cache()
         out["gpu_eager_baseline"] = gpu_eager_baseline(a, dev)

@@ -34,6 +34,7 @@ md = f'''# r02-g — final state of round 2 (one B200, csnet-L-x2, 224x224)
 | `gpu_eager_baseline` (the reference's ATen / cuDNN calls, same GPU, bs 256) | fp32 {d["gpu_eager_baseline"]["fp32"]["value"]:.0f} img/s, autocast fp16 {d["gpu_eager_baseline"]["autocast_fp16"]["value"]:.0f} img/s |
 | `cpu_baseline` (oracle port, {d["cpu_baseline"]["cores"]} host cores) | {d["cpu_baseline"]["value"]:.1f} img/s |
 | `train` — fwd + BCE + bwd + Adam, fp32, bs {d["train"]["per_gpu_batch"]} | **{d["train"]["value"]:.0f} img/s** ({d["train"]["ms_per_step"]:.1f} ms, {d["train"]["gpu_launches"] // d["train"]["steps"]} launches / step), e2e from pinned host batches {d["train"]["e2e"]["value"]:.0f}; {100 * d["train"]["roofline"]["frac"]:.1f} % of the module-fused fp32 roofline (426 MB / image) |
+| `train_c3_batch` — the same step at SURVEY config c3's batch, 1024 images on ONE GPU, ILBlock-granular recompute (`Trainer(recompute=True)`), fp32 | {d["train_c3_batch"]["value"]:.0f} img/s ({d["train_c3_batch"]["ms_per_step"]:.0f} ms / step), peak memory {d["train_c3_batch"]["peak_memory_GiB"]:.1f} GiB (plain step at bs 256: {d["train"]["peak_memory_GiB"]:.1f} GiB), e2e {d["train_c3_batch"]["e2e"]["value"]:.0f} |
 | 2 GPUs (`torchrun`, weak scaling) | inference {d2["value"]:.0f} img/s, e2e {d2["e2e"]["value"]:.0f}; train {d2["train"]["value"]:.0f} img/s with the NCCL all-reduce of the 563 576-byte bucket |
 '''
 for c in d["configs"]:

@@ -9,6 +9,7 @@ dev = torch.device("cuda", 0)
 S = 224
 batches = [int(b) for b in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["32", "128"])]
 prof = len(sys.argv) > 2 and sys.argv[2] == "prof"
+recompute = "recompute" in sys.argv[2:]
 
 def timed(fn, k):
     torch.cuda.synchronize()
@@ -21,13 +22,18 @@ def timed(fn, k):
 for B in batches:
     model, cfg, _ = checkpoints.build_from_npz("csnet-L-x2")
     model.cuda(0)
-    tr = Trainer(model, lr=1e-4, weight_decay=5e-3)
+    tr = Trainer(model, lr=1e-4, weight_decay=5e-3, recompute=recompute)
     x = torch.from_numpy(synth.randn_images(B, S, S, 1234)).to(dev)
     t = torch.from_numpy(synth.random_masks(B, S, S, 1236)).to(dev)
     for _ in range(3): tr.step(x, t)
     ms, wall = timed(lambda: tr.step(x, t), 5)
     mem = torch.cuda.max_memory_allocated() / 2**30
-    rec = {"batch": B, "eager_ms": ms, "eager_img_s": B / ms * 1e3, "max_mem_GiB": mem}
+    rec = {"batch": B, "recompute": recompute, "eager_ms": ms, "eager_img_s": B / ms * 1e3, "max_mem_GiB": mem}
+    if recompute:
+        print(json.dumps(rec), flush=True)
+        del tr, model, x, t
+        torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
+        continue
     if prof:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as p:

@@ -39,7 +39,9 @@ def _flops_term(module, gaps, bns):
         wts.append(f)
         f /= module.expandflop
     terms = [(wts[b] * gaps[b].abs() * torch.pow(bns[b].weight, 2)).sum() for b in range(branches) if gaps[b] is not None]
-    module.all_flops = module.all_flops + 0.5 * sum(terms)
+    val = 0.5 * sum(terms)
+    if not T.RECOMPUTING:            # (a checkpointed re-run repeats the same autograd ops — it must save the same tensors — but not the side effect)
+        module.all_flops = module.all_flops + val
 
 
 def goct_conv_raw(conv, xs: List[Optional[torch.Tensor]], alpha_in, alpha_out, ksize: int, stride: int):
@@ -152,9 +154,17 @@ def csnet_forward(model, x):
     if x.shape[2] % 16 or x.shape[3] % 16:
         raise ValueError(f"input size {tuple(x.shape[2:])} must be a multiple of 16")
     feats, cur = {}, [x.float()]
+    # recompute mode (Trainer(recompute=True) / model.recompute = True): an ILBlock keeps only its inputs; its six modules' saved tensors
+    # (conv outputs, BN inputs, pooled copies) are rebuilt block by block in the backward pass — ~3.4x less activation memory for one
+    # extra forward, which is what lets batch 1024 at 224 x 224 train on one 180 GB GPU in fp32 (SURVEY config c3's batch)
+    ckpt = bool(getattr(model, "recompute", False)) and torch.is_grad_enabled()
+    if ckpt:
+        import contextlib
+        from torch.utils.checkpoint import checkpoint
+        ctx = lambda: (contextlib.nullcontext(), T.recomputing())
     for s in range(5):
         for blk in getattr(model, f"stage{s}"):
-            cur = blk(cur)
+            cur = checkpoint(blk, cur, use_reentrant=False, context_fn=ctx) if ckpt else blk(cur)
         feats[s] = cur
     fuse = model.oct_fuse([feats[2][0], feats[3][0], feats[4][0]])
     cls = model.cls_layer

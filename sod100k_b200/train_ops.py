@@ -50,6 +50,21 @@ def lib():
     return _lib
 
 
+# True while a checkpointed ILBlock is being re-run in the backward pass (modular.csnet_forward with recompute): the second run must
+# not update BatchNorm running statistics or the dynamic-weight-decay accumulator again
+RECOMPUTING = False
+
+
+class recomputing:
+    def __enter__(self):
+        global RECOMPUTING
+        self._old, RECOMPUTING = RECOMPUTING, True
+
+    def __exit__(self, *exc):
+        global RECOMPUTING
+        RECOMPUTING = self._old
+
+
 # kernels launched through this module since import (bench.py reports the count of a timed region): kernels per entry point
 LAUNCHES = 0
 _KERNELS = {"csnet_train_bn_prelu_bwd": 2, "csnet_train_mix_wgrad": 2, "csnet_train_dw_wgrad": 2, "csnet_train_dw_bwd": 2}
@@ -223,7 +238,7 @@ def bn_prelu_train(z, bn: torch.nn.BatchNorm2d, prelu: torch.nn.PReLU):
         y, _, _, gap = BnPreluFn.apply(z, bn.weight, bn.bias, prelu.weight, bn.running_mean, bn.running_var)
         return y, gap
     y, mean, var, gap = BnPreluFn.apply(z, bn.weight, bn.bias, prelu.weight)
-    if bn.track_running_stats:
+    if bn.track_running_stats and not RECOMPUTING:
         with torch.no_grad():
             m = z.shape[0] * z.shape[2] * z.shape[3]
             mom = 0.1 if bn.momentum is None else bn.momentum

@@ -292,3 +292,24 @@ def test_host_fed_step_equals_device_step():
     assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(outs[0][0], outs[1][0]))
     for k, v in outs[0][1].items():
         assert torch.equal(v, outs[1][1][k]), k
+
+
+def test_recompute_mode_is_bit_identical_and_smaller():
+    """Trainer(recompute=True): every ILBlock is checkpointed (only its inputs are kept, its modules re-run in the backward pass).  Same
+    kernels in the same order on the same values: losses, parameters and BatchNorm running statistics after two steps with the
+    dynamic-weight-decay term must be bit-identical to the plain step; peak activation memory must drop."""
+    res = []
+    for rc in (False, True):
+        m, cfg, params, buffers, x, t = _setup("csnet-L-x2", 4, (96, 128), 71)
+        tr = Trainer(m, lr=1e-3, weight_decay=5e-3, flops_weight=3.0, flops_expand=1.0, recompute=rc)
+        xt, tt = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+        torch.cuda.synchronize(); torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        losses = [float(tr.step(xt, tt)) for _ in range(2)]
+        torch.cuda.synchronize()
+        res.append((losses, {k: v.detach().clone() for k, v in m.state_dict().items()}, torch.cuda.max_memory_allocated() - base))
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(res[0][0], res[1][0]))
+    for k, v in res[0][1].items():
+        assert torch.equal(v, res[1][1][k]), k
+    print("peak activation bytes, plain vs recompute:", res[0][2], res[1][2])
+    assert res[1][2] < 0.6 * res[0][2], (res[0][2], res[1][2])
