@@ -8,11 +8,17 @@
 // roofline of these kernels, so each thread owns a 4 px x 16 channel (forward / dgrad) or 4 x 4 (x 3 taps) (wgrad) register tile
 // and reads its operands from shared memory as 16-byte vectors.
 //
-//   conv_fwd_kernel<KS>   dst = sum over conv paths (K-concatenated in the loop) + bilinear resample-add paths; with `transposed` it
-//                         is the data gradient of one path (weights read as [co][flipped tap][ci] while staging).
+//   conv1x1_kernel<PX, VEC> / conv1x1_narrow_kernel   every 1x1 mix and its data gradient: inputs global -> registers (each input element is
+//                         needed by exactly one thread), weights in shared memory, several channels of loads issued ahead of their FMAs.
+//   conv_fwd_kernel<KS>   3x3 (KS = 3, dil 1) and dilated (KS = 0) mixes: dst = sum over conv paths (K-concatenated in the loop) + bilinear
+//                         resample-add paths; with `transposed` the data gradient of one path (weights read as [co][flipped tap][ci]
+//                         while staging); input tile with halo staged by cp.async.
 //   conv_wgrad_kernel<KS> dw[ci][tap][co] = sum_{n,y,x} in[n][ci][y+ky-1][x+kx-1] * ddst[n][co][y][x]: per-block partials over a
-//                         share of the (image, row band) units, merged IN ORDER by reduce_partials_kernel (no atomics).
-//   dw3_kernel / dw3_wgrad_kernel   depthwise 3x3 (Conv2dX100 groups=C), a 4-pixel column strip per thread sliding down the rows.
+//                         share of the (image, row band) units, two cp.async stages in flight, interleaved 4 x 4 thread tiles on a
+//                         bank-conflict-free channel pitch, merged IN ORDER by reduce_partials_kernel (no atomics).
+//   dw3_kernel / dw3_bwd_kernel (dw3_wgrad_kernel)   depthwise 3x3 (Conv2dX100 groups=C): a 4-pixel column strip per thread sliding down
+//                         the rows; the backward produces dx and the dw partials in one pass over dy.
+//   pool_fwd / pool2_fwd / pool_bwd(4), resample_bwd_kernel<UP>   the pooling a path carries (with arg-max) and the bilinear adjoint.
 #pragma once
 #include <cuda_runtime.h>
 
